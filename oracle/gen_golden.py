@@ -1,0 +1,142 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (kaiidams/voice100).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.npz
+
+The reference imports from /root/reference; `pytorch_lightning` (not installable here) is
+replaced by the stand-in in oracle/_shim.  Weights come from voice100_b200.synth (numpy PCG64,
+reproducible anywhere) and are loaded with the reference's own `load_state_dict`; every
+BatchNorm then gets data-calibrated running statistics from one training-mode forward with
+momentum=1 so that BN folding is genuinely exercised.  The fixtures store the calibrated BN
+statistics and the reference OUTPUTS; inputs and all other weights are regenerated from seeds.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from voice100_b200 import synth
+
+from voice100.data_modules import (BLANK_AUDIO, MelSpectrogramAudioTransform,  # noqa: E402
+                                   generate_audio_text_batch)
+from voice100.models.asr import AudioToTextCTC  # noqa: E402
+from voice100.models.tts import AlignTextToAudioModel, TextToAlignTextModel  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+torch.set_num_threads(4)
+
+
+def load(model, sd_np):
+    sd = {k: torch.from_numpy(v) for k, v in sd_np.items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    # criterion / augmentation buffers are not part of the inference path
+    assert all(m.startswith(("criterion", "batch_augment")) for m in missing), missing
+
+
+def calibrate(model, *inputs):
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm1d)]
+    for m in bns:
+        m.momentum = 1.0
+    model.train()
+    with torch.no_grad():
+        model(*inputs)
+    model.eval()
+    out = {}
+    for k, v in model.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            out["bn/" + k] = v.numpy().copy()
+    return out
+
+
+def gen_logmel():
+    tr = MelSpectrogramAudioTransform()
+    w_noise = torch.from_numpy(synth.noise_waveform(1, 16000, seed=11))[0]
+    w_harm = torch.from_numpy(synth.harmonic_waveform(1, 12345, seed=12))[0]
+    w_short = torch.from_numpy(synth.noise_waveform(1, 400, seed=13))[0]
+    feats = []
+    with torch.no_grad():
+        for w in (w_noise, w_harm, w_short):
+            # voice100/data_modules.py:290-291 (file load + resample at :288-289 are out of scope)
+            feats.append(torch.log(tr.melspec(w).T + tr.log_offset))
+        mel_power = tr.melspec(w_harm)
+    (audio, audio_len), _ = generate_audio_text_batch([(f, torch.zeros(1, dtype=torch.long)) for f in feats])
+    np.savez_compressed(
+        os.path.join(OUT, "logmel.npz"),
+        noise_16000=feats[0].numpy(), harm_12345=feats[1].numpy(), noise_400=feats[2].numpy(),
+        harm_12345_melpower=mel_power.numpy(),
+        batch_audio=audio.numpy(), batch_audio_len=audio_len.numpy(),
+        blank_audio=np.float64(BLANK_AUDIO), audio_size=np.int64(tr.audio_size))
+    print("logmel", [tuple(f.shape) for f in feats], tuple(audio.shape))
+
+
+def gen_asr(name, hidden, embed, vocab, batch, samples, lengths=None, seed=21):
+    tr = MelSpectrogramAudioTransform()
+    wav = torch.from_numpy(synth.noise_waveform(batch, samples, seed=seed))
+    if lengths is None:
+        lengths = [samples] * batch
+    with torch.no_grad():
+        feats = [torch.log(tr.melspec(wav[i, :n]).T + tr.log_offset) for i, n in enumerate(lengths)]
+    (audio, audio_len), _ = generate_audio_text_batch([(f, torch.zeros(1, dtype=torch.long)) for f in feats])
+    model = AudioToTextCTC(audio_size=64, embed_size=embed, vocab_size=vocab, hidden_size=hidden,
+                           learning_rate=1e-3, weight_decay=0.0)
+    load(model, synth.asr_state_dict(64, embed, vocab, hidden, seed=seed, randomize_bn=True))
+    bn = calibrate(model, audio)
+    with torch.no_grad():
+        logits = model(audio)
+        out_len = model.output_length(audio_len)
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), logits=logits.numpy(), tokens=logits.argmax(-1).numpy(),
+        audio_len=audio_len.numpy(), out_len=out_len.numpy(), lengths=np.asarray(lengths, np.int32),
+        cfg=np.asarray([64, embed, vocab, hidden, batch, samples, seed], np.int64), **bn)
+    print(name, tuple(logits.shape), "logit std %.4f" % float(logits.std()),
+          "enc params", sum(p.numel() for p in model.encoder.parameters()),
+          "dec params", sum(p.numel() for p in model.decoder.parameters()))
+
+
+def gen_tts(seed=31):
+    B, L, H, V = 2, 24, 512, 29
+    text = torch.from_numpy(synth.text_tokens(B, L, V, seed=seed))
+    amodel = TextToAlignTextModel(vocab_size=V, hidden_size=H, learning_rate=1e-3)
+    load(amodel, synth.align_state_dict(V, H, seed=seed, randomize_bn=True))
+    bn_a = calibrate(amodel, text)
+    with torch.no_grad():
+        pred = amodel(text)
+    # host alignment on the seeded synthetic alignment (random-init preds can be negative)
+    align = synth.synthetic_alignment(B, L, seed=seed)
+    ats = [amodel.align(text[i], torch.from_numpy(align[i])) for i in range(B)]
+    aligntext = torch.nn.utils.rnn.pad_sequence(ats, batch_first=True, padding_value=0)
+    vmodel = AlignTextToAudioModel(vocab_size=V, hidden_size=H, learning_rate=1e-3)
+    load(vmodel, synth.audio_state_dict(V, H, seed=seed, randomize_bn=True, randomize_norm=True))
+    bn_v = calibrate(vmodel, aligntext)
+    with torch.no_grad():
+        hasf0, f0_hat, logspc_hat, codeap_hat = vmodel(aligntext)
+        f0, logspc, codeap = vmodel.predict(aligntext)
+    np.savez_compressed(
+        os.path.join(OUT, "tts_en_base.npz"),
+        align_pred=pred.numpy(), aligntext=aligntext.numpy(),
+        aligntext_len=np.asarray([len(a) for a in ats], np.int32),
+        hasf0_logits=hasf0.numpy(), f0_hat=f0_hat.numpy(), f0=f0.numpy(), logspc=logspc.numpy(),
+        codeap=codeap.numpy(), cfg=np.asarray([V, H, B, L, seed], np.int64),
+        **{"a/" + k: v for k, v in bn_a.items()}, **{"v/" + k: v for k, v in bn_v.items()})
+    print("tts", tuple(pred.shape), tuple(aligntext.shape), tuple(logspc.shape),
+          "align params", sum(p.numel() for p in amodel.layers.parameters()),
+          "audio dec params", sum(p.numel() for p in vmodel.decoder.parameters()),
+          "voiced frac %.2f" % float((hasf0 >= 0).float().mean()))
+
+
+if __name__ == "__main__":
+    gen_logmel()
+    gen_asr("asr_en_small", hidden=256, embed=256, vocab=29, batch=2, samples=32000)
+    gen_asr("asr_ja_phone_ragged", hidden=128, embed=128, vocab=44, batch=3, samples=24000,
+            lengths=[9000, 17777, 24000], seed=22)
+    gen_tts()

@@ -1,0 +1,334 @@
+"""CPU oracle for the Voice100 batched-inference hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file restates, on the CPU in fp32, the arithmetic of the reference path named in
+BASELINE.json:north_star.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import it; the product package `voice100_b200` never does (it
+fails loudly when the CUDA library is missing -- there is no CPU fallback).
+
+Where the reference's arithmetic lives
+--------------------------------------
+* The reference is pure Python; its conv / batch-norm / ReLU6 / transposed-conv / embedding
+  arithmetic is `torch` (pinned torch 1.13.1, poetry.lock:1755-1756; this image has 2.11.0) and
+  its STFT + mel arithmetic is `torchaudio.transforms.MelSpectrogram` (pinned torchaudio 0.13.1,
+  poetry.lock:1796-1797; this image has 2.11.0).  Neither is vendored under /root/reference.
+  The functions below restate the published algorithms with `torch.nn.functional` primitives
+  (the same ATen kernels the reference dispatches to on CPU) and, for the front end, with an
+  explicit reflect-pad -> frame -> Hann -> rFFT -> |.|^2 -> mel -> log pipeline plus an
+  independent numpy version (`logmel_numpy`).
+* Nothing here is a module tree copied from the reference: the network is evaluated
+  functionally from a flat `state_dict` (reference key layout, see voice100_b200/synth.py).
+
+Pinning
+-------
+The reference's own tests pin NO numeric result on this path, so the
+oracle is pinned against outputs of the UNMODIFIED reference modules run in the build
+container: oracle/gen_golden.py imports /root/reference (with the pytorch_lightning stand-in
+in oracle/_shim), runs them on seeded inputs and writes tests/golden/*.npz;
+tests/test_oracle_golden.py checks every function here against those vectors.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# voice100/data_modules.py:23-26
+MELSPEC_DIM = 64
+LOG_OFFSET = 1e-6
+BLANK_AUDIO = math.log(LOG_OFFSET)  # -13.815510557964274
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by voice100/models/asr.py:36,52
+
+SD = Dict[str, torch.Tensor]
+
+
+def to_torch_sd(sd) -> SD:
+    return {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------------------------
+# Front end: voice100/data_modules.py:262-292 (MelSpectrogramAudioTransform), arithmetic from
+# torchaudio.transforms.MelSpectrogram(sample_rate=16000, n_fft=512, win_length=400,
+# hop_length=160, n_mels=64) with torchaudio defaults f_min=0, f_max=sr/2, power=2, center=True,
+# pad_mode="reflect", window=hann(periodic), norm=None, mel_scale="htk".
+# ----------------------------------------------------------------------------------------------
+
+def mel_filterbank(sample_rate=16000, n_fft=512, n_mels=MELSPEC_DIM, f_min=0.0, f_max=None) -> torch.Tensor:
+    """torchaudio.functional.melscale_fbanks (htk, norm=None): fb[n_freqs, n_mels], fp32."""
+    f_max = float(sample_rate // 2) if f_max is None else f_max
+    n_freqs = n_fft // 2 + 1
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_min = 2595.0 * math.log10(1.0 + f_min / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + f_max / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def mel_power(waveform: torch.Tensor, sample_rate=16000, n_fft=512, win_length=400, hop_length=160,
+              n_mels=MELSPEC_DIM) -> torch.Tensor:
+    """`MelSpectrogramAudioTransform.melspec(waveform[..., L]) -> [..., n_mels, 1 + L//hop]`
+    (voice100/data_modules.py:276-281,290).  Same call sequence as torchaudio's
+    Spectrogram/MelScale (functional.spectrogram -> torch.stft(center, reflect) -> |.|^2 ->
+    matmul(spec^T, fb)^T), so it is bit-identical to the reference on the same host."""
+    x = waveform.to(torch.float32)
+    lead = x.shape[:-1]
+    x = x.reshape(-1, x.shape[-1])
+    spec = torch.stft(x, n_fft=n_fft, hop_length=hop_length, win_length=win_length,
+                      window=torch.hann_window(win_length, periodic=True), center=True,
+                      pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+    power = spec.abs().pow(2.0)                                    # [N, n_fft/2+1, T]
+    mel = torch.matmul(power.transpose(-1, -2), mel_filterbank(sample_rate, n_fft, n_mels)).transpose(-1, -2)
+    return mel.reshape(*lead, n_mels, -1)
+
+
+def mel_power_explicit(waveform: torch.Tensor, sample_rate=16000, n_fft=512, win_length=400,
+                       hop_length=160, n_mels=MELSPEC_DIM) -> torch.Tensor:
+    """The same transform spelled out step by step (what the CUDA kernel implements): frame t
+    covers reflect-padded samples [hop*t, hop*t + n_fft); the periodic Hann(win_length) window
+    sits centred in the frame (taps 56..455 for 400/512).  Differs from `mel_power` only by fp32
+    FFT round-off (~1e-7 of the frame's peak power)."""
+    x = waveform.to(torch.float32)
+    lead = x.shape[:-1]
+    x = x.reshape(-1, x.shape[-1])
+    pad = n_fft // 2
+    xp = F.pad(x.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)
+    frames = xp.unfold(-1, n_fft, hop_length)                      # [N, T, n_fft]
+    left = (n_fft - win_length) // 2
+    win = torch.zeros(n_fft)
+    win[left:left + win_length] = torch.hann_window(win_length, periodic=True)
+    spec = torch.fft.rfft(frames * win, dim=-1)                    # [N, T, n_fft/2+1]
+    power = spec.abs().pow(2.0)
+    mel = torch.matmul(power, mel_filterbank(sample_rate, n_fft, n_mels))   # [N, T, n_mels]
+    return mel.transpose(-1, -2).reshape(*lead, n_mels, -1)
+
+
+def logmel_clip(waveform: torch.Tensor, log_offset=LOG_OFFSET, **kw) -> torch.Tensor:
+    """One clip: `log(melspec(w).T + log_offset) -> [T, 64]` (voice100/data_modules.py:290-291)."""
+    return torch.log(mel_power(waveform, **kw).transpose(-1, -2) + log_offset)
+
+
+def logmel_batch(waveform: torch.Tensor, lengths: Sequence[int], **kw) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Ragged batch the way the reference builds one: features are computed per clip on the
+    clip's own samples (reflect at the clip's own end), then padded with BLANK_AUDIO
+    (voice100/data_modules.py:446-455, padding_value at :453).  Returns
+    (audio[B, T_max, 64], audio_len[B] int32)."""
+    feats = [logmel_clip(waveform[i, : int(n)], **kw) for i, n in enumerate(lengths)]
+    audio_len = torch.tensor([f.shape[0] for f in feats], dtype=torch.int32)
+    audio = torch.nn.utils.rnn.pad_sequence(feats, batch_first=True, padding_value=BLANK_AUDIO)
+    return audio, audio_len
+
+
+def logmel_numpy(waveform: np.ndarray, sample_rate=16000, n_fft=512, win_length=400, hop_length=160,
+                 n_mels=MELSPEC_DIM, log_offset=LOG_OFFSET) -> np.ndarray:
+    """Independent numpy restatement of the same front end for ONE clip -> [T, n_mels] fp32.
+    Uses float64 internally; agrees with the fp32 pipeline to ~1e-5 in the log domain."""
+    x = np.asarray(waveform, np.float64)
+    L = x.shape[0]
+    pad = n_fft // 2
+    idx = np.arange(-pad, L + pad)
+    idx = np.where(idx < 0, -idx, idx)
+    idx = np.where(idx >= L, 2 * (L - 1) - idx, idx)
+    xp = x[idx]
+    T = 1 + L // hop_length
+    left = (n_fft - win_length) // 2
+    win = np.zeros(n_fft)
+    win[left:left + win_length] = 0.5 * (1.0 - np.cos(2.0 * np.pi * np.arange(win_length) / win_length))
+    frames = np.stack([xp[hop_length * t: hop_length * t + n_fft] for t in range(T)]) * win
+    power = np.abs(np.fft.rfft(frames, axis=-1)) ** 2
+    fb = mel_filterbank(sample_rate, n_fft, n_mels).numpy().astype(np.float64)
+    return np.log(power @ fb + log_offset).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Model blocks: voice100/models/asr.py:27-59
+# ----------------------------------------------------------------------------------------------
+
+def _bn_eval(x: torch.Tensor, sd: SD, p: str, calib: Optional[dict]) -> torch.Tensor:
+    """BatchNorm1d in eval mode: gamma*(x-mu_run)/sqrt(var_run+eps)+beta (asr.py:36,52).
+    With `calib` set, first overwrite the running stats with this batch's statistics (what one
+    training-mode forward with momentum=1 would store: biased->unbiased variance), so randomly
+    initialised networks keep O(1) activations through all nine blocks."""
+    if calib is not None:
+        n = x.shape[0] * x.shape[2]
+        sd[p + ".running_mean"] = x.mean(dim=(0, 2)).clone()
+        sd[p + ".running_var"] = (x.var(dim=(0, 2), unbiased=False) * (n / max(1, n - 1))).clone()
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"],
+                        sd[p + ".bias"], training=False, eps=BN_EPS)
+
+
+def conv_bn_relu6(x, sd, p, kernel_size, stride=1, groups=1, calib=None):
+    """ConvBNActivate (asr.py:27-37): Conv1d(bias=False, padding=(k-1)//2) -> BN -> ReLU6."""
+    y = F.conv1d(x, sd[p + ".0.weight"], None, stride=stride, padding=(kernel_size - 1) // 2, groups=groups)
+    return F.hardtanh(_bn_eval(y, sd, p + ".1", calib), 0.0, 6.0)
+
+
+def inverted_residual(x, sd, p, kernel_size, stride=1, use_residual=True, calib=None):
+    """InvertedResidual (asr.py:40-59): 1x1 expand (x4) -> depthwise k -> 1x1 project (+BN, linear),
+    `x + conv(x)` iff use_residual."""
+    h = sd[p + ".conv.0.0.weight"].shape[0]
+    y = conv_bn_relu6(x, sd, p + ".conv.0", 1, calib=calib)
+    y = conv_bn_relu6(y, sd, p + ".conv.1", kernel_size, stride=stride, groups=h, calib=calib)
+    y = F.conv1d(y, sd[p + ".conv.2.weight"])
+    y = _bn_eval(y, sd, p + ".conv.3", calib)
+    return x + y if use_residual else y
+
+
+def _asr_blocks(sd: SD):
+    half = sd["encoder.layers.0.conv.2.weight"].shape[0]
+    ks = (11, 19, 27, 35, 51, 59, 67, 75, 83)                       # asr.py:67-76
+    return [(k, 2 if i == 0 else 1, i not in (0, 4, 8)) for i, k in enumerate(ks)]
+
+
+def asr_encoder(x_ncw: torch.Tensor, sd: SD, calib=None) -> torch.Tensor:
+    """ConvVoiceEncoder.forward on [B, 64, T] -> [B, embed, (T+1)//2] (asr.py:62-79)."""
+    for i, (k, s, r) in enumerate(_asr_blocks(sd)):
+        x_ncw = inverted_residual(x_ncw, sd, f"encoder.layers.{i}", k, s, r, calib)
+    return x_ncw
+
+
+def asr_forward(audio: torch.Tensor, sd: SD, calib=None) -> torch.Tensor:
+    """AudioToTextCTC.forward(audio[B,T,64]) -> logits[B,(T+1)//2,V] (asr.py:110-116).
+    Dropout(0.2) in LinearCharDecoder (asr.py:89-91) is the identity in eval mode."""
+    x = asr_encoder(audio.transpose(1, 2), sd, calib)
+    logits = F.conv1d(x, sd["decoder.layers.1.weight"], sd["decoder.layers.1.bias"])
+    return logits.transpose(1, 2)
+
+
+def asr_output_length(audio_len: torch.Tensor) -> torch.Tensor:
+    """asr.py:81-82,118-122."""
+    return torch.div(audio_len + 1, 2, rounding_mode="trunc")
+
+
+def ctc_greedy(logits: torch.Tensor) -> torch.Tensor:
+    """tests/test_onnx.py:40: `logits.argmax(-1)` -> int64 [B, T]."""
+    return logits.argmax(-1)
+
+
+DEFAULT_CHARACTERS = "_ abcdefghijklmnopqrstuvwxyz'"   # voice100/text.py:14
+
+
+def ctc_collapse_text(tokens: Sequence[int], vocab: str = DEFAULT_CHARACTERS) -> str:
+    """CharTokenizer.decode + merge_repeated (voice100/text.py:93-104): drop ids outside the
+    vocab, collapse runs of the same character, drop the blank '_' and a lone space."""
+    import re
+    text = "".join(vocab[int(t)] for t in tokens if 0 <= int(t) < len(vocab))
+    text = re.sub(r"(.)\1+", r"\1", text).replace("_", "")
+    return "" if text == " " else text
+
+
+# ----------------------------------------------------------------------------------------------
+# TTS: voice100/models/tts.py:13-29,67-110,152-201 and voice100/models/_layers_v1.py:96-138
+# ----------------------------------------------------------------------------------------------
+
+def align_forward(text: torch.Tensor, sd: SD, calib=None) -> torch.Tensor:
+    """TextToAlignTextModel.forward(text[B,L] int64) -> [B,L,2] = log(align+1) (tts.py:79-87)."""
+    x = F.embedding(text, sd["embedding.weight"]).transpose(1, 2)
+    for i, k in enumerate((5, 11, 17, 29)):
+        x = inverted_residual(x, sd, f"layers.{i}", k, 1, True, calib)
+    x = F.conv1d(x, sd["layers.4.weight"], sd["layers.4.bias"])
+    return x.transpose(1, 2)
+
+
+def align_text(text: Sequence[int], align: np.ndarray, head=5, tail=5) -> np.ndarray:
+    """TextToAlignTextModel.align for one utterance (tts.py:89-110): token i occupies frames
+    [round(t+gap_i), round(t+gap_i+dur_i)), at least one frame; python round() = half-to-even;
+    total length head + int(sum(align)) + tail; writes past the end are an IndexError in the
+    reference, so inputs here must not produce them."""
+    a = torch.as_tensor(np.asarray(align))
+    n = head + int(torch.sum(a)) + tail
+    out = np.zeros((n,), dtype=np.int64)
+    t = head
+    for i in range(a.shape[0]):
+        t += a[i, 0].item()
+        s = round(t)
+        t += a[i, 1].item()
+        e = round(t)
+        if s == e:
+            e = max(0, e + 1)
+        out[s:e] = int(text[i])
+    return out
+
+
+def voice_decoder(x: torch.Tensor, sd: SD, p="decoder", calib=None) -> torch.Tensor:
+    """VoiceDecoder.forward [B,H,T] -> [B,260,2T-1] (tts.py:13-29)."""
+    for i, k in enumerate((65, 33, 17, 11)):
+        x = inverted_residual(x, sd, f"{p}.layers.{i}", k, 1, True, calib)
+    x = F.conv_transpose1d(x, sd[f"{p}.layers.4.weight"], sd[f"{p}.layers.4.bias"], stride=2, padding=2)
+    for j, k in enumerate((33, 11, 7)):
+        x = inverted_residual(x, sd, f"{p}.layers.{5 + j}", k, 1, True, calib)
+    return F.conv1d(x, sd[f"{p}.layers.8.weight"], sd[f"{p}.layers.8.bias"])
+
+
+def audio_forward(aligntext: torch.Tensor, sd: SD, calib=None):
+    """AlignTextToAudioModel.forward -> (hasf0_logits[B,T'], f0_hat[B,T'], logspc_hat[B,T',257],
+    codeap_hat[B,T',1]), T' = 2T-1 (tts.py:172-190)."""
+    x = F.embedding(aligntext, sd["embedding.weight"]).transpose(1, 2)
+    x = voice_decoder(x, sd, "decoder", calib).transpose(1, 2)
+    hasf0, f0, logspc, codeap = torch.split(x, [1, 1, 257, 1], dim=2)
+    return hasf0[:, :, 0], f0[:, :, 0], logspc, codeap
+
+
+def audio_predict(aligntext: torch.Tensor, sd: SD):
+    """AlignTextToAudioModel.predict (tts.py:192-201): WORLDNorm.unnormalize
+    (_layers_v1.py:131-138: std*x+mean) then f0 := 0 where hasf0_logit < 0."""
+    hasf0, f0, logspc, codeap = audio_forward(aligntext, sd)
+    f0 = sd["norm.f0_std"] * f0 + sd["norm.f0_mean"]
+    logspc = sd["norm.logspc_std"] * logspc + sd["norm.logspc_mean"]
+    codeap = sd["norm.codeap_std"] * codeap + sd["norm.codeap_mean"]
+    f0 = torch.where(hasf0 < 0, torch.zeros((1,), dtype=f0.dtype), f0)
+    return f0, logspc, codeap
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers shared by tests / bench
+# ----------------------------------------------------------------------------------------------
+
+def calibrate_asr(sd: SD, audio: torch.Tensor) -> SD:
+    """Return a copy of `sd` whose BN running stats are those of `audio` (see _bn_eval)."""
+    sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        asr_forward(audio, sd, calib={})
+    return sd
+
+
+def calibrate_align(sd: SD, text: torch.Tensor) -> SD:
+    sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        align_forward(text, sd, calib={})
+    return sd
+
+
+def calibrate_audio(sd: SD, aligntext: torch.Tensor) -> SD:
+    sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        audio_forward(aligntext, sd, calib={})
+    return sd
+
+
+def parity_report(ref: torch.Tensor, got: torch.Tensor) -> Dict[str, float]:
+    """max-abs and RMS error normalised by the reference's std."""
+    ref = ref.double().flatten()
+    got = got.double().flatten()
+    std = float(ref.std()) or 1.0
+    d = (ref - got).abs()
+    return {"max_abs": float(d.max()), "rms": float(d.pow(2).mean().sqrt()), "ref_std": std,
+            "max_abs_rel_std": float(d.max()) / std, "rms_rel_std": float(d.pow(2).mean().sqrt()) / std}
+
+
+def token_agreement(ref_logits: torch.Tensor, got_tokens: torch.Tensor, margin: float):
+    """CTC greedy agreement: (raw, gated, gated_fraction).  `gated` counts only frames whose
+    fp32 top-1/top-2 logit margin exceeds `margin` (ties below bf16 resolution are not
+    decidable by any bf16 implementation)."""
+    top2 = ref_logits.float().topk(2, dim=-1).values
+    gate = (top2[..., 0] - top2[..., 1]) > margin
+    same = ref_logits.argmax(-1) == got_tokens
+    raw = float(same.float().mean())
+    gated = float(same[gate].float().mean()) if gate.any() else 1.0
+    return raw, gated, float(gate.float().mean())

@@ -1,0 +1,114 @@
+"""Pin the CPU oracle against outputs of the unmodified reference (tests/golden, made by
+oracle/gen_golden.py) and against the known-answer anchors of SURVEY.md section 8c."""
+import math
+
+import numpy as np
+import torch
+
+import v100_oracle as orc
+from voice100_b200 import synth
+from helpers import asr_case, golden, tts_case
+
+
+def test_constants_and_shapes():
+    g = golden("logmel")
+    assert float(g["blank_audio"]) == orc.BLANK_AUDIO == math.log(1e-6)
+    assert abs(orc.BLANK_AUDIO - (-13.815510557964274)) < 1e-12
+    assert int(g["audio_size"]) == orc.MELSPEC_DIM == 64           # reference tests/test_datasets.py:273
+    fb = orc.mel_filterbank()
+    assert fb.shape == (257, 64) and int((fb > 0).sum()) == 500   # SURVEY 8c anchor
+    for sec, frames in ((1, 101), (10, 1001), (15, 1501), (60, 6001)):
+        assert 1 + (sec * 16000) // 160 == frames
+    assert [int(x) for x in orc.asr_output_length(torch.tensor([1501, 1001, 100, 1]))] == [751, 501, 50, 1]
+
+
+def test_param_counts_match_readme():
+    n = lambda sd, p: sum(v.size for k, v in sd.items() if k.startswith(p) and "num_batches" not in k
+                          and "running" not in k)
+    asr = synth.asr_state_dict(64, 512, 29, 512)
+    assert n(asr, "encoder.") == 11_606_784 and n(asr, "decoder.") == 14_877     # README.md:135-147
+    al = synth.align_state_dict(29, 512)
+    assert n(al, "layers.") == 8_553_474 and n(al, "embedding.") == 14_848       # README.md:59-69
+    au = synth.audio_state_dict(29, 512)
+    assert n(au, "decoder.") == 11_044_868 and n(au, "norm.") == 518             # README.md:73-85
+
+
+def test_logmel_matches_reference():
+    g = golden("logmel")
+    cases = {"noise_16000": synth.noise_waveform(1, 16000, seed=11)[0],
+             "harm_12345": synth.harmonic_waveform(1, 12345, seed=12)[0],
+             "noise_400": synth.noise_waveform(1, 400, seed=13)[0]}
+    for k, w in cases.items():
+        got = orc.logmel_clip(torch.from_numpy(w)).numpy()
+        assert got.shape == g[k].shape == (1 + len(w) // 160, 64)
+        np.testing.assert_allclose(got, g[k], rtol=0, atol=2e-5, err_msg=k)
+        # step-by-step restatements: fp32 FFT round-off shows up in near-silent mel bins only
+        ex = torch.log(orc.mel_power_explicit(torch.from_numpy(w)).T + orc.LOG_OFFSET).numpy()
+        np.testing.assert_allclose(ex, g[k], rtol=0, atol=2e-3, err_msg=k + " explicit")
+        np.testing.assert_allclose(orc.logmel_numpy(w), g[k], rtol=0, atol=2e-3, err_msg=k + " numpy")
+    mp = orc.mel_power(torch.from_numpy(cases["harm_12345"])).numpy()
+    np.testing.assert_allclose(mp, g["harm_12345_melpower"], rtol=1e-5, atol=1e-7)
+    # ragged batch: per-clip features padded with BLANK_AUDIO (data_modules.py:446-455)
+    L = max(len(w) for w in cases.values())
+    wav = np.zeros((3, L), np.float32)
+    for i, w in enumerate(cases.values()):
+        wav[i, :len(w)] = w
+    audio, audio_len = orc.logmel_batch(torch.from_numpy(wav), [len(w) for w in cases.values()])
+    assert [int(x) for x in audio_len] == [int(x) for x in g["batch_audio_len"]] == [101, 78, 3]
+    np.testing.assert_allclose(audio.numpy(), g["batch_audio"], rtol=0, atol=2e-5)
+    assert float(audio[2, 3:].max()) == float(np.float32(orc.BLANK_AUDIO))
+
+
+def _asr(name):
+    sd, wav, lengths, g = asr_case(name)
+    audio, audio_len = orc.logmel_batch(wav, lengths)
+    with torch.no_grad():
+        logits = orc.asr_forward(audio, sd)
+    assert logits.shape == g["logits"].shape
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=2e-4)
+    assert [int(x) for x in audio_len] == [int(x) for x in g["audio_len"]]
+    assert [int(x) for x in orc.asr_output_length(audio_len)] == [int(x) for x in g["out_len"]]
+    agree = (orc.ctc_greedy(logits).numpy() == g["tokens"]).mean()
+    assert agree > 0.999, agree
+
+
+def test_asr_en_small_matches_reference():
+    _asr("asr_en_small")
+
+
+def test_asr_ja_ragged_matches_reference():
+    _asr("asr_ja_phone_ragged")
+
+
+def test_tts_matches_reference():
+    sd_a, sd_v, text, align, g = tts_case()
+    with torch.no_grad():
+        pred = orc.align_forward(text, sd_a)
+    np.testing.assert_allclose(pred.numpy(), g["align_pred"], rtol=0, atol=2e-4)
+    ats = [orc.align_text(text[i].tolist(), align[i]) for i in range(text.shape[0])]
+    assert [len(a) for a in ats] == [int(x) for x in g["aligntext_len"]]
+    at = np.zeros_like(g["aligntext"])
+    for i, a in enumerate(ats):
+        at[i, :len(a)] = a
+    assert (at == g["aligntext"]).all()
+    with torch.no_grad():
+        hasf0, f0_hat, _, _ = orc.audio_forward(torch.from_numpy(at), sd_v)
+        f0, logspc, codeap = orc.audio_predict(torch.from_numpy(at), sd_v)
+    T = at.shape[1]
+    assert logspc.shape == (at.shape[0], 2 * T - 1, 257) and codeap.shape == (at.shape[0], 2 * T - 1, 1)
+    np.testing.assert_allclose(hasf0.numpy(), g["hasf0_logits"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(logspc.numpy(), g["logspc"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(codeap.numpy(), g["codeap"], rtol=0, atol=1e-3)
+    # f0 is gated by the sign of hasf0: compare away from the decision boundary
+    safe = np.abs(g["hasf0_logits"]) > 1e-3
+    np.testing.assert_allclose(f0.numpy()[safe], g["f0"][safe], rtol=0, atol=2e-2)
+    assert ((f0.numpy() == 0) == (g["f0"] == 0))[safe].all()
+
+
+def test_ctc_collapse_known_answers():
+    # reference tests/test_text.py:57-59 style: repeats merged, blank dropped
+    enc = lambda s: [orc.DEFAULT_CHARACTERS.index(c) for c in s]
+    assert orc.ctc_collapse_text(enc("__hh_eel_ll__oo  w_")) == "hello w"
+    assert orc.ctc_collapse_text(enc("___")) == ""
+    assert orc.ctc_collapse_text(enc("_ _")) == ""
+    assert orc.ctc_collapse_text([0, 99, -1, 2, 2, 0, 2]) == "aa"

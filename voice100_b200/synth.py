@@ -1,0 +1,193 @@
+"""Deterministic synthetic weights and inputs (numpy PCG64, no torch RNG).
+
+There is no network for checkpoints or datasets, so every test, the oracle,
+the golden-vector generator and bench.py build their inputs from this one
+module.  Everything is a pure function of (spec, seed): the same call yields
+the same bytes in this container and on the GPU box, which is what lets the
+golden fixtures under tests/golden/ store OUTPUTS only.
+
+The `state_dict` key layout is the reference's own (probed by importing
+/root/reference with the shim in oracle/_shim):
+  ASR   voice100/models/asr.py:27-94     encoder.layers.{i}.conv.{0.0,0.1,1.0,1.1,2,3}.*,
+                                         decoder.layers.1.{weight,bias}
+  align voice100/models/tts.py:67-77     embedding.weight, layers.{0-3}.conv.*, layers.4.*
+  audio voice100/models/tts.py:13-29,152-170  embedding.weight, decoder.layers.{0-3,5-7}.conv.*,
+                                         decoder.layers.4.* (ConvTranspose1d [C_in,C_out,5]),
+                                         decoder.layers.8.*, norm.{f0,logspc,codeap}_{mean,std}
+"""
+from __future__ import annotations
+
+import zlib
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+# (in, out, kernel, stride, residual) per InvertedResidual -- voice100/models/asr.py:67-76
+def asr_encoder_blocks(audio_size: int, embed_size: int, hidden_size: int):
+    half = hidden_size // 2
+    return [
+        (audio_size, half, 11, 2, False),
+        (half, half, 19, 1, True),
+        (half, half, 27, 1, True),
+        (half, half, 35, 1, True),
+        (half, hidden_size, 51, 1, False),
+        (hidden_size, hidden_size, 59, 1, True),
+        (hidden_size, hidden_size, 67, 1, True),
+        (hidden_size, hidden_size, 75, 1, True),
+        (hidden_size, embed_size, 83, 1, False),
+    ]
+
+
+# voice100/models/tts.py:72-76
+ALIGN_KERNELS = (5, 11, 17, 29)
+# voice100/models/tts.py:17-25
+VOICE_DECODER_PRE_KERNELS = (65, 33, 17, 11)
+VOICE_DECODER_POST_KERNELS = (33, 11, 7)
+
+
+def _rng(seed: int, tag: str) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64([int(seed), zlib.crc32(tag.encode())]))
+
+
+def _uniform(seed, tag, shape, lo, hi):
+    u = _rng(seed, tag).random(size=shape)  # float64 in [0,1): stream-stable across numpy versions
+    return (lo + (hi - lo) * u).astype(np.float32)
+
+
+def _bn(sd, seed, prefix, c, randomize_bn):
+    if randomize_bn:
+        sd[prefix + ".weight"] = _uniform(seed, prefix + ".weight", (c,), 0.5, 1.5)
+        sd[prefix + ".bias"] = _uniform(seed, prefix + ".bias", (c,), -0.5, 0.5)
+        sd[prefix + ".running_mean"] = _uniform(seed, prefix + ".running_mean", (c,), -0.2, 0.2)
+        sd[prefix + ".running_var"] = _uniform(seed, prefix + ".running_var", (c,), 0.5, 1.5)
+    else:  # torch defaults (BatchNorm1d.reset_parameters)
+        sd[prefix + ".weight"] = np.ones((c,), np.float32)
+        sd[prefix + ".bias"] = np.zeros((c,), np.float32)
+        sd[prefix + ".running_mean"] = np.zeros((c,), np.float32)
+        sd[prefix + ".running_var"] = np.ones((c,), np.float32)
+    sd[prefix + ".num_batches_tracked"] = np.zeros((), np.int64)
+
+
+def _conv(sd, seed, key, shape, fan_in, gain=1.0):
+    b = gain / np.sqrt(fan_in)  # torch Conv default: kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in))
+    sd[key] = _uniform(seed, key, shape, -b, b)
+
+
+def _inverted_residual(sd, seed, prefix, c_in, c_out, k, randomize_bn, gain):
+    h = c_in * 4  # expand_ratio=4, voice100/models/asr.py:41-43
+    _conv(sd, seed, f"{prefix}.conv.0.0.weight", (h, c_in, 1), c_in, gain)
+    _bn(sd, seed, f"{prefix}.conv.0.1", h, randomize_bn)
+    _conv(sd, seed, f"{prefix}.conv.1.0.weight", (h, 1, k), k, gain)
+    _bn(sd, seed, f"{prefix}.conv.1.1", h, randomize_bn)
+    _conv(sd, seed, f"{prefix}.conv.2.weight", (c_out, h, 1), h, gain)
+    _bn(sd, seed, f"{prefix}.conv.3", c_out, randomize_bn)
+
+
+def asr_state_dict(audio_size=64, embed_size=512, vocab_size=29, hidden_size=512,
+                   seed=1234, randomize_bn=False, gain=1.0) -> Dict[str, np.ndarray]:
+    """Weights for AudioToTextCTC(audio_size, embed_size, vocab_size, hidden_size)."""
+    sd: Dict[str, np.ndarray] = {}
+    for i, (ci, co, k, _s, _r) in enumerate(asr_encoder_blocks(audio_size, embed_size, hidden_size)):
+        _inverted_residual(sd, seed, f"encoder.layers.{i}", ci, co, k, randomize_bn, gain)
+    _conv(sd, seed, "decoder.layers.1.weight", (vocab_size, embed_size, 1), embed_size, gain)
+    _conv(sd, seed, "decoder.layers.1.bias", (vocab_size,), embed_size, gain)
+    return sd
+
+
+def align_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=False, gain=1.0):
+    """Weights for TextToAlignTextModel(vocab_size, hidden_size)."""
+    sd: Dict[str, np.ndarray] = {}
+    sd["embedding.weight"] = _rng(seed, "embedding.weight").standard_normal(
+        (vocab_size, hidden_size)).astype(np.float32)
+    for i, k in enumerate(ALIGN_KERNELS):
+        _inverted_residual(sd, seed, f"layers.{i}", hidden_size, hidden_size, k, randomize_bn, gain)
+    _conv(sd, seed, "layers.4.weight", (2, hidden_size, 1), hidden_size, gain)
+    _conv(sd, seed, "layers.4.bias", (2,), hidden_size, gain)
+    return sd
+
+
+def audio_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=False, gain=1.0,
+                     randomize_norm=False):
+    """Weights for AlignTextToAudioModel(vocab_size, hidden_size, use_mcep=False)."""
+    half = hidden_size // 2
+    out_ch = 1 + 1 + 257 + 1  # hasf0, f0, logspc, codeap -- voice100/models/tts.py:160-167
+    sd: Dict[str, np.ndarray] = {}
+    sd["embedding.weight"] = _rng(seed, "embedding.weight").standard_normal(
+        (vocab_size, hidden_size)).astype(np.float32)
+    for i, k in enumerate(VOICE_DECODER_PRE_KERNELS):
+        _inverted_residual(sd, seed, f"decoder.layers.{i}", hidden_size, hidden_size, k, randomize_bn, gain)
+    # ConvTranspose1d weight layout is [C_in, C_out, k]; torch fan_in for it is C_out*k
+    _conv(sd, seed, "decoder.layers.4.weight", (hidden_size, half, 5), half * 5, gain)
+    _conv(sd, seed, "decoder.layers.4.bias", (half,), half * 5, gain)
+    for j, k in enumerate(VOICE_DECODER_POST_KERNELS):
+        _inverted_residual(sd, seed, f"decoder.layers.{5 + j}", half, half, k, randomize_bn, gain)
+    _conv(sd, seed, "decoder.layers.8.weight", (out_ch, half, 1), half, gain)
+    _conv(sd, seed, "decoder.layers.8.bias", (out_ch,), half, gain)
+    if randomize_norm:
+        sd["norm.f0_std"] = _uniform(seed, "norm.f0_std", (1,), 20.0, 60.0)
+        sd["norm.f0_mean"] = _uniform(seed, "norm.f0_mean", (1,), 100.0, 200.0)
+        sd["norm.logspc_std"] = _uniform(seed, "norm.logspc_std", (257,), 0.5, 2.0)
+        sd["norm.logspc_mean"] = _uniform(seed, "norm.logspc_mean", (257,), -8.0, -2.0)
+        sd["norm.codeap_std"] = _uniform(seed, "norm.codeap_std", (1,), 0.5, 2.0)
+        sd["norm.codeap_mean"] = _uniform(seed, "norm.codeap_mean", (1,), -3.0, 0.0)
+    else:  # voice100/models/_layers_v1.py:100-117 defaults
+        sd["norm.f0_std"] = np.ones((1,), np.float32)
+        sd["norm.f0_mean"] = np.zeros((1,), np.float32)
+        sd["norm.logspc_std"] = np.ones((257,), np.float32)
+        sd["norm.logspc_mean"] = np.zeros((257,), np.float32)
+        sd["norm.codeap_std"] = np.ones((1,), np.float32)
+        sd["norm.codeap_mean"] = np.zeros((1,), np.float32)
+    return sd
+
+
+def bn_prefixes(sd: Dict[str, np.ndarray]) -> List[str]:
+    """BatchNorm module prefixes of a state dict, in forward order."""
+    return [k[: -len(".running_mean")] for k in sd if k.endswith(".running_mean")]
+
+
+# ----------------------------------------------------------------------------
+# inputs
+# ----------------------------------------------------------------------------
+
+def noise_waveform(batch: int, samples: int, seed=1234, amp=0.1) -> np.ndarray:
+    """`amp * N(0,1)` fp32 audio, the survey's default probe input."""
+    return (amp * _rng(seed, f"noise{batch}x{samples}").standard_normal((batch, samples))).astype(np.float32)
+
+
+def harmonic_waveform(batch: int, samples: int, seed=1234, sample_rate=16000) -> np.ndarray:
+    """Speech-like synthetic audio: sum of 1-8 harmonics of a random f0 in [100,1000) Hz with
+    amplitudes U*exp(-0.2 i).  Same recipe as the reference's own test fixture
+    (tests/test_datasets.py:70-83, make_random_audio), re-expressed on numpy PCG64."""
+    g = _rng(seed, f"harm{batch}x{samples}")
+    t = np.arange(samples, dtype=np.float64) / sample_rate
+    out = np.zeros((batch, samples), np.float64)
+    for b in range(batch):
+        f0 = 100.0 + 900.0 * g.random()
+        n = 1 + int(g.integers(0, 8))
+        for i in range(n):
+            a = g.random() * np.exp(-0.2 * i)
+            out[b] += a * np.sin(2 * np.pi * f0 * (i + 1) * t + 2 * np.pi * g.random())
+        out[b] /= max(1.0, np.abs(out[b]).max())
+    return out.astype(np.float32)
+
+
+def ragged_lengths(batch: int, lo: int, hi: int, seed=1234) -> np.ndarray:
+    """Seeded clip lengths in samples, U[lo, hi]; the last one is pinned to `hi` so the batch
+    maximum is known."""
+    ln = _rng(seed, f"len{batch}").integers(lo, hi + 1, size=batch).astype(np.int32)
+    ln[-1] = hi
+    return ln
+
+
+def text_tokens(batch: int, length: int, vocab_size=29, seed=1234) -> np.ndarray:
+    return _rng(seed, f"text{batch}x{length}").integers(1, vocab_size, size=(batch, length)).astype(np.int64)
+
+
+def synthetic_alignment(batch: int, length: int, seed=1234) -> np.ndarray:
+    """Seeded stand-in for exp(pred)-1 (random-init models give negative gaps):
+    gap ~ U[0,1), duration ~ U[0,4) frames per token."""
+    g = _rng(seed, f"align{batch}x{length}")
+    a = np.empty((batch, length, 2), np.float32)
+    a[..., 0] = g.random((batch, length))
+    a[..., 1] = 4.0 * g.random((batch, length))
+    return a
