@@ -1,0 +1,152 @@
+/*
+ * v100.h -- C ABI of libv100.so: the B200 (sm_100a) kernels behind Voice100's batched
+ * inference hot path.
+ *
+ * The reference (kaiidams/voice100) is pure Python and has no FFI: its operator interface for
+ * this path is a handful of torch.nn.Module.forward methods.  Each entry point below replaces
+ * the library kernels one such forward dispatches to; the citation says which
+ * (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller; the library allocates nothing;
+ *  - activations are "NCW with pitch": x[b][c][t] at  base + (b*C + c)*pitch + t,  t < T,
+ *    bf16 unless stated, pitch % 8 == 0 (16-byte rows) and base 16-byte aligned.  This is the
+ *    reference's own layout inside ConvVoiceEncoder/VoiceDecoder (asr.py:111, tts.py:174);
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it and are
+ *    CUDA-graph capturable;
+ *  - return value 0 = ok; <0 = V100_E_* below; >0 = a cudaError_t.  v100_last_error() returns a
+ *    thread-local description of the last failure.  There is no CPU fallback: an unsupported
+ *    shape is an error, never a silent slow path.
+ */
+#ifndef V100_H_
+#define V100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V100_ABI_VERSION 1
+
+#define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
+#define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
+#define V100_E_DRIVER    (-3)   /* could not resolve cuTensorMapEncodeTiled / wrong device    */
+
+#define V100_ACT_NONE  0
+#define V100_ACT_RELU6 1
+
+/* log-mel output selectors */
+#define V100_MEL_LOG_BF16_NCW  0  /* log(mel+offset), bf16 [B][64][pitch], frames >= n_i = log(offset)  */
+#define V100_MEL_LOG_F32_NTC   1  /* log(mel+offset), fp32 [B][T][64]  (the reference's feature layout) */
+#define V100_MEL_POWER_F32_NCW 2  /* mel power, fp32 [B][64][pitch]    (MelSpectrogram.forward layout)  */
+
+int v100_abi_version(void);
+const char* v100_last_error(void);
+
+/*
+ * Log-mel front end.  Replaces MelSpectrogramAudioTransform.melspec + log
+ * (voice100/data_modules.py:276-281,290-291; torchaudio MelSpectrogram: reflect pad 256,
+ * 512-sample frames every 160, periodic Hann(400) centred, |rFFT|^2, 64 HTK mel filters) and
+ * the BLANK_AUDIO feature padding of generate_audio_text_batch (data_modules.py:446-455).
+ *   wav      fp32 [B][wav_pitch] samples, clip i valid for len[i] samples (len[i] > 256)
+ *   fb_*     the sparse mel filterbank: filter m covers bins [fb_start[m], fb_start[m]+fb_count[m])
+ *            with weights fb_w[fb_off[m] ...]  (built by the host from the torchaudio formula)
+ *   out      see V100_MEL_*;  T = frames written per clip (>= max_i 1 + len[i]/160)
+ */
+int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch,
+                const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off,
+                const float* fb_w, float log_offset,
+                void* out, int T, int64_t out_pitch, int out_mode, void* stream);
+
+/*
+ * fp32 [B][T][C] features -> bf16 NCW [B][C][pitch].  Replaces the transpose at the top of
+ * AudioToTextCTC.forward (voice100/models/asr.py:111) plus the bf16 cast.
+ */
+int v100_ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, void* stream);
+
+/*
+ * Dense fp32 NCW [B][C][T] <-> pitched bf16 NCW.  Entry/exit casts of ConvVoiceEncoder.forward
+ * (voice100/models/asr.py:78-79) and VoiceDecoder.forward (tts.py:28-29) when those sub-modules are
+ * called on their own with the reference's fp32 NCW tensors.
+ */
+int v100_ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, void* stream);
+int v100_ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, void* stream);
+
+/*
+ * Pointwise (1x1) Conv1d as a bf16 tcgen05 GEMM with TMA-staged tiles and TMEM accumulators:
+ *   y[b][co][t] = act(scale[co] * sum_ci W[co][ci] * x[b][ci][t] + shift[co]) (+ res[b][co][t])
+ * Replaces Conv1d(k=1,bias=False) + BatchNorm1d(eval) + ReLU6 and the residual add of
+ * InvertedResidual (voice100/models/asr.py:27-37,45-59); scale/shift are the folded BN.
+ *   W bf16 [C_out][C_in] row-major, C_in % 8 == 0;  x, y, res bf16 NCW;  scale/shift fp32 [C_out]
+ *   (scale may be NULL = 1);  res may be NULL; res shares y's pitch.
+ */
+int v100_conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale,
+                      const float* shift, const void* res, void* y, int64_t y_pitch,
+                      int B, int C_in, int C_out, int T, int act, void* stream);
+
+/*
+ * Same GEMM, fp32 NCW output and bias only:  y[b][co][t] = sum_ci W[co][ci] x[b][ci][t] + bias[co].
+ * Replaces the biased 1x1 heads: LinearCharDecoder (asr.py:89-94), TextToAlignTextModel's
+ * Conv1d(512->2) (tts.py:77) and VoiceDecoder's Conv1d(256->260) (tts.py:26).
+ */
+int v100_conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias,
+                        float* y, int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream);
+
+/*
+ * Depthwise Conv1d + folded BN + ReLU6:
+ *   y[b][c][o] = act(scale[c] * sum_j w[c][j] * x[b][c][o*stride + j - (k-1)/2] + shift[c])
+ * with zero padding, k odd, T_out = (T_in-1)/stride + 1.  Replaces ConvBNActivate with
+ * groups=C (voice100/models/asr.py:27-37,49).  w bf16 [C][k].
+ */
+int v100_dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale,
+                       const float* shift, void* y, int64_t y_pitch,
+                       int B, int C, int T_in, int k, int stride, int act, void* stream);
+
+/* Same contract, always the plain CUDA-core kernel (any stride).  Used for stride != 1 internally;
+ * exported so the tests can cross-check the tensor-core kernel against it on the device. */
+int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const float* scale,
+                            const float* shift, void* y, int64_t y_pitch,
+                            int B, int C, int T_in, int k, int stride, int act, void* stream);
+
+/*
+ * ConvTranspose1d(C_in -> C_out, kernel 5, stride 2, padding 2) + bias as two-phase tcgen05
+ * GEMMs over shifted TMA views (even outputs: taps 0,2,4; odd outputs: taps 1,3), interleaved
+ * in the epilogue.  Replaces VoiceDecoder.layers[4] (voice100/models/tts.py:22).
+ *   Wp bf16 [C_out][5*C_in], Wp[co][tap*C_in + ci] = weight[ci][co][tap];  y bf16 NCW, T_out = 2T-1.
+ */
+int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
+                                   void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream);
+
+/*
+ * Embedding lookup into NCW: y[b][c][t] = table[ids[b][t]][c].  Replaces nn.Embedding +
+ * transpose (voice100/models/tts.py:81-83,174-175).  ids int64 [B][T]; table bf16 [V][C].
+ */
+int v100_embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch,
+                            int B, int T, int V, int C, void* stream);
+
+/*
+ * CTC head tail: fp32 NCW logits [B][V][pitch] -> logits [B][T][V] fp32 (optional) and greedy
+ * tokens int64 [B][T] (first maximal index).  Replaces transpose(1,2) (asr.py:114) and
+ * logits.argmax(-1) (tests/test_onnx.py:40).
+ */
+int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null, int64_t* tokens,
+                      int B, int V, int T, void* stream);
+
+/*
+ * WORLD head tail: fp32 NCW [B][260][pitch] -> hasf0[B][T], f0[B][T], logspc[B][T][257],
+ * codeap[B][T][1], with std*x+mean and f0 := 0 where hasf0 < 0 when `unnormalize` != 0.
+ * Replaces split + WORLDNorm.unnormalize + where (tts.py:181-190,196-200; _layers_v1.py:131-138).
+ * mean/std fp32 [259] ordered f0, logspc[257], codeap (ignored when unnormalize == 0).
+ */
+int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std,
+                        float* hasf0, float* f0, float* logspc, float* codeap,
+                        int B, int T, int unnormalize, void* stream);
+
+/* fp32 NCW [B][C][pitch] -> fp32 [B][T][C] (align head output [B][L][2]). */
+int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V100_H_ */

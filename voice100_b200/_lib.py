@@ -1,0 +1,65 @@
+"""ctypes binding of libv100.so (C ABI in include/v100.h).
+
+There is no fallback of any kind: if the shared library is missing or an entry point fails, the caller
+gets an exception.  Build the library with `python -m voice100_b200.build`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libv100.so")
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> argtypes; mirrors include/v100.h declaration by declaration
+SIGNATURES = {
+    "v100_abi_version": [],
+    "v100_logmel": [_p, _p, _i, _l, _p, _p, _p, _p, _f, _p, _i, _l, _i, _p],
+    "v100_ntc_f32_to_ncw_bf16": [_p, _p, _i, _i, _i, _l, _p],
+    "v100_ncw_f32_to_bf16": [_p, _p, _l, _i, _i, _i, _p],
+    "v100_ncw_bf16_to_f32": [_p, _l, _p, _i, _i, _i, _p],
+    "v100_conv1x1_bf16": [_p, _l, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "v100_conv1x1_f32out": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_dwconv1d_bf16": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "v100_dwconv1d_bf16_simt": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "v100_convtranspose1d_k5s2_bf16": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_embedding_ncw_bf16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p],
+    "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
+}
+
+ABI_VERSION = 1
+_lib = None
+
+
+class V100Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libv100.so once; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise V100Error(f"{LIB_PATH} is missing: run `python -m voice100_b200.build` (there is no CPU/PyTorch "
+                            "fallback for the Voice100 hot path)")
+        handle = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = _i
+        handle.v100_last_error.argtypes = []
+        handle.v100_last_error.restype = C.c_char_p
+        if handle.v100_abi_version() != ABI_VERSION:
+            raise V100Error("libv100.so ABI version mismatch: rebuild with `python -m voice100_b200.build --force`")
+        _lib = handle
+    return _lib
+
+
+def call(name, *args):
+    """Invoke an entry point; non-zero status raises with the library's own message."""
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise V100Error(f"{name} failed (status {rc}): {handle.v100_last_error().decode()}")

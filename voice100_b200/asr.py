@@ -1,0 +1,114 @@
+"""ASR: ConvVoiceEncoder + LinearCharDecoder + CTC greedy, on the libv100 kernels.
+
+Interface mirrors voice100/models/asr.py:62-122 (constructor arguments, `forward`, `output_length`,
+`.encoder` / `.decoder` sub-modules working on NCW tensors, `state_dict` keys).  Inference only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from ._lib import V100Error
+from .blocks import InvertedResidualParams, PreparedCache, require_eval_cuda, run_inverted_residual
+from .synth import asr_encoder_blocks
+
+__all__ = ["AudioToTextCTC", "ConvVoiceEncoder", "LinearCharDecoder"]
+
+
+class ConvVoiceEncoder(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, hidden_size: int):
+        super().__init__()
+        self.layers = nn.Sequential(*[
+            InvertedResidualParams(ci, co, k, s, r)
+            for ci, co, k, s, r in asr_encoder_blocks(in_channels, out_channels, hidden_size)])
+        self._prepared = PreparedCache(self, lambda: [blk.prepare() for blk in self.layers])
+
+    def run(self, x: K.Ncw) -> K.Ncw:
+        for w in self._prepared.get():
+            x = run_inverted_residual(x, w)
+        return x
+
+    def forward(self, embed: torch.Tensor) -> torch.Tensor:
+        """fp32 NCW [B, in_channels, T] -> fp32 NCW [B, out_channels, (T+1)//2]."""
+        require_eval_cuda(self, embed)
+        return K.ncw_to_f32(self.run(K.ncw_from_f32(embed.float().contiguous())))
+
+    def output_length(self, embed_len: torch.Tensor) -> torch.Tensor:
+        return torch.div(embed_len + 1, 2, rounding_mode="trunc")
+
+
+class LinearCharDecoder(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        # index 0 is Dropout(0.2) in the reference (identity in eval); index 1 carries the weights
+        self.layers = nn.Sequential(nn.Identity(), nn.Conv1d(in_channels, out_channels, 1, bias=True))
+        self._prepared = PreparedCache(self, lambda: (
+            self.layers[1].weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(),
+            self.layers[1].bias.detach().float().contiguous()))
+
+    def run(self, x: K.Ncw) -> K.Ncw:
+        W, b = self._prepared.get()
+        return K.conv1x1_f32(x, W, b)
+
+    def forward(self, enc_out: torch.Tensor) -> torch.Tensor:
+        """fp32 NCW [B, embed, T] -> fp32 NCW logits [B, V, T]."""
+        require_eval_cuda(self, enc_out)
+        y = self.run(K.ncw_from_f32(enc_out.float().contiguous()))
+        return y.valid().contiguous()
+
+
+class AudioToTextCTC(nn.Module):
+    def __init__(self, audio_size: int, embed_size: int, vocab_size: int, hidden_size: int,
+                 learning_rate: float = 1e-3, weight_decay: float = 0.0):
+        super().__init__()
+        self.hparams = dict(audio_size=audio_size, embed_size=embed_size, vocab_size=vocab_size,
+                            hidden_size=hidden_size, learning_rate=learning_rate, weight_decay=weight_decay)
+        self.embed_size = embed_size
+        self.encoder = ConvVoiceEncoder(audio_size, embed_size, hidden_size)
+        self.decoder = LinearCharDecoder(embed_size, vocab_size)
+        self.eval()
+
+    def _run(self, x: K.Ncw, want_logits: bool):
+        return K.ctc_finalize(self.decoder.run(self.encoder.run(x)), want_logits)
+
+    def forward(self, audio: torch.Tensor) -> torch.Tensor:
+        """audio fp32 [B, T, audio_size] -> logits fp32 [B, (T+1)//2, vocab_size]."""
+        require_eval_cuda(self, audio)
+        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous()), True)[0]
+
+    def greedy(self, audio) -> torch.Tensor:
+        """CTC best-path tokens int64 [B, (T+1)//2] = forward(audio).argmax(-1) without materialising the
+        logits.  `audio` is fp32 [B, T, 64] or the bf16 Ncw produced by logmel_batch(ncw_bf16=True)."""
+        if isinstance(audio, K.Ncw):
+            require_eval_cuda(self, audio.data)
+            return self._run(audio, False)[1]
+        require_eval_cuda(self, audio)
+        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous()), False)[1]
+
+    def output_length(self, audio_len: torch.Tensor) -> torch.Tensor:
+        return self.encoder.output_length(audio_len)
+
+
+class AsrPipeline:
+    """waveform -> tokens: log-mel + encoder + CTC head + greedy argmax, every stage a libv100 kernel.
+    This is the path BASELINE.json's metric (ASR audio-seconds/second) is measured on."""
+
+    def __init__(self, transform, model: AudioToTextCTC):
+        self.transform, self.model = transform, model
+
+    @torch.no_grad()
+    def __call__(self, waveform: torch.Tensor, lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """device waveform fp32 [B, L], lengths [B] -> (tokens int64 [B, T'], valid lengths int [B])."""
+        feats, audio_len = self.transform.logmel_batch(waveform, lengths, ncw_bf16=True)
+        return self.model.greedy(feats), self.model.output_length(audio_len)
+
+    @torch.no_grad()
+    def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda"):
+        """Host (ideally pinned) buffers in, host tokens out: the end-to-end call a user makes."""
+        wav_d = waveform.to(device, non_blocking=True)
+        len_d = lengths.to(device, non_blocking=True)
+        tokens, out_len = self(wav_d, len_d)
+        return tokens.cpu(), out_len.cpu()

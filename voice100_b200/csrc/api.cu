@@ -1,0 +1,156 @@
+// extern "C" surface of libv100.so (see include/v100.h) + host plumbing.
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "host.h"
+
+namespace v100 {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static thread_local int dev_cached = -1, sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != dev_cached) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    dev_cached = dev;
+  }
+  return sms > 0 ? sms : 148;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// libv100 does not link libcuda: the one driver call it needs is resolved through the runtime.
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint32_t ones[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu strides %llu)",
+                int(r), rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                (unsigned long long)strides[0]);
+  return 0;
+}
+
+int make_tmap_2d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1) {
+  const cuuint64_t dims[2] = {cuuint64_t(d0), cuuint64_t(d1)};
+  const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
+  const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
+  return encode(m, base, 2, dims, strides, box);
+}
+
+int make_tmap_3d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
+                 int64_t stride2_bytes, int box0, int box1) {
+  const cuuint64_t dims[3] = {cuuint64_t(d0), cuuint64_t(d1), cuuint64_t(d2)};
+  const cuuint64_t strides[2] = {cuuint64_t(stride1_bytes), cuuint64_t(stride2_bytes)};
+  const cuuint32_t box[3] = {cuuint32_t(box0), cuuint32_t(box1), 1};
+  return encode(m, base, 3, dims, strides, box);
+}
+
+}  // namespace v100
+
+using namespace v100;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int v100_abi_version(void) { return V100_ABI_VERSION; }
+const char* v100_last_error(void) { return g_err; }
+
+int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const int32_t* fb_start,
+                const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T,
+                int64_t out_pitch, int out_mode, void* stream) {
+  return logmel(wav, len, B, wav_pitch, fb_start, fb_count, fb_off, fb_w, log_offset, out, T, out_pitch, out_mode,
+                STREAM(stream));
+}
+
+int v100_ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, void* stream) {
+  return ntc_f32_to_ncw_bf16(x, y, B, T, C, y_pitch, STREAM(stream));
+}
+
+int v100_ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, void* stream) {
+  return ncw_f32_to_bf16(x, y, y_pitch, B, C, T, STREAM(stream));
+}
+
+int v100_ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, void* stream) {
+  return ncw_bf16_to_f32(x, x_pitch, y, B, C, T, STREAM(stream));
+}
+
+int v100_conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
+                      const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act,
+                      void* stream) {
+  return conv1x1_bf16(x, x_pitch, W, scale, shift, res, y, y_pitch, B, C_in, C_out, T, act, STREAM(stream));
+}
+
+int v100_conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
+                        int B, int C_in, int C_out, int T, void* stream) {
+  return conv1x1_f32out(x, x_pitch, W, bias, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
+}
+
+int v100_dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
+                       int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, void* stream) {
+  return dwconv1d_bf16(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, 0, STREAM(stream));
+}
+
+// Same contract as v100_dwconv1d_bf16 but always the plain CUDA-core kernel (any stride); exported so the
+// tests can cross-check the tensor-core kernel against it on the GPU.
+int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
+                            void* y, int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act,
+                            void* stream) {
+  return dwconv1d_bf16(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, 1, STREAM(stream));
+}
+
+int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* y,
+                                   int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream) {
+  return convtranspose1d_k5s2_bf16(x, x_pitch, Wp, bias, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
+}
+
+int v100_embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V,
+                            int C, void* stream) {
+  return embedding_ncw_bf16(ids, table, y, y_pitch, B, T, V, C, STREAM(stream));
+}
+
+int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null, int64_t* tokens, int B, int V,
+                      int T, void* stream) {
+  return ctc_finalize(y_ncw, y_pitch, logits_or_null, tokens, B, V, T, STREAM(stream));
+}
+
+int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0,
+                        float* f0, float* logspc, float* codeap, int B, int T, int unnormalize, void* stream) {
+  return world_finalize(y_ncw, y_pitch, mean, std, hasf0, f0, logspc, codeap, B, T, unnormalize, STREAM(stream));
+}
+
+int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream) {
+  return ncw_f32_to_ntc(y_ncw, y_pitch, out, B, C, T, STREAM(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,467 @@
+// Pointwise / multi-tap Conv1d as a persistent, warp-specialised tcgen05 GEMM (sm_100a).
+//
+//   D[co][t] = sum_tap sum_ci  W[co][tap*C_in + ci] * X[b][ci][t + shift(tap)]
+//
+// Operand roles: the WEIGHTS are the UMMA "A" operand (M = 128 output channels, K-major, 128B swizzle),
+// the ACTIVATIONS are the "B" operand (N = 128/256 time steps, MN-major because NCW keeps time
+// contiguous, 128B swizzle).  Accumulators live in TMEM (lane = output channel, column = time), double
+// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
+// allocator, warp 3 = idle, warps 4..11 = epilogue (two groups of four warps; warp%4 selects the TMEM
+// lane quadrant it is allowed to read).
+//
+// Epilogues:
+//   OUT_BF16: y = act(scale*acc + shift) (+ residual) -> bf16, staged in 128B-swizzled smem and written
+//             with TMA stores; the residual tile is TMA-loaded into the same staging buffer ahead of
+//             time.  With N_ACC == 2 (ConvTranspose1d k5 s2) the even/odd output phases are two
+//             accumulators interleaved here.
+//   OUT_F32 : y = acc + bias -> fp32 NCW, direct 16-byte stores (the small biased heads).
+#include "common.cuh"
+#include "host.h"
+
+namespace v100 {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kBAtomBytes = kBlockK * 64 * 2;       // 8 KB: 64 k-rows x 64 time steps
+constexpr int kChunkBytes = kBlockM * 64 * 2;       // 16 KB: 128 channels x 64 time steps (staging)
+constexpr int kMaxTaps = 5;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
+
+enum { OUT_BF16 = 0, OUT_F32 = 1 };
+
+struct GemmParams {
+  int C_out, C_in, B;
+  int m_tiles, t_tiles, num_tiles, k_blocks;
+  int n_taps;
+  int tap_shift[kMaxTaps];
+  int tap_acc[kMaxTaps];
+  const float* scale;
+  const float* shift;
+  int act;
+  int has_res;
+  float* y32;
+  long long y32_pitch;
+};
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+struct GemmCfg {
+  static constexpr int kStageBytes = kATileBytes + (BLOCK_N / 64) * kBAtomBytes;
+  static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? 4 * kChunkBytes : 0;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = 1024 + STAGES * kStageBytes + kStagingBytes + kBarBytes;
+  static constexpr int kTmemCols = 2 * N_ACC * BLOCK_N;
+  static constexpr int kOutCols = N_ACC * BLOCK_N;       // output time steps per tile
+  static constexpr int kChunksPerGroup = kOutCols / 128;  // 64-column chunks per epilogue group per tile
+  static_assert(kTmemCols == 512 || kTmemCols == 256, "TMEM allocation must be a power of two");
+  static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+};
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::kStagingBytes);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint64_t* res_bar = bars + 2 * STAGES + 4;    // [2 groups][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_x);
+    if (OUT_MODE == OUT_BF16) {
+      tma_prefetch_desc(&tm_y);
+      if (p.has_res) tma_prefetch_desc(&tm_res);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters_per_tile = p.n_taps * p.k_blocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile % p.m_tiles;
+        const int r = tile / p.m_tiles;
+        const int t_tile = r % p.t_tiles;
+        const int b = r / p.t_tiles;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int t_in0 = t_tile * BLOCK_N + p.tap_shift[tap];
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kATileBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(sa, &tm_w, &full_bar[stage], tap * p.C_in + kb * kBlockK, m_tile * kBlockM);
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              tma_load_3d(sb + a * kBAtomBytes, &tm_x, &full_bar[stage], t_in0 + a * 64, kb * kBlockK, b);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      // kind::f16 instruction descriptor: D=f32, A=B=bf16, A K-major, B MN-major, M=128, N=BLOCK_N
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                                 (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        const int accbuf = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[accbuf], acc_phase ^ 1);
+        tc_fence_after();
+        uint32_t used = 0;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          const int acc = p.tap_acc[tap];
+          const uint32_t d_tmem = tmem_base + accbuf * (N_ACC * BLOCK_N) + acc * BLOCK_N;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // A: K-major SW128 (8-row groups 1024 B apart; +32 B per 16-element K step inside the atom)
+              const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024);
+              // B: MN-major SW128 (64-time atoms 8 KB apart = LBO; 8-k-row groups 1024 B apart = SBO;
+              //    16 k rows = 2048 B per K step)
+              const uint64_t db = umma_desc(b_addr + k * 2048, kBAtomBytes, 1024);
+              umma_bf16(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+            }
+            used |= 1u << acc;
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[accbuf]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int g = (warp - 4) >> 2;      // epilogue group
+    const int row = q * 32 + lane;      // accumulator row == output channel within the tile
+    const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
+
+    if constexpr (OUT_MODE == OUT_BF16) {
+      constexpr int CPG = Cfg::kChunksPerGroup;
+      const bool elected = (row == 0);
+      uint8_t* stg = staging + g * 2 * kChunkBytes;
+      uint64_t* rbar = res_bar + g * 2;
+      const uint32_t bar_free = 1 + g * 2, bar_done = 2 + g * 2;
+      const uint32_t swz = uint32_t(row & 7);
+      uint8_t* my_row = stg + row * 128;
+
+      if (p.has_res && elected && int(blockIdx.x) < p.num_tiles) {
+        const int tile = blockIdx.x;
+        const int r = tile / p.m_tiles;
+        mbar_expect_tx(&rbar[0], kChunkBytes);
+        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + g * 64, (tile % p.m_tiles) * kBlockM,
+                    r / p.t_tiles);
+      }
+      int iter = 0;
+      uint32_t n = 0;  // chunk sequence number of this group
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        const int m_tile = tile % p.m_tiles;
+        const int r = tile / p.m_tiles;
+        const int t_tile = r % p.t_tiles;
+        const int b = r / p.t_tiles;
+        const int accbuf = iter & 1;
+        const int ch = m_tile * kBlockM + row;
+        const float sc = (p.scale != nullptr && ch < p.C_out) ? __ldg(p.scale + ch) : 1.0f;
+        const float sh = (ch < p.C_out) ? __ldg(p.shift + ch) : 0.0f;
+        mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < CPG; ++i, ++n) {
+          const int c = g + 2 * i;  // 64-column output chunk of this tile
+          const int buf = n & 1;
+          uint32_t v0[32], v1[32];
+          const uint32_t col0 = accbuf * (N_ACC * BLOCK_N);
+          if constexpr (N_ACC == 1) {
+            tmem_ld32(lane_addr + col0 + c * 64, v0);
+            tmem_ld32(lane_addr + col0 + c * 64 + 32, v1);
+          } else {
+            tmem_ld32(lane_addr + col0 + c * 32, v0);            // even output phase
+            tmem_ld32(lane_addr + col0 + BLOCK_N + c * 32, v1);  // odd output phase
+          }
+          tmem_ld_wait();
+          if (i == CPG - 1) {  // this thread is done reading the accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[accbuf]);
+          }
+          float f0[32], f1[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f0[j] = fmaf(__uint_as_float(v0[j]), sc, sh);
+            f1[j] = fmaf(__uint_as_float(v1[j]), sc, sh);
+            if (p.act == V100_ACT_RELU6) {
+              f0[j] = fminf(fmaxf(f0[j], 0.0f), 6.0f);
+              f1[j] = fminf(fmaxf(f1[j], 0.0f), 6.0f);
+            }
+          }
+          // staging buffer `buf` is free (its previous TMA store has been read out) ...
+          named_bar_sync(bar_free, 128);
+          // ... and, if there is a residual, holds this chunk's residual tile
+          if (p.has_res) mbar_wait(&rbar[buf], (n >> 1) & 1);
+          uint8_t* rowp = my_row + buf * kChunkBytes;
+#pragma unroll
+          for (int k16 = 0; k16 < 8; ++k16) {
+            uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4));
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              if constexpr (N_ACC == 1) {
+                const int j = k16 * 8 + e;
+                o[e] = j < 32 ? f0[j] : f1[j - 32];
+              } else {
+                const int j = k16 * 4 + (e >> 1);
+                o[e] = (e & 1) ? f1[j] : f0[j];
+              }
+            }
+            if (p.has_res) {
+              const uint4 rr = *dst;
+              o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
+              o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
+              o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
+              o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
+            }
+            uint4 w;
+            w.x = pack_bf16x2(o[0], o[1]);
+            w.y = pack_bf16x2(o[2], o[3]);
+            w.z = pack_bf16x2(o[4], o[5]);
+            w.w = pack_bf16x2(o[6], o[7]);
+            *dst = w;
+          }
+          fence_proxy_async();
+          named_bar_sync(bar_done, 128);
+          if (elected) {
+            tma_store_3d(&tm_y, stg + buf * kChunkBytes, t_tile * Cfg::kOutCols + c * 64, m_tile * kBlockM, b);
+            tma_store_commit();
+            tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
+            if (p.has_res) {
+              int ntile = tile, nc = c + 2;
+              if (i == CPG - 1) { ntile = tile + gridDim.x; nc = g; }
+              if (ntile < p.num_tiles) {
+                const int nr = ntile / p.m_tiles;
+                mbar_expect_tx(&rbar[buf ^ 1], kChunkBytes);
+                tma_load_3d(stg + (buf ^ 1) * kChunkBytes, &tm_res, &rbar[buf ^ 1],
+                            (nr % p.t_tiles) * Cfg::kOutCols + nc * 64, (ntile % p.m_tiles) * kBlockM,
+                            nr / p.t_tiles);
+              }
+            }
+          }
+        }
+      }
+      if (elected) tma_store_wait_all<0>();
+    } else {
+      // fp32 NCW direct store, bias only; group g owns columns [g*BLOCK_N/2, (g+1)*BLOCK_N/2)
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+        const int m_tile = tile % p.m_tiles;
+        const int r = tile / p.m_tiles;
+        const int t_tile = r % p.t_tiles;
+        const int b = r / p.t_tiles;
+        const int accbuf = iter & 1;
+        const int ch = m_tile * kBlockM + row;
+        const bool live = ch < p.C_out;
+        const float bias = live ? __ldg(p.shift + ch) : 0.0f;
+        float* yrow = p.y32 + (static_cast<long long>(b) * p.C_out + (live ? ch : 0)) * p.y32_pitch;
+        mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          const int col = g * (BLOCK_N / 2) + cc * 32;
+          uint32_t v[32];
+          tmem_ld32(lane_addr + accbuf * (N_ACC * BLOCK_N) + col, v);
+          tmem_ld_wait();
+          if (cc == BLOCK_N / 64 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[accbuf]);
+          }
+          if (live) {
+            const long long t0 = static_cast<long long>(t_tile) * BLOCK_N + col;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              if (t0 + 4 * k4 < p.y32_pitch) {
+                float4 o;
+                o.x = __uint_as_float(v[4 * k4 + 0]) + bias;
+                o.y = __uint_as_float(v[4 * k4 + 1]) + bias;
+                o.z = __uint_as_float(v[4 * k4 + 2]) + bias;
+                o.w = __uint_as_float(v[4 * k4 + 3]) + bias;
+                *reinterpret_cast<float4*>(yrow + t0 + 4 * k4) = o;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
+                       const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
+  auto kern = conv_gemm_kernel<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V100_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured_dev = dev;
+  }
+  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tw, tx, ty, tr, p);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int pick_block_n(int T) {
+  const int pad256 = (T + 255) / 256 * 256, pad128 = (T + 127) / 128 * 128;
+  return pad128 < pad256 ? 128 : 256;
+}
+
+static int check_ncw(const void* p, int64_t pitch, int T, const char* what) {
+  if (p == nullptr) return fail(V100_E_INVALID, "%s: null pointer", what);
+  if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return fail(V100_E_INVALID, "%s: base not 16-byte aligned", what);
+  if (pitch < T || (pitch & 7) != 0) return fail(V100_E_INVALID, "%s: pitch %lld must be >= T=%d and a multiple of 8", what, (long long)pitch, T);
+  return 0;
+}
+
+int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
+                 const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act,
+                 cudaStream_t stream) {
+  if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "conv1x1: non-positive size");
+  if (C_in % 8 != 0) return fail(V100_E_UNSUPPORTED, "conv1x1: C_in=%d must be a multiple of 8", C_in);
+  if (shift == nullptr || W == nullptr) return fail(V100_E_INVALID, "conv1x1: null W/shift");
+  if (int e = check_ncw(x, x_pitch, T, "conv1x1 x")) return e;
+  if (int e = check_ncw(y, y_pitch, T, "conv1x1 y")) return e;
+  if (res != nullptr) if (int e = check_ncw(res, y_pitch, T, "conv1x1 res")) return e;
+  const int bn = pick_block_n(T);
+  CUtensorMap tw, tx, ty, tr;
+  if (int e = make_tmap_2d(&tw, W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&ty, y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tr, res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
+  GemmParams p{};
+  p.C_out = C_out; p.C_in = C_in; p.B = B;
+  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
+  p.t_tiles = (T + bn - 1) / bn;
+  p.num_tiles = p.m_tiles * p.t_tiles * B;
+  p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
+  p.n_taps = 1; p.tap_shift[0] = 0; p.tap_acc[0] = 0;
+  p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr;
+  if (bn == 256) return launch_gemm<256, 1, OUT_BF16, 3>(tw, tx, ty, tr, p, stream);
+  return launch_gemm<128, 1, OUT_BF16, 4>(tw, tx, ty, tr, p, stream);
+}
+
+int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
+                   int B, int C_in, int C_out, int T, cudaStream_t stream) {
+  if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "conv1x1_f32out: non-positive size");
+  if (C_in % 8 != 0) return fail(V100_E_UNSUPPORTED, "conv1x1_f32out: C_in=%d must be a multiple of 8", C_in);
+  if (bias == nullptr || W == nullptr || y == nullptr) return fail(V100_E_INVALID, "conv1x1_f32out: null pointer");
+  if (int e = check_ncw(x, x_pitch, T, "conv1x1_f32out x")) return e;
+  if (y_pitch < T || (y_pitch & 3) != 0 || (reinterpret_cast<uintptr_t>(y) & 15) != 0)
+    return fail(V100_E_INVALID, "conv1x1_f32out: y pitch must be >= T and a multiple of 4, base 16B aligned");
+  const int bn = pick_block_n(T);
+  CUtensorMap tw, tx;
+  if (int e = make_tmap_2d(&tw, W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  GemmParams p{};
+  p.C_out = C_out; p.C_in = C_in; p.B = B;
+  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
+  p.t_tiles = (T + bn - 1) / bn;
+  p.num_tiles = p.m_tiles * p.t_tiles * B;
+  p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
+  p.n_taps = 1; p.tap_shift[0] = 0; p.tap_acc[0] = 0;
+  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
+  p.y32 = y; p.y32_pitch = y_pitch;
+  if (bn == 256) return launch_gemm<256, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
+  return launch_gemm<128, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
+}
+
+int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* y,
+                              int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream) {
+  if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "convtranspose: non-positive size");
+  if (C_in % 64 != 0) return fail(V100_E_UNSUPPORTED, "convtranspose: C_in=%d must be a multiple of 64", C_in);
+  if (bias == nullptr || Wp == nullptr) return fail(V100_E_INVALID, "convtranspose: null W/bias");
+  const int T_out = 2 * T - 1;
+  if (int e = check_ncw(x, x_pitch, T, "convtranspose x")) return e;
+  if (int e = check_ncw(y, y_pitch, T_out, "convtranspose y")) return e;
+  CUtensorMap tw, tx, ty;
+  if (int e = make_tmap_2d(&tw, Wp, int64_t(C_in) * 5, C_out, int64_t(C_in) * 5 * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&ty, y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
+  GemmParams p{};
+  p.C_out = C_out; p.C_in = C_in; p.B = B;
+  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
+  p.t_tiles = (T + 127) / 128;
+  p.num_tiles = p.m_tiles * p.t_tiles * B;
+  p.k_blocks = C_in / kBlockK;
+  // y[co][o] = b[co] + sum_{ci,k,t: o = 2t - 2 + k} x[ci][t] W[ci][co][k]   (tts.py:22, stride 2, padding 2)
+  //   o = 2j   : (k,t) = (0,j+1) (2,j) (4,j-1)   -> accumulator 0
+  //   o = 2j+1 : (k,t) = (1,j+1) (3,j)           -> accumulator 1
+  p.n_taps = 5;
+  const int shifts[5] = {+1, +1, 0, 0, -1};
+  const int accs[5] = {0, 1, 0, 1, 0};
+  for (int i = 0; i < 5; ++i) { p.tap_shift[i] = shifts[i]; p.tap_acc[i] = accs[i]; }
+  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
+  return launch_gemm<128, 2, OUT_BF16, 4>(tw, tx, ty, ty, p, stream);
+}
+
+}  // namespace v100

@@ -1,0 +1,192 @@
+// Depthwise Conv1d + folded BatchNorm + ReLU6 on NCW bf16 activations.
+//
+// Two kernels:
+//  * dw_mma_kernel (stride 1, the hot one).  With k up to 83 taps the depthwise stage of
+//    ConvVoiceEncoder costs 72 MFLOP per audio-second -- on fp32 CUDA cores that is ~2.5x MORE time
+//    than its HBM traffic, so the FIR is evaluated on the tensor cores instead: for one channel,
+//        out[t0 + 8m + n] = sum_q sum_kk  X_q[m][kk] * W_q[kk][n],     m<16, n<8, kk<16
+//        X_q[m][kk] = x[t0 - p + 8(m+2q) + kk - d]      (rows are 16-byte shifts of the time series)
+//        W_q[kk][n] = w[16q + kk - n - d]               (a Toeplitz block of the filter, zero outside)
+//    i.e. Q = ceil((k+7+d)/16) mma.sync.m16n8k16 (bf16 x bf16 -> fp32) per 128 outputs.  The Toeplitz
+//    blocks live in registers for the whole row; the A fragments are plain coalesced 32-bit shared
+//    loads of the staged row (fragment word index = lane + 8q + {0,4,32,36}), and the D fragment is
+//    128 consecutive outputs, stored coalesced.  One warp per (batch, channel) row, 8 rows per CTA.
+//  * dw_simt_kernel: any stride / any k, plain CUDA cores.  Used for the stride-2 first block
+//    (0.4 % of the depthwise FLOPs) and exported for cross-checking.
+#include "common.cuh"
+#include "host.h"
+
+namespace v100 {
+
+constexpr int kDwChunk = 1024;            // outputs per CTA along time (8 mma tiles)
+constexpr int kDwRow = kDwChunk + 128;    // staged inputs per row (halo <= 48 left, <= 93 right)
+constexpr int kDwWarps = 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kDwWarps * 32)
+dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
+              const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+              long long y_pitch, int C, int T, int k, int act) {
+  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][kDwRow];
+  __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 8];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * kDwWarps + warp;
+  const int b = blockIdx.z;
+  const int tc0 = blockIdx.x * kDwChunk;
+  const int p = (k - 1) >> 1;
+  const int pl8 = (p + 7) & ~7;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
+  const int e = pl8 - p;
+  const int eh = e >> 1, d = e & 1;
+  __nv_bfloat16* xs = xs_all[warp];
+  __nv_bfloat16* ws = ws_all[warp];
+  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
+
+  // stage the row segment [tc0 - pl8, tc0 - pl8 + kDwRow) with zeros outside [0, T)
+  const int tcA = tc0 - pl8;
+#pragma unroll
+  for (int v = lane; v < kDwRow / 8; v += 32) {
+    const int t = tcA + v * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < T) {
+      val = *reinterpret_cast<const uint4*>(xrow + t);
+      if (t + 8 > T) {  // straddles the end of the clip: the pitch padding is not data
+        uint32_t* u = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (t + i >= T) u[i >> 1] &= (i & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+      }
+    }
+    *reinterpret_cast<uint4*>(xs + v * 8) = val;
+  }
+  // zero-extended filter: ws[8 + i] = w[i - d] for 0 <= i - d < k
+  for (int i = lane; i < 16 * Q + 8; i += 32) {
+    const int j = i - 8 - d;
+    ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
+  }
+  __syncwarp();
+
+  const int g = lane >> 2, tg = lane & 3;
+  uint32_t bf0[Q], bf1[Q];
+  {
+    const unsigned short* wsu = reinterpret_cast<const unsigned short*>(ws);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int i0 = 8 + 16 * q + 2 * tg - g;
+      bf0[q] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);
+      bf1[q] = uint32_t(wsu[i0 + 8]) | (uint32_t(wsu[i0 + 9]) << 16);
+    }
+  }
+  const float sc = scale ? scale[c] : 1.0f;
+  const float sh = shift[c];
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + eh + lane;
+  __nv_bfloat16* yrow = y + (static_cast<long long>(b) * C + c) * y_pitch;
+
+  const int n_tiles = min(kDwChunk / 128, (T - tc0 + 127) / 128);
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const uint32_t* xt = xw + tile * 64;
+    uint32_t A0[Q + 4], A2[Q + 4];
+#pragma unroll
+    for (int q = 0; q < Q + 4; ++q) {
+      A0[q] = xt[8 * q];
+      A2[q] = xt[8 * q + 4];
+    }
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int q = 0; q < Q; ++q) mma_bf16_16816(acc, A0[q], A0[q + 4], A2[q], A2[q + 4], bf0[q], bf1[q]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[i] = fmaf(acc[i], sc, sh);
+      if (act == V100_ACT_RELU6) acc[i] = fminf(fmaxf(acc[i], 0.0f), 6.0f);
+    }
+    const int t = tc0 + tile * 128 + 2 * lane;
+    if (t < T) *reinterpret_cast<uint32_t*>(yrow + t) = pack_bf16x2(acc[0], acc[1]);
+    if (t + 64 < T) *reinterpret_cast<uint32_t*>(yrow + t + 64) = pack_bf16x2(acc[2], acc[3]);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+dw_simt_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
+               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+               long long y_pitch, int C, int T_in, int T_out, int k, int stride, int act) {
+  const int c = blockIdx.y, b = blockIdx.z;
+  const int o0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  if (o0 >= T_out) return;
+  const int p = (k - 1) >> 1;
+  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
+  const __nv_bfloat16* wrow = w + static_cast<long long>(c) * k;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = 0; j < k; ++j) {
+    const float wj = __bfloat162float(wrow[j]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = (o0 + r) * stride + j - p;
+      if (i >= 0 && i < T_in) acc[r] = fmaf(wj, __bfloat162float(xrow[i]), acc[r]);
+    }
+  }
+  const float sc = scale ? scale[c] : 1.0f, sh = shift[c];
+  uint32_t o[4];
+#pragma unroll
+  for (int r = 0; r < 8; r += 2) {
+    float v0 = fmaf(acc[r], sc, sh), v1 = fmaf(acc[r + 1], sc, sh);
+    if (act == V100_ACT_RELU6) {
+      v0 = fminf(fmaxf(v0, 0.0f), 6.0f);
+      v1 = fminf(fmaxf(v1, 0.0f), 6.0f);
+    }
+    o[r >> 1] = pack_bf16x2(v0, v1);
+  }
+  // o0 % 8 == 0 and pitch % 8 == 0, so the 16-byte store stays inside the row's pitch
+  *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * C + c) * y_pitch + o0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int Q>
+static void launch_dw_mma(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
+                          void* y, int64_t y_pitch, int B, int C, int T, int k, int act, cudaStream_t stream) {
+  dim3 grid((T + kDwChunk - 1) / kDwChunk, C / kDwWarps, B);
+  dw_mma_kernel<Q><<<grid, kDwWarps * 32, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<const __nv_bfloat16*>(w), scale, shift,
+      static_cast<__nv_bfloat16*>(y), y_pitch, C, T, k, act);
+}
+
+int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
+                  int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int force_simt,
+                  cudaStream_t stream) {
+  if (B <= 0 || C <= 0 || T_in <= 0 || k <= 0 || stride <= 0) return fail(V100_E_INVALID, "dwconv: non-positive size");
+  if ((k & 1) == 0) return fail(V100_E_UNSUPPORTED, "dwconv: kernel size %d must be odd", k);
+  if (x == nullptr || w == nullptr || shift == nullptr || y == nullptr) return fail(V100_E_INVALID, "dwconv: null pointer");
+  const int T_out = (T_in - 1) / stride + 1;
+  if (x_pitch < T_in || (x_pitch & 7) || y_pitch < T_out || (y_pitch & 7) ||
+      (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(V100_E_INVALID, "dwconv: pitches must be multiples of 8 and >= T, bases 16-byte aligned");
+  if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
+  const int p = (k - 1) / 2;
+  const int d = (((p + 7) & ~7) - p) & 1;
+  const int Q = (k + 7 + d + 15) / 16;
+  if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 6) {
+    switch (Q) {
+      case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 2: launch_dw_mma<2>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 3: launch_dw_mma<3>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 4: launch_dw_mma<4>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 5: launch_dw_mma<5>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      default: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+    }
+  } else {
+    dim3 grid((T_out + 1023) / 1024, C, B);
+    dw_simt_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                             static_cast<const __nv_bfloat16*>(w), scale, shift,
+                                             static_cast<__nv_bfloat16*>(y), y_pitch, C, T_in, T_out, k, stride, act);
+  }
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace v100

@@ -1,0 +1,209 @@
+// Small layout / head-tail kernels around the GEMMs (all HBM-trivial next to the conv stack).
+#include "common.cuh"
+#include "host.h"
+
+#include <algorithm>
+
+namespace v100 {
+
+// fp32 [B][T][C] -> bf16 NCW [B][C][pitch] through a 32x32 shared tile (AudioToTextCTC.forward's transpose).
+__global__ void __launch_bounds__(256)
+ntc_to_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int C, long long y_pitch) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    tile[r][tx] = (t < T && c < C) ? x[(static_cast<long long>(b) * T + t) * C + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    if (c < C && t < T) y[(static_cast<long long>(b) * C + c) * y_pitch + t] = __float2bfloat16(tile[tx][r]);
+  }
+}
+
+int ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, cudaStream_t stream) {
+  if (x == nullptr || y == nullptr) return fail(V100_E_INVALID, "ntc_to_ncw: null pointer");
+  if (B <= 0 || T <= 0 || C <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "ntc_to_ncw: bad sizes");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  ntc_to_ncw_kernel<<<grid, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), T, C, y_pitch);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Dense NCW casts between the caller's fp32 [B][C][T] tensors and the pitched bf16 working layout
+// (entry/exit of ConvVoiceEncoder.forward / VoiceDecoder.forward when used as stand-alone modules).
+__global__ void __launch_bounds__(256)
+ncw_cast_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb, float* __restrict__ yf,
+                __nv_bfloat16* __restrict__ yb, long long rows, int T, long long pitch) {
+  const long long total = rows * T;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long r = i / T;
+    const int t = int(i - r * T);
+    if (yb) yb[r * pitch + t] = __float2bfloat16(xf[i]);
+    else yf[i] = __bfloat162float(xb[r * pitch + t]);
+  }
+}
+
+int ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, cudaStream_t stream) {
+  if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || T <= 0 || y_pitch < T)
+    return fail(V100_E_INVALID, "ncw_f32_to_bf16: bad arguments");
+  const long long rows = static_cast<long long>(B) * C;
+  const int grid = int(std::min<long long>((rows * T + 255) / 256, 148LL * 16));
+  ncw_cast_kernel<<<grid, 256, 0, stream>>>(x, nullptr, nullptr, static_cast<__nv_bfloat16*>(y), rows, T, y_pitch);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, cudaStream_t stream) {
+  if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || T <= 0 || x_pitch < T)
+    return fail(V100_E_INVALID, "ncw_bf16_to_f32: bad arguments");
+  const long long rows = static_cast<long long>(B) * C;
+  const int grid = int(std::min<long long>((rows * T + 255) / 256, 148LL * 16));
+  ncw_cast_kernel<<<grid, 256, 0, stream>>>(nullptr, static_cast<const __nv_bfloat16*>(x), y, nullptr, rows, T, x_pitch);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// y[b][c][t] = table[ids[b][t]][c]; one thread = one channel x 8 time steps (16-byte store).
+__global__ void __launch_bounds__(256)
+embedding_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                 __nv_bfloat16* __restrict__ y, long long y_pitch, int T, int V, int C) {
+  const int b = blockIdx.z;
+  const int c = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int t0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
+  if (c >= C || t0 >= T) return;
+  const unsigned short* tab = reinterpret_cast<const unsigned short*>(table);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    unsigned short v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = t0 + i + h;
+      long long id = t < T ? ids[static_cast<long long>(b) * T + t] : 0;
+      id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+      v[h] = t < T ? tab[id * C + c] : 0;
+    }
+    o[i >> 1] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
+  }
+  *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * C + c) * y_pitch + t0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+int embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
+                       cudaStream_t stream) {
+  if (ids == nullptr || table == nullptr || y == nullptr) return fail(V100_E_INVALID, "embedding: null pointer");
+  if (B <= 0 || T <= 0 || V <= 0 || C <= 0 || B > 65535) return fail(V100_E_INVALID, "embedding: bad sizes");
+  if (y_pitch < T || (y_pitch & 7) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(V100_E_INVALID, "embedding: pitch must be >= T and a multiple of 8, base 16B aligned");
+  dim3 grid((T + 255) / 256, (C + 7) / 8, B);
+  embedding_kernel<<<grid, 256, 0, stream>>>(ids, static_cast<const __nv_bfloat16*>(table),
+                                             static_cast<__nv_bfloat16*>(y), y_pitch, T, V, C);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 NCW [B][V][pitch] -> logits [B][T][V] (optional) + greedy tokens (first maximal index).
+__global__ void __launch_bounds__(128)
+ctc_finalize_kernel(const float* __restrict__ y, long long pitch, float* __restrict__ logits,
+                    int64_t* __restrict__ tokens, int V, int T) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T) return;
+  const float* col = y + static_cast<long long>(b) * V * pitch + t;
+  float best = col[0];
+  int arg = 0;
+  float* lrow = logits ? logits + (static_cast<long long>(b) * T + t) * V : nullptr;
+  if (lrow) lrow[0] = best;
+  for (int v = 1; v < V; ++v) {
+    const float x = col[static_cast<long long>(v) * pitch];
+    if (lrow) lrow[v] = x;
+    if (x > best) { best = x; arg = v; }
+  }
+  tokens[static_cast<long long>(b) * T + t] = arg;
+}
+
+int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* tokens, int B, int V, int T,
+                 cudaStream_t stream) {
+  if (y_ncw == nullptr || tokens == nullptr) return fail(V100_E_INVALID, "ctc_finalize: null pointer");
+  if (B <= 0 || V <= 0 || T <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "ctc_finalize: bad sizes");
+  dim3 grid((T + 127) / 128, B);
+  ctc_finalize_kernel<<<grid, 128, 0, stream>>>(y_ncw, y_pitch, logits, tokens, V, T);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// fp32 NCW [B][C][pitch] -> [B][T][C] through a 32x32 tile.
+__global__ void __launch_bounds__(256)
+ncw_to_ntc_kernel(const float* __restrict__ y, long long pitch, float* __restrict__ out, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    tile[r][tx] = (c < C && t < T) ? y[(static_cast<long long>(b) * C + c) * pitch + t] : 0.0f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    if (t < T && c < C) out[(static_cast<long long>(b) * T + t) * C + c] = tile[tx][r];
+  }
+}
+
+int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream) {
+  if (y_ncw == nullptr || out == nullptr) return fail(V100_E_INVALID, "ncw_to_ntc: null pointer");
+  if (B <= 0 || C <= 0 || T <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "ncw_to_ntc: bad sizes");
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  ncw_to_ntc_kernel<<<grid, 256, 0, stream>>>(y_ncw, y_pitch, out, C, T);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// WORLD head tail.  Channel order of the decoder output (tts.py:160-167,181-190):
+//   0 = hasf0 logit, 1 = f0, 2..258 = logspc[257], 259 = codeap.
+// mean/std index: 0 = f0, 1..257 = logspc, 258 = codeap.
+__global__ void __launch_bounds__(256)
+world_finalize_kernel(const float* __restrict__ y, long long pitch, const float* __restrict__ mean,
+                      const float* __restrict__ stdv, float* __restrict__ hasf0, float* __restrict__ f0,
+                      float* __restrict__ logspc, float* __restrict__ codeap, int T, int unnormalize) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  constexpr int C = 260;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    float v = 0.0f;
+    if (c < C && t < T) {
+      v = y[(static_cast<long long>(b) * C + c) * pitch + t];
+      if (unnormalize && c >= 1) v = fmaf(stdv[c - 1], v, mean[c - 1]);
+      if (unnormalize && c == 1 && y[(static_cast<long long>(b) * C) * pitch + t] < 0.0f) v = 0.0f;
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    if (t >= T || c >= C) continue;
+    const float v = tile[tx][r];
+    const long long bt = static_cast<long long>(b) * T + t;
+    if (c == 0) { if (hasf0) hasf0[bt] = v; }
+    else if (c == 1) f0[bt] = v;
+    else if (c < 259) logspc[bt * 257 + (c - 2)] = v;
+    else codeap[bt] = v;
+  }
+}
+
+int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* stdv, float* hasf0, float* f0,
+                   float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream) {
+  if (y_ncw == nullptr || f0 == nullptr || logspc == nullptr || codeap == nullptr)
+    return fail(V100_E_INVALID, "world_finalize: null pointer");
+  if (unnormalize && (mean == nullptr || stdv == nullptr)) return fail(V100_E_INVALID, "world_finalize: null mean/std");
+  if (B <= 0 || T <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "world_finalize: bad sizes");
+  dim3 grid((T + 31) / 32, (260 + 31) / 32, B);
+  world_finalize_kernel<<<grid, 256, 0, stream>>>(y_ncw, y_pitch, mean, stdv, hasf0, f0, logspc, codeap, T, unnormalize);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace v100

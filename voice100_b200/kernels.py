@@ -1,0 +1,179 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and the current stream only.
+
+All activations are `Ncw` objects: bf16 (or fp32 for head outputs) tensors of shape [B, C, pitch] whose
+first `T` columns are data (pitch = T rounded up to 8 so every row starts 16-byte aligned, which is
+what TMA and the 16-byte vector accesses in the kernels require).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU6 = 0, 1
+MEL_LOG_BF16_NCW, MEL_LOG_F32_NTC, MEL_POWER_F32_NCW = 0, 1, 2
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def pitch_of(T: int, mult: int = 8) -> int:
+    return (T + mult - 1) // mult * mult
+
+
+@dataclass
+class Ncw:
+    data: torch.Tensor  # [B, C, pitch]
+    T: int
+
+    @property
+    def B(self):
+        return self.data.shape[0]
+
+    @property
+    def C(self):
+        return self.data.shape[1]
+
+    @property
+    def pitch(self):
+        return self.data.shape[2]
+
+    def valid(self) -> torch.Tensor:
+        return self.data[:, :, : self.T]
+
+
+def empty_ncw(B, C, T, device, dtype=torch.bfloat16) -> Ncw:
+    return Ncw(torch.empty((B, C, pitch_of(T)), device=device, dtype=dtype), T)
+
+
+def _cuda(t: torch.Tensor, dtype=None):
+    if not t.is_cuda:
+        raise _lib.V100Error("voice100_b200 kernels need CUDA tensors (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.V100Error(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.V100Error("expected a contiguous tensor")
+    return t
+
+
+def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: int, mode: int):
+    """wav fp32 [B, L]; lengths int32 [B] (device); fb = (start, count, off, w) device tensors."""
+    _cuda(wav, torch.float32), _cuda(lengths, torch.int32)
+    B = wav.shape[0]
+    if mode == MEL_LOG_BF16_NCW:
+        out = empty_ncw(B, 64, T, wav.device)
+        optr, pitch = out.data.data_ptr(), out.pitch
+    elif mode == MEL_POWER_F32_NCW:
+        out = Ncw(torch.empty((B, 64, pitch_of(T, 4)), device=wav.device, dtype=torch.float32), T)
+        optr, pitch = out.data.data_ptr(), out.pitch
+    else:
+        out = torch.empty((B, T, 64), device=wav.device, dtype=torch.float32)
+        optr, pitch = out.data_ptr(), 64
+    _lib.call("v100_logmel", wav.data_ptr(), lengths.data_ptr(), B, wav.stride(0), fb[0].data_ptr(),
+              fb[1].data_ptr(), fb[2].data_ptr(), fb[3].data_ptr(), float(log_offset), optr, T, pitch, mode,
+              _stream())
+    return out
+
+
+def ntc_f32_to_ncw(x: torch.Tensor) -> Ncw:
+    _cuda(x, torch.float32)
+    B, T, Cc = x.shape
+    y = empty_ncw(B, Cc, T, x.device)
+    _lib.call("v100_ntc_f32_to_ncw_bf16", x.data_ptr(), y.data.data_ptr(), B, T, Cc, y.pitch, _stream())
+    return y
+
+
+def ncw_from_f32(x: torch.Tensor) -> Ncw:
+    _cuda(x, torch.float32)
+    B, Cc, T = x.shape
+    y = empty_ncw(B, Cc, T, x.device)
+    _lib.call("v100_ncw_f32_to_bf16", x.data_ptr(), y.data.data_ptr(), y.pitch, B, Cc, T, _stream())
+    return y
+
+
+def ncw_to_f32(x: Ncw) -> torch.Tensor:
+    y = torch.empty((x.B, x.C, x.T), device=x.data.device, dtype=torch.float32)
+    _lib.call("v100_ncw_bf16_to_f32", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, _stream())
+    return y
+
+
+def conv1x1(x: Ncw, W: torch.Tensor, scale, shift, act: int, res: Ncw = None) -> Ncw:
+    C_out, C_in = W.shape
+    assert C_in == x.C, (C_in, x.C)
+    y = empty_ncw(x.B, C_out, x.T, x.data.device)
+    if res is not None:
+        assert res.data.shape == y.data.shape and res.T == x.T
+    _lib.call("v100_conv1x1_bf16", x.data.data_ptr(), x.pitch, W.data_ptr(), _ptr(scale), shift.data_ptr(),
+              None if res is None else res.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, C_in, C_out, x.T,
+              act, _stream())
+    return y
+
+
+def conv1x1_f32(x: Ncw, W: torch.Tensor, bias: torch.Tensor) -> Ncw:
+    C_out, C_in = W.shape
+    assert C_in == x.C
+    y = Ncw(torch.empty((x.B, C_out, x.pitch), device=x.data.device, dtype=torch.float32), x.T)
+    _lib.call("v100_conv1x1_f32out", x.data.data_ptr(), x.pitch, W.data_ptr(), bias.data_ptr(), y.data.data_ptr(),
+              y.pitch, x.B, C_in, C_out, x.T, _stream())
+    return y
+
+
+def dwconv(x: Ncw, w: torch.Tensor, scale, shift, k: int, stride: int, act: int, simt: bool = False) -> Ncw:
+    T_out = (x.T - 1) // stride + 1
+    y = empty_ncw(x.B, x.C, T_out, x.data.device)
+    _lib.call("v100_dwconv1d_bf16_simt" if simt else "v100_dwconv1d_bf16", x.data.data_ptr(), x.pitch,
+              w.data_ptr(), _ptr(scale), shift.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, k, stride,
+              act, _stream())
+    return y
+
+
+def convtranspose_k5s2(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor) -> Ncw:
+    C_out = Wp.shape[0]
+    assert Wp.shape[1] == 5 * x.C
+    y = empty_ncw(x.B, C_out, 2 * x.T - 1, x.data.device)
+    _lib.call("v100_convtranspose1d_k5s2_bf16", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
+              y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, _stream())
+    return y
+
+
+def embedding_ncw(ids: torch.Tensor, table: torch.Tensor) -> Ncw:
+    _cuda(ids, torch.int64)
+    B, T = ids.shape
+    V, Cc = table.shape
+    y = empty_ncw(B, Cc, T, ids.device)
+    _lib.call("v100_embedding_ncw_bf16", ids.data_ptr(), table.data_ptr(), y.data.data_ptr(), y.pitch, B, T, V, Cc,
+              _stream())
+    return y
+
+
+def ctc_finalize(y: Ncw, want_logits: bool = True):
+    B, V, T = y.B, y.C, y.T
+    logits = torch.empty((B, T, V), device=y.data.device, dtype=torch.float32) if want_logits else None
+    tokens = torch.empty((B, T), device=y.data.device, dtype=torch.int64)
+    _lib.call("v100_ctc_finalize", y.data.data_ptr(), y.pitch, _ptr(logits), tokens.data_ptr(), B, V, T, _stream())
+    return logits, tokens
+
+
+def world_finalize(y: Ncw, mean, std, unnormalize: bool):
+    B, T, dev = y.B, y.T, y.data.device
+    assert y.C == 260
+    hasf0 = torch.empty((B, T), device=dev, dtype=torch.float32)
+    f0 = torch.empty((B, T), device=dev, dtype=torch.float32)
+    logspc = torch.empty((B, T, 257), device=dev, dtype=torch.float32)
+    codeap = torch.empty((B, T, 1), device=dev, dtype=torch.float32)
+    _lib.call("v100_world_finalize", y.data.data_ptr(), y.pitch, _ptr(mean), _ptr(std), hasf0.data_ptr(),
+              f0.data_ptr(), logspc.data_ptr(), codeap.data_ptr(), B, T, 1 if unnormalize else 0, _stream())
+    return hasf0, f0, logspc, codeap
+
+
+def ncw_f32_to_ntc(y: Ncw) -> torch.Tensor:
+    out = torch.empty((y.B, y.T, y.C), device=y.data.device, dtype=torch.float32)
+    _lib.call("v100_ncw_f32_to_ntc", y.data.data_ptr(), y.pitch, out.data_ptr(), y.B, y.C, y.T, _stream())
+    return out

@@ -1,0 +1,154 @@
+"""TTS: TextToAlignTextModel and AlignTextToAudioModel (VoiceDecoder) on the libv100 kernels.
+
+Interface mirrors voice100/models/tts.py:13-29,67-110,152-201 and WORLDNorm.unnormalize
+(voice100/models/_layers_v1.py:96-138).  Inference only.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+from torch import nn
+
+from . import kernels as K
+from ._lib import V100Error
+from .blocks import InvertedResidualParams, PreparedCache, require_eval_cuda, run_inverted_residual
+from .synth import ALIGN_KERNELS, VOICE_DECODER_POST_KERNELS, VOICE_DECODER_PRE_KERNELS
+
+__all__ = ["TextToAlignTextModel", "AlignTextToAudioModel", "VoiceDecoder", "WORLDNorm"]
+
+
+def _head(conv: nn.Conv1d):
+    return (conv.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(), conv.bias.detach().float().contiguous())
+
+
+class TextToAlignTextModel(nn.Module):
+    def __init__(self, vocab_size: int, hidden_size: int, learning_rate: float = 1e-3) -> None:
+        super().__init__()
+        self.hparams = dict(vocab_size=vocab_size, hidden_size=hidden_size, learning_rate=learning_rate)
+        self.embedding = nn.Embedding(vocab_size, hidden_size)
+        self.layers = nn.Sequential(
+            *[InvertedResidualParams(hidden_size, hidden_size, k) for k in ALIGN_KERNELS],
+            nn.Conv1d(hidden_size, 2, 1, bias=True))
+        self._prepared = PreparedCache(self, lambda: dict(
+            table=self.embedding.weight.detach().to(torch.bfloat16).contiguous(),
+            blocks=[self.layers[i].prepare() for i in range(4)], head=_head(self.layers[4])))
+        self.eval()
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """text int64 [B, L] -> fp32 [B, L, 2] = log(align + 1)."""
+        require_eval_cuda(self, x)
+        w = self._prepared.get()
+        h = K.embedding_ncw(x.contiguous(), w["table"])
+        for blk in w["blocks"]:
+            h = run_inverted_residual(h, blk)
+        return K.ncw_f32_to_ntc(K.conv1x1_f32(h, *w["head"]))
+
+    def align(self, text: torch.Tensor, align: torch.Tensor, head: int = 5, tail: int = 5) -> torch.Tensor:
+        """Host-side expansion of one utterance's tokens to 20 ms frames (tts.py:89-110): token i fills
+        frames [round(t + gap_i), round(t + gap_i + dur_i)), at least one; python round() semantics."""
+        assert text.dim() == 1 and align.dim() == 2
+        gaps = align.detach().cpu().tolist()
+        toks = text.detach().cpu().tolist()
+        total = head + int(torch.sum(align)) + tail
+        out = [0] * total
+        t = head
+        for (gap, dur), tok in zip(gaps, toks):
+            t += gap
+            s = round(t)
+            t += dur
+            e = round(t)
+            if s == e:
+                e = max(0, e + 1)
+            if e > total or s < 0:
+                raise IndexError("alignment runs past the aligned text (same failure as the reference)")
+            out[s:e] = [tok] * (e - s)
+        return torch.tensor(out, dtype=text.dtype)
+
+
+class VoiceDecoder(nn.Module):
+    def __init__(self, hidden_size: int, out_channels: int) -> None:
+        super().__init__()
+        half = hidden_size // 2
+        self.layers = nn.Sequential(
+            *[InvertedResidualParams(hidden_size, hidden_size, k) for k in VOICE_DECODER_PRE_KERNELS],
+            nn.ConvTranspose1d(hidden_size, half, kernel_size=5, padding=2, stride=2),
+            *[InvertedResidualParams(half, half, k) for k in VOICE_DECODER_POST_KERNELS],
+            nn.Conv1d(half, out_channels, 1, bias=True))
+        self._prepared = PreparedCache(self, self._prepare)
+
+    def _prepare(self):
+        up = self.layers[4]
+        c_in, c_out, _ = up.weight.shape
+        # Wp[co][tap*C_in + ci] = weight[ci][co][tap]  (ConvTranspose1d stores [C_in, C_out, k])
+        wp = up.weight.detach().permute(1, 2, 0).reshape(c_out, 5 * c_in).to(torch.bfloat16).contiguous()
+        return dict(pre=[self.layers[i].prepare() for i in range(4)], wp=wp,
+                    up_bias=up.bias.detach().float().contiguous(),
+                    post=[self.layers[i].prepare() for i in range(5, 8)], head=_head(self.layers[8]))
+
+    def run(self, x: K.Ncw) -> K.Ncw:
+        """bf16 Ncw [B, H, T] -> fp32 Ncw [B, out_channels, 2T-1]."""
+        w = self._prepared.get()
+        for blk in w["pre"]:
+            x = run_inverted_residual(x, blk)
+        x = K.convtranspose_k5s2(x, w["wp"], w["up_bias"])
+        for blk in w["post"]:
+            x = run_inverted_residual(x, blk)
+        return K.conv1x1_f32(x, *w["head"])
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        require_eval_cuda(self, x)
+        return self.run(K.ncw_from_f32(x.float().contiguous())).valid().contiguous()
+
+
+class WORLDNorm(nn.Module):
+    """Per-feature mean/std of the WORLD parameters (_layers_v1.py:96-117); only `unnormalize` is on the
+    inference path and it is fused into v100_world_finalize."""
+
+    def __init__(self, logspc_size: int, codeap_size: int):
+        super().__init__()
+        mk = lambda v, n: nn.Parameter(torch.full([n], v), requires_grad=False)
+        self.f0_std, self.f0_mean = mk(1.0, 1), mk(0.0, 1)
+        self.logspc_std, self.logspc_mean = mk(1.0, logspc_size), mk(0.0, logspc_size)
+        self.codeap_std, self.codeap_mean = mk(1.0, codeap_size), mk(0.0, codeap_size)
+
+    def packed(self):
+        mean = torch.cat([self.f0_mean, self.logspc_mean, self.codeap_mean]).detach().float().contiguous()
+        std = torch.cat([self.f0_std, self.logspc_std, self.codeap_std]).detach().float().contiguous()
+        return mean, std
+
+
+class AlignTextToAudioModel(nn.Module):
+    def __init__(self, vocab_size: int, hidden_size: int, learning_rate: float = 1e-3, use_mcep: bool = False) -> None:
+        super().__init__()
+        if use_mcep:
+            raise V100Error("use_mcep=True (25 mel-cepstrum outputs) is not on the accelerated path")
+        self.hparams = dict(vocab_size=vocab_size, hidden_size=hidden_size, learning_rate=learning_rate,
+                            use_mcep=use_mcep)
+        self.hidden_size, self.vocab_size = hidden_size, vocab_size
+        self.sample_rate, self.n_fft = 16000, 512
+        self.hasf0_size, self.f0_size, self.logspc_size, self.codeap_size = 1, 1, 257, 1
+        self.audio_size = 260
+        self.embedding = nn.Embedding(vocab_size, hidden_size)
+        self.decoder = VoiceDecoder(hidden_size, self.audio_size)
+        self.norm = WORLDNorm(self.logspc_size, self.codeap_size)
+        self._prepared = PreparedCache(self, lambda: dict(
+            table=self.embedding.weight.detach().to(torch.bfloat16).contiguous(), norm=self.norm.packed()))
+        self.eval()
+
+    def _decode(self, aligntext: torch.Tensor) -> K.Ncw:
+        require_eval_cuda(self, aligntext)
+        w = self._prepared.get()
+        return self.decoder.run(K.embedding_ncw(aligntext.contiguous(), w["table"]))
+
+    def forward(self, aligntext: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """aligntext int64 [B, T] -> (hasf0_logits [B,T'], f0_hat [B,T'], logspc_hat [B,T',257],
+        codeap_hat [B,T',1]) normalised, T' = 2T-1."""
+        return K.world_finalize(self._decode(aligntext), None, None, False)
+
+    def predict(self, aligntext: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (f0 [B,T'], logspc [B,T',257], codeap [B,T',1]) un-normalised, f0 = 0 where unvoiced."""
+        y = self._decode(aligntext)
+        mean, std = self._prepared.get()["norm"]
+        _, f0, logspc, codeap = K.world_finalize(y, mean, std, True)
+        return f0, logspc, codeap
