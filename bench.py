@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the Voice100 ASR hot path: log-mel + ConvVoiceEncoder + CTC head + greedy argmax.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): ASR audio-seconds per second on `asr_en_base` (AudioToTextCTC(64,512,29,512)),
+256 utterances x 15 s of synthetic 16 kHz audio PER GPU (weak scaling: utterances are independent, so
+ranks share nothing on the data path; NCCL only reduces the timings).  One step = one pass of the whole
+path over one batch.  Prints ONE JSON line on rank 0.
+
+  value     device-resident inputs, CUDA-event timed, max over ranks.
+  e2e       same metric through AsrPipeline.transcribe_host: pinned HOST waveforms in, HOST tokens out,
+            H2D/D2H inside the timed region (copies pipelined against compute in utterance chunks).
+  roofline  the dominant kernel (tcgen05 conv GEMM) against the measured bf16 peak; `roofline_all`
+            lists every kernel class (depthwise and log-mel against the measured HBM copy bandwidth).
+  cpu_baseline / --impl reference
+            the CPU oracle (oracle/v100_oracle.py: the reference's arithmetic on torch CPU fp32, all host
+            threads) on a bounded sample of the same workload.  /root/reference itself is Python that
+            cannot travel to the GPU box; the oracle is pinned to it by tests/golden.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMPLE_RATE = 16000
+CLIP_SECONDS = 15
+BATCH_PER_GPU = 256
+MODEL = dict(audio_size=64, embed_size=512, vocab_size=29, hidden_size=512)
+WORKLOAD = "asr_en_base: AudioToTextCTC(64,512,29,512), 256 x 15 s synthetic 16 kHz audio per GPU"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithmic work per launch (SURVEY.md section 8d / DESIGN.md): bf16 activations = 2 B
+# --------------------------------------------------------------------------------------------------
+def asr_work_model(B, T_in, hidden, embed, vocab, audio_size=64):
+    """-> list of dicts (kind, flops, bytes) in launch order for one step."""
+    from voice100_b200.synth import asr_encoder_blocks
+    L = (T_in - 1) * 160  # samples per clip (frames = 1 + L//160)
+    work = [dict(kind="logmel", flops=0.0, bytes=4.0 * B * L + 2.0 * 64 * B * T_in)]
+    T = T_in
+    for ci, co, k, s, res in asr_encoder_blocks(audio_size, embed, hidden):
+        h = 4 * ci
+        M = B * T
+        work.append(dict(kind="gemm", flops=2.0 * M * ci * h, bytes=2.0 * M * (ci + h) + 2.0 * ci * h))
+        T_out = (T - 1) // s + 1
+        Mo = B * T_out
+        work.append(dict(kind="dwconv", flops=2.0 * k * h * Mo, bytes=2.0 * h * (M + Mo) + 2.0 * h * k))
+        work.append(dict(kind="gemm", flops=2.0 * Mo * h * co,
+                         bytes=2.0 * Mo * (h + co) + (2.0 * Mo * co if res else 0.0) + 2.0 * h * co))
+        T = T_out
+    M = B * T
+    work.append(dict(kind="gemm", flops=2.0 * M * embed * vocab, bytes=2.0 * M * embed + 4.0 * M * vocab))
+    work.append(dict(kind="ctc_finalize", flops=0.0, bytes=4.0 * M * vocab + 8.0 * M))
+    return work
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU while the timed region runs (nvidia-smi loop)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # "under load": the upper half of the samples (idle samples at either end drag the median down)
+        load = sm[len(sm) // 2:] if sm else []
+        return dict(sm_mhz=(load[len(load) // 2] if load else None), sm_max_mhz=(max(smax) if smax else None),
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_throughput(min_seconds=10.0, batch=8, max_reps=6):
+    """The CPU oracle on a bounded sample of the workload: `batch` x 15 s clips per pass, repeated until
+    `min_seconds` of CPU work has been timed.  -> (audio_s_per_s, threads, sample description)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import v100_oracle as orc
+    from voice100_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = orc.to_torch_sd(synth.asr_state_dict(**MODEL, seed=1234))
+    L = SAMPLE_RATE * CLIP_SECONDS
+    wav = torch.from_numpy(synth.noise_waveform(batch, L, seed=1234))
+
+    def one_pass():
+        with torch.no_grad():
+            audio, _ = orc.logmel_batch(wav, [L] * batch)
+            return orc.ctc_greedy(orc.asr_forward(audio, sd))
+
+    one_pass()  # warm-up
+    t_total, reps = 0.0, 0
+    while t_total < min_seconds and reps < max_reps:
+        t0 = time.perf_counter()
+        one_pass()
+        t_total += time.perf_counter() - t0
+        reps += 1
+    value = reps * batch * CLIP_SECONDS / t_total
+    return value, torch.get_num_threads(), f"{reps} passes of {batch} x {CLIP_SECONDS} s clips ({t_total:.1f} s of CPU work)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import v100_oracle as orc
+    from voice100_b200 import synth
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    batch = 8
+    sd = orc.to_torch_sd(synth.asr_state_dict(**MODEL, seed=1234))
+    L = SAMPLE_RATE * CLIP_SECONDS
+    wav = torch.from_numpy(synth.noise_waveform(batch, L, seed=1234))
+
+    def step():
+        with torch.no_grad():
+            audio, _ = orc.logmel_batch(wav, [L] * batch)
+            return orc.ctc_greedy(orc.asr_forward(audio, sd))
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = steps * batch * CLIP_SECONDS / dt
+    sample = f"each step = {batch} x {CLIP_SECONDS} s clips of the workload on {torch.get_num_threads()} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "asr_audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU (default: the metric's 256)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import voice100_b200 as v
+    from voice100_b200 import _lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the Voice100 hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    B = args.batch
+    L = SAMPLE_RATE * CLIP_SECONDS
+    T_in = 1 + L // 160
+
+    model = v.AudioToTextCTC(**MODEL)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(t)) for k, t in synth.asr_state_dict(**MODEL, seed=1234).items()})
+    model = model.to(dev).eval()
+    pipe = v.AsrPipeline(v.MelSpectrogramAudioTransform().to(dev), model)
+
+    # device-resident inputs: two rotating batches, each 245 MB (> the 126 MB L2), 0.1*N(0,1)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wavs = [0.1 * torch.randn((B, L), device=dev, generator=g) for _ in range(2)]
+    lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        pipe(wavs[i & 1], lengths)
+    n0 = _lib.stats["launches"]
+    pipe(wavs[0], lengths)
+    launches_per_step = _lib.stats["launches"] - n0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        tokens, out_len = pipe(wavs[i & 1], lengths)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    audio_seconds_per_step = world * B * CLIP_SECONDS
+    value = audio_seconds_per_step * K / (ms_max / 1e3)
+
+    # ---- per-kernel device times (separate pass, CUDA events around every launch) ----
+    work = asr_work_model(B, T_in, MODEL["hidden_size"], MODEL["embed_size"], MODEL["vocab_size"])
+    class Tracer:
+        def __init__(self):
+            self.ev = []
+
+        def before(self, name):
+            self._s = torch.cuda.Event(enable_timing=True)
+            self._s.record()
+
+        def after(self, name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append((name, self._s, e))
+
+    _lib.tracer = Tracer()
+    prof_steps = min(K, 5)
+    for i in range(prof_steps):
+        pipe(wavs[i & 1], lengths)
+    torch.cuda.synchronize()
+    ev, _lib.tracer = _lib.tracer.ev, None
+    per_launch = [0.0] * len(work)
+    assert len(ev) == prof_steps * len(work), (len(ev), len(work))
+    for i, (_, s, e) in enumerate(ev):
+        per_launch[i % len(work)] += s.elapsed_time(e) / prof_steps
+    peaks = load_peaks()
+    classes = {}
+    for wk, msl in zip(work, per_launch):
+        c = classes.setdefault(wk["kind"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        c["ms"] += msl; c["flops"] += wk["flops"]; c["bytes"] += wk["bytes"]; c["launches"] += 1
+    total_kernel_ms = sum(c["ms"] for c in classes.values())
+    roofline_all = {}
+    for kind, c in classes.items():
+        tf = c["flops"] / (c["ms"] * 1e-3) / 1e12 if c["ms"] > 0 else 0.0
+        gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else 0.0
+        entry = dict(ms_per_step=round(c["ms"], 4), launches=c["launches"], share=round(c["ms"] / total_kernel_ms, 4),
+                     tflops=round(tf, 1), gbs=round(gbs, 1))
+        if kind == "gemm":
+            entry.update(bound="tensor", frac=round(tf / peaks["tf_sustained"], 4),
+                         hbm_frac=round(gbs / peaks["hbm_gbs"], 4))
+        else:
+            entry.update(bound="hbm", frac=round(gbs / peaks["hbm_gbs"], 4))
+        roofline_all[kind] = entry
+    dom = max(classes, key=lambda k: classes[k]["ms"])
+    dc = classes[dom]
+    if dom == "gemm":
+        ach = dc["flops"] / dc["launches"] / (dc["ms"] / dc["launches"] * 1e-3) / 1e12
+        roofline = dict(kernel="conv_gemm_kernel (tcgen05)", bound="tensor", achieved=round(ach, 2),
+                        peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
+                        traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                        note="mean over the %d GEMM launches of a step (algorithmic FLOPs / CUDA-event time)" % dc["launches"])
+    else:
+        ach = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
+        roofline = dict(kernel=dom, bound="hbm", achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                        frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=peaks["source"])
+
+    # ---- end to end: pinned host waveforms in, host tokens out ----
+    host_wav = [torch.empty((B, L), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for hw, dw in zip(host_wav, wavs):
+        hw.copy_(dw)
+    host_len = torch.full((B,), L, dtype=torch.int32).pin_memory()
+    for i in range(2):
+        pipe.transcribe_host(host_wav[i & 1], host_len, device=dev)
+    barrier()
+    Ke = max(3, min(K, 10))
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        tok_h, len_h = pipe.transcribe_host(host_wav[i & 1], host_len, device=dev)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    te = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = audio_seconds_per_step * Ke / float(te.item())
+    h2d = B * L * 4 + B * 4
+    d2h = int(tok_h.numel() * 8 + len_h.numel() * len_h.element_size())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        val, cores, sample = cpu_oracle_throughput()
+        cpu = {"value": round(val, 2), "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "asr_audio_seconds_per_second", "value": round(value, 1), "unit": "audio-s/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_max / K, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "clip_seconds": CLIP_SECONDS,
+                       "parallelism": f"dp{world} (utterance-sharded, no data-path collective)",
+                       "l2": "inputs rotate between two 245 MB batches and every activation tensor exceeds the 126 MB L2"},
+            "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": Ke},
+            "gpu_launches": launches_per_step * K,
+            "gpu_launches_per_step": launches_per_step,
+            "clocks": clocks,
+            "roofline": roofline,
+            "roofline_all": roofline_all,
+            "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,13 +110,16 @@ int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const
                             int B, int C, int T_in, int k, int stride, int act, void* stream);
 
 /*
- * ConvTranspose1d(C_in -> C_out, kernel 5, stride 2, padding 2) + bias as two-phase tcgen05
- * GEMMs over shifted TMA views (even outputs: taps 0,2,4; odd outputs: taps 1,3), interleaved
- * in the epilogue.  Replaces VoiceDecoder.layers[4] (voice100/models/tts.py:22).
- *   Wp bf16 [C_out][5*C_in], Wp[co][tap*C_in + ci] = weight[ci][co][tap];  y bf16 NCW, T_out = 2T-1.
+ * ConvTranspose1d(C_in -> C_out, kernel 5, stride 2, padding 2) + bias as a two-phase tcgen05
+ * GEMM (even outputs: taps 0,2,4; odd outputs: taps 1,3; two TMEM accumulators interleaved in the
+ * epilogue).  Replaces VoiceDecoder.layers[4] (voice100/models/tts.py:22).
+ *   Wp bf16 [C_out][5*C_in], Wp[co][tap*C_in + ci] = weight[ci][co][tap];  y bf16 NCW, T_out = 2T-1;
+ *   workspace: caller-provided bf16 [B][3*C_in][x_pitch] scratch (the x(t+1) | x(t) | x(t-1) stack:
+ *   TMA box coordinates must be 16-byte aligned, so one-step time shifts are materialised once).
  */
 int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
-                                   void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream);
+                                   void* workspace, void* y, int64_t y_pitch,
+                                   int B, int C_in, int C_out, int T, void* stream);
 
 /*
  * Embedding lookup into NCW: y[b][c][t] = table[ids[b][t]][c].  Replaces nn.Embedding +

@@ -1,0 +1,116 @@
+"""CPU-side checks of the drop-in boundary: libv100.so loads without a GPU and exports exactly the
+symbols include/v100.h declares; the ctypes table matches the header; product code never imports the
+oracle; modules refuse to run without CUDA."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import voice100_b200 as v
+from voice100_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "v100.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|const char\*)\s+(v100_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    return {name: [a.strip() for a in args.split(",")] if args.strip() != "void" else [] for name, args in decls}
+
+
+def test_library_loads_and_exports_header_symbols():
+    from voice100_b200 import build
+    build.build()
+    assert os.path.exists(_lib.LIB_PATH)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    funcs = header_functions()
+    assert len(funcs) >= 15
+    for name in funcs:
+        assert hasattr(handle, name), f"{name} declared in v100.h but not exported"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (v100_\w+)", out))
+    assert exported == set(funcs), exported ^ set(funcs)
+    assert _lib.lib().v100_abi_version() == 1
+
+
+def test_ctypes_table_matches_header():
+    funcs = header_functions()
+    for name, argtypes in _lib.SIGNATURES.items():
+        assert name in funcs, name
+        assert len(argtypes) == len(funcs[name]), (name, len(argtypes), funcs[name])
+        for ct, decl in zip(argtypes, funcs[name]):
+            if "*" in decl:
+                assert ct is ctypes.c_void_p, (name, decl)
+            elif decl.startswith("int64_t"):
+                assert ct is ctypes.c_int64, (name, decl)
+            elif decl.startswith("float"):
+                assert ct is ctypes.c_float, (name, decl)
+            else:
+                assert ct is ctypes.c_int, (name, decl)
+    assert set(funcs) - set(_lib.SIGNATURES) == {"v100_last_error"}
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "voice100_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "v100_oracle" not in text and "import oracle" not in text, f
+
+
+def test_no_cpu_fallback():
+    m = v.AudioToTextCTC(64, 128, 29, 128)
+    with pytest.raises(v.V100Error):
+        m(torch.zeros(1, 50, 64))
+    with pytest.raises(v.V100Error):
+        v.MelSpectrogramAudioTransform().melspec(torch.zeros(1000))
+    with pytest.raises(v.V100Error):
+        v.TextToAlignTextModel(29, 64)(torch.zeros(1, 5, dtype=torch.long))
+    m.train()
+    with pytest.raises(v.V100Error):
+        m(torch.zeros(1, 50, 64))
+
+
+def test_state_dict_layout_matches_reference_keys():
+    for model, sd in ((v.AudioToTextCTC(64, 128, 29, 128), synth.asr_state_dict(64, 128, 29, 128)),
+                      (v.TextToAlignTextModel(29, 64), synth.align_state_dict(29, 64)),
+                      (v.AlignTextToAudioModel(29, 64), synth.audio_state_dict(29, 64))):
+        assert set(model.state_dict().keys()) == set(sd.keys())
+        for k, t in model.state_dict().items():
+            assert tuple(t.shape) == tuple(sd[k].shape), k
+        model.load_state_dict({k: torch.from_numpy(np.asarray(x)) for k, x in sd.items()})
+
+
+def test_align_host_function_matches_oracle():
+    import v100_oracle as orc
+    text = torch.from_numpy(synth.text_tokens(3, 17, seed=5))
+    align = synth.synthetic_alignment(3, 17, seed=5)
+    m = v.TextToAlignTextModel(29, 64)
+    for i in range(3):
+        got = m.align(text[i], torch.from_numpy(align[i]))
+        assert got.tolist() == orc.align_text(text[i].tolist(), align[i]).tolist()
+
+
+def test_sparse_filterbank_roundtrip():
+    from voice100_b200.data_modules import mel_filterbank, sparse_filterbank
+    fb = mel_filterbank(16000, 512, 64)
+    start, count, off, w = sparse_filterbank(fb)
+    dense = np.zeros_like(fb)
+    for m in range(64):
+        dense[start[m]:start[m] + count[m], m] = w[off[m]:off[m] + count[m]]
+    assert np.array_equal(dense, fb) and len(w) <= 520 and count.max() <= 24
+
+
+def test_bench_work_model_matches_survey():
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    work = bench.asr_work_model(1, 101, 512, 512, 29)   # ~ one audio-second (100 in-frames -> ~50 out)
+    gemm = sum(w["flops"] for w in work if w["kind"] == "gemm") / 1e6
+    dw = sum(w["flops"] for w in work if w["kind"] == "dwconv") / 1e6
+    assert abs(gemm - 1084.6 - 1.48) / 1086 < 0.03 and abs(dw - 72.0) / 72.0 < 0.03, (gemm, dw)

@@ -1,0 +1,219 @@
+"""Per-kernel parity on the device: every C-ABI entry point against a plain fp32 PyTorch evaluation of
+the same op on the same (bf16-rounded) operands.  Runs only on the GPU box (-m gpu)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import v100_oracle as orc
+from voice100_b200 import kernels as K
+from voice100_b200 import synth
+from voice100_b200.data_modules import MelSpectrogramAudioTransform
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ncw(x_f32: torch.Tensor) -> K.Ncw:
+    """fp32 [B,C,T] on device -> pitched bf16 Ncw with NaN poison in the pitch padding."""
+    B, C, T = x_f32.shape
+    out = K.empty_ncw(B, C, T, x_f32.device)
+    out.data.fill_(float("nan"))
+    out.data[:, :, :T] = x_f32.to(torch.bfloat16)
+    return out
+
+
+def rel_err(got, ref):
+    got, ref = got.double(), ref.double()
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# pointwise GEMM (tcgen05 + TMA)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C_in,C_out,T,act,res", [
+    (1, 64, 128, 64, 0, False),        # one tile, one k-block
+    (1, 128, 128, 256, 0, False),      # two k-blocks, full 256 tile
+    (2, 64, 256, 1501, 1, False),      # asr layer-0 expand shape (ragged T, ReLU6)
+    (3, 256, 1024, 751, 1, False),     # expand
+    (3, 1024, 256, 751, 0, True),      # project + residual
+    (2, 512, 2048, 300, 1, False),
+    (2, 2048, 512, 300, 0, True),
+    (5, 256, 256, 100, 0, True),       # BLOCK_N=128 path
+    (2, 72, 200, 333, 1, False),       # K not a multiple of 64, C_out not a multiple of 128
+    (40, 128, 384, 520, 0, True),      # > 148 tiles: persistent loop + both TMEM buffers reused
+])
+def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res):
+    x = rnd(B, C_in, T, seed=1)
+    W = rnd(C_out, C_in, seed=2, scale=1.0 / math.sqrt(C_in)).to(torch.bfloat16)
+    scale = (torch.rand(C_out, device=DEV) + 0.5)
+    shift = torch.randn(C_out, device=DEV) * 0.3
+    r = rnd(B, C_out, T, seed=3) if res else None
+    xn, rn = ncw(x), (ncw(r) if res else None)
+    y = K.conv1x1(xn, W, scale, shift, act, rn)
+    torch.cuda.synchronize()
+    ref = torch.einsum("oc,bct->bot", W.float(), xn.valid().float()) * scale[None, :, None] + shift[None, :, None]
+    if act:
+        ref = ref.clamp(0, 6)
+    if res:
+        ref = ref + rn.valid().float()
+    got = y.valid().float()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 1.2e-2, rel_err(got, ref)   # bf16 output rounding is 2^-8 relative
+
+
+@pytest.mark.parametrize("B,C_in,C_out,T", [(2, 256, 29, 751), (3, 512, 44, 100), (2, 256, 260, 277), (1, 512, 2, 24)])
+def test_conv1x1_f32out_matches_torch(B, C_in, C_out, T):
+    x = rnd(B, C_in, T, seed=4)
+    W = rnd(C_out, C_in, seed=5, scale=1.0 / math.sqrt(C_in)).to(torch.bfloat16)
+    bias = torch.randn(C_out, device=DEV)
+    xn = ncw(x)
+    y = K.conv1x1_f32(xn, W, bias)
+    torch.cuda.synchronize()
+    ref = torch.einsum("oc,bct->bot", W.float(), xn.valid().float()) + bias[None, :, None]
+    assert rel_err(y.valid(), ref) < 1e-4
+
+
+@pytest.mark.parametrize("B,C_in,C_out,T", [(2, 512, 256, 277), (1, 64, 128, 40), (3, 128, 64, 130)])
+def test_convtranspose_matches_torch(B, C_in, C_out, T):
+    x = rnd(B, C_in, T, seed=6)
+    w = rnd(C_in, C_out, 5, seed=7, scale=1.0 / math.sqrt(C_in * 2.5)).to(torch.bfloat16)
+    bias = torch.randn(C_out, device=DEV)
+    xn = ncw(x)
+    wp = w.permute(1, 2, 0).reshape(C_out, 5 * C_in).contiguous()
+    y = K.convtranspose_k5s2(xn, wp, bias)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose1d(xn.valid().float(), w.float(), bias, stride=2, padding=2)
+    assert y.T == 2 * T - 1 == ref.shape[2]
+    assert rel_err(y.valid().float(), ref) < 1.2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# depthwise conv (mma.sync Toeplitz kernel and the CUDA-core kernel)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [5, 7, 11, 17, 19, 27, 29, 33, 35, 51, 59, 65, 67, 75, 83])
+@pytest.mark.parametrize("T", [751, 96])
+def test_dwconv_mma_matches_torch(k, T):
+    B, C = 2, 64
+    x = rnd(B, C, T, seed=k).abs()
+    w = rnd(C, k, seed=k + 1, scale=1.0 / math.sqrt(k)).to(torch.bfloat16)
+    scale, shift = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    xn = ncw(x)
+    ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], padding=(k - 1) // 2, groups=C)
+    ref = (ref * scale[None, :, None] + shift[None, :, None]).clamp(0, 6)
+    for simt in (False, True):
+        y = K.dwconv(xn, w, scale, shift, k, 1, K.ACT_RELU6, simt=simt)
+        torch.cuda.synchronize()
+        assert y.T == T
+        assert rel_err(y.valid().float(), ref) < 1.2e-2, ("simt" if simt else "mma", rel_err(y.valid().float(), ref))
+
+
+def test_dwconv_long_rows_and_stride2():
+    B, C, T, k = 2, 16, 3001, 83                       # 60 s clip: three 1024-output chunks per row
+    x = rnd(B, C, T, seed=9)
+    w = rnd(C, k, seed=10, scale=0.1).to(torch.bfloat16)
+    shift = torch.zeros(C, device=DEV)
+    xn = ncw(x)
+    y = K.dwconv(xn, w, None, shift, k, 1, K.ACT_NONE)
+    ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], padding=41, groups=C)
+    assert rel_err(y.valid().float(), ref) < 1.2e-2
+    B, C, T, k = 3, 256, 1501, 11                      # asr layer 0: stride 2
+    x = rnd(B, C, T, seed=11)
+    w = rnd(C, k, seed=12, scale=0.3).to(torch.bfloat16)
+    xn = ncw(x)
+    y = K.dwconv(xn, w, None, torch.zeros(C, device=DEV), k, 2, K.ACT_RELU6)
+    ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], stride=2, padding=5, groups=C).clamp(0, 6)
+    assert y.T == 751 == ref.shape[2]
+    assert rel_err(y.valid().float(), ref) < 1.2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# log-mel
+# ------------------------------------------------------------------------------------------------
+def test_logmel_matches_oracle_and_golden():
+    from helpers import golden
+    g = golden("logmel")
+    tr = MelSpectrogramAudioTransform().to(DEV)
+    clips = [synth.noise_waveform(1, 16000, seed=11)[0], synth.harmonic_waveform(1, 12345, seed=12)[0],
+             synth.noise_waveform(1, 400, seed=13)[0]]
+    L = max(len(c) for c in clips)
+    wav = np.zeros((3, L), np.float32)
+    for i, c in enumerate(clips):
+        wav[i, :len(c)] = c
+    lengths = torch.tensor([len(c) for c in clips], dtype=torch.int32)
+    audio, audio_len = tr.logmel_batch(torch.from_numpy(wav).to(DEV), lengths.to(DEV))
+    torch.cuda.synchronize()
+    assert audio_len.tolist() == g["batch_audio_len"].tolist()
+    # fp32 FFT round-off only matters in near-silent bins of the clean harmonic clip (see oracle test)
+    np.testing.assert_allclose(audio.cpu().numpy(), g["batch_audio"], rtol=0, atol=3e-3)
+    np.testing.assert_allclose(audio[0].cpu().numpy(), g["noise_16000"], rtol=0, atol=2e-4)
+    mp = tr.melspec(torch.from_numpy(clips[1]).to(DEV)).cpu().numpy()
+    assert mp.shape == g["harm_12345_melpower"].shape
+    np.testing.assert_allclose(mp, g["harm_12345_melpower"], rtol=2e-3, atol=1e-6)
+    one = tr(torch.from_numpy(clips[0]).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(one, g["noise_16000"], rtol=0, atol=2e-4)
+
+
+def test_logmel_ragged_batch_bf16_ncw():
+    tr = MelSpectrogramAudioTransform().to(DEV)
+    B, L = 9, 16000 * 3 + 77
+    wav = torch.from_numpy(synth.noise_waveform(B, L, seed=5))
+    lengths = torch.from_numpy(synth.ragged_lengths(B, 300, L, seed=5))
+    ref, ref_len = orc.logmel_batch(wav, lengths.tolist())
+    out, out_len = tr.logmel_batch(wav.to(DEV), lengths.to(DEV), ncw_bf16=True)
+    torch.cuda.synchronize()
+    assert out_len.cpu().tolist() == ref_len.tolist()
+    got = out.valid().float().transpose(1, 2).cpu()
+    assert got.shape == ref.shape
+    # bf16 has 8 mantissa bits: |x| < 16 -> abs error <= 2^-5
+    assert float((got - ref).abs().max()) <= 0.0625 + 1e-3
+    assert (got[0, int(ref_len[0]):] == torch.tensor(orc.BLANK_AUDIO).to(torch.bfloat16).float()).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# small layout / head kernels
+# ------------------------------------------------------------------------------------------------
+def test_layout_and_head_kernels():
+    x = rnd(3, 101, 64, seed=20)
+    y = K.ntc_f32_to_ncw(x)
+    assert torch.equal(y.valid().float(), x.transpose(1, 2).to(torch.bfloat16).float())
+    z = rnd(2, 40, 77, seed=21)
+    assert torch.equal(K.ncw_to_f32(K.ncw_from_f32(z)), z.to(torch.bfloat16).float())
+    ids = torch.randint(0, 29, (3, 45), device=DEV)
+    table = rnd(29, 64, seed=22).to(torch.bfloat16)
+    e = K.embedding_ncw(ids, table)
+    assert torch.equal(e.valid(), F.embedding(ids, table).transpose(1, 2))
+    lg = K.Ncw(torch.randn(4, 29, 104, device=DEV), 101)
+    lg.data[0, 3, 7] = lg.data[0, 11, 7] = 50.0          # tie -> first maximal index
+    logits, tokens = K.ctc_finalize(lg)
+    ref = lg.valid().transpose(1, 2)
+    assert torch.equal(logits, ref) and torch.equal(tokens, ref.argmax(-1)) and int(tokens[0, 7]) == 3
+    assert torch.equal(K.ncw_f32_to_ntc(lg), ref)
+    w = K.Ncw(torch.randn(2, 260, 56, device=DEV), 53)
+    mean, std = torch.randn(259, device=DEV), torch.rand(259, device=DEV) + 0.5
+    hasf0, f0, logspc, codeap = K.world_finalize(w, mean, std, True)
+    v = w.valid()
+    assert torch.equal(hasf0, v[:, 0])
+    ref_f0 = torch.where(v[:, 0] < 0, torch.zeros(1, device=DEV), std[0] * v[:, 1] + mean[0])
+    torch.testing.assert_close(f0, ref_f0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(logspc, (std[1:258, None] * v[:, 2:259] + mean[1:258, None]).transpose(1, 2), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(codeap, (std[258] * v[:, 259:] + mean[258]).transpose(1, 2), rtol=1e-6, atol=1e-6)
+    h2, f2, l2, c2 = K.world_finalize(w, None, None, False)
+    assert torch.equal(f2, v[:, 1]) and torch.equal(l2, v[:, 2:259].transpose(1, 2))
+
+
+def test_errors_are_loud():
+    from voice100_b200 import V100Error
+    x = K.empty_ncw(1, 60, 16, DEV)     # C_in not a multiple of 8
+    with pytest.raises(V100Error):
+        K.conv1x1(x, torch.zeros(8, 60, device=DEV, dtype=torch.bfloat16), None, torch.zeros(8, device=DEV), 0)
+    with pytest.raises(V100Error):
+        K.dwconv(K.empty_ncw(1, 8, 16, DEV), torch.zeros(8, 4, device=DEV, dtype=torch.bfloat16), None,
+                 torch.zeros(8, device=DEV), 4, 1, 0)

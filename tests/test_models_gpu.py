@@ -1,0 +1,103 @@
+"""End-to-end parity of the drop-in modules against the CPU oracle (and through it the reference's
+golden vectors).  bf16 tensor-core compute vs fp32 reference: tolerances are stated per check as a
+fraction of the reference output's standard deviation."""
+import numpy as np
+import pytest
+import torch
+
+import v100_oracle as orc
+import voice100_b200 as v
+from voice100_b200 import synth
+from helpers import asr_case, tts_case
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# bf16 carries 8 mantissa bits through 27 convolutions: measured error is ~1-2 % of the logit std.
+LOGIT_MAX_REL_STD = 0.08
+LOGIT_RMS_REL_STD = 0.02
+
+
+def _load(model, sd):
+    model.load_state_dict({k: (t if isinstance(t, torch.Tensor) else torch.from_numpy(np.asarray(t))) for k, t in sd.items()})
+    return model.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["asr_en_small", "asr_ja_phone_ragged"])
+def test_asr_matches_golden(name):
+    sd, wav, lengths, g = asr_case(name)
+    audio_size, embed, vocab, hidden = [int(x) for x in g["cfg"][:4]]
+    model = _load(v.AudioToTextCTC(audio_size, embed, vocab, hidden), sd)
+    tr = v.MelSpectrogramAudioTransform().to(DEV)
+    audio, audio_len = tr.logmel_batch(wav.to(DEV), torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    logits = model(audio)
+    tokens, out_len = v.AsrPipeline(tr, model)(wav.to(DEV), torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    torch.cuda.synchronize()
+    ref = torch.from_numpy(g["logits"])
+    assert logits.shape == ref.shape
+    assert out_len.cpu().tolist() == g["out_len"].tolist()
+    rep = orc.parity_report(ref, logits.cpu())
+    print(name, rep)
+    assert rep["max_abs_rel_std"] < LOGIT_MAX_REL_STD and rep["rms_rel_std"] < LOGIT_RMS_REL_STD, rep
+    margin = 2.5 * rep["max_abs"]
+    raw, gated, frac = orc.token_agreement(ref, tokens.cpu(), margin)
+    raw2, _, _ = orc.token_agreement(ref, logits.argmax(-1).cpu(), margin)
+    print(name, "token agreement raw %.4f gated %.4f (gate keeps %.2f of frames)" % (raw, gated, frac))
+    assert gated == 1.0 and raw > 0.9 and raw2 > 0.9
+
+
+def test_asr_base_live_oracle():
+    """asr_en_base size, BN calibrated on the batch, CUDA path vs the oracle run live on the host."""
+    B, L = 4, 16000 * 3
+    wav = torch.from_numpy(synth.noise_waveform(B, L, seed=77))
+    lengths = [L, L - 5000, L - 16000, L]
+    sd = orc.to_torch_sd(synth.asr_state_dict(64, 512, 29, 512, seed=77, randomize_bn=True))
+    audio_ref, _ = orc.logmel_batch(wav, lengths)
+    sd = orc.calibrate_asr(sd, audio_ref)
+    with torch.no_grad():
+        ref = orc.asr_forward(audio_ref, sd)
+    model = _load(v.AudioToTextCTC(64, 512, 29, 512), sd)
+    tr = v.MelSpectrogramAudioTransform().to(DEV)
+    tokens, _ = v.AsrPipeline(tr, model)(wav.to(DEV), torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    audio, _ = tr.logmel_batch(wav.to(DEV), torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    logits = model(audio).cpu()
+    rep = orc.parity_report(ref, logits)
+    raw, gated, frac = orc.token_agreement(ref, tokens.cpu(), 2.5 * rep["max_abs"])
+    print("asr_en_base", rep, raw, gated, frac)
+    assert rep["max_abs_rel_std"] < LOGIT_MAX_REL_STD and rep["rms_rel_std"] < LOGIT_RMS_REL_STD, rep
+    assert gated == 1.0 and raw > 0.9
+    # sub-module API on NCW tensors (asr.py:78,93)
+    enc = model.encoder(audio.transpose(1, 2).contiguous())
+    with torch.no_grad():
+        enc_ref = orc.asr_encoder(audio_ref.transpose(1, 2), sd)
+    assert enc.shape == enc_ref.shape
+    assert orc.parity_report(enc_ref, enc.cpu())["rms_rel_std"] < LOGIT_RMS_REL_STD
+
+
+def test_tts_matches_golden():
+    sd_a, sd_v, text, align, g = tts_case()
+    V, H = int(g["cfg"][0]), int(g["cfg"][1])
+    amodel = _load(v.TextToAlignTextModel(V, H), sd_a)
+    vmodel = _load(v.AlignTextToAudioModel(V, H), sd_v)
+    pred = amodel(text.to(DEV)).cpu()
+    rep = orc.parity_report(torch.from_numpy(g["align_pred"]), pred)
+    print("align", rep)
+    assert rep["max_abs_rel_std"] < 0.08 and rep["rms_rel_std"] < 0.02, rep
+    ats = [amodel.align(text[i], torch.from_numpy(align[i])) for i in range(text.shape[0])]
+    at = torch.nn.utils.rnn.pad_sequence(ats, batch_first=True, padding_value=0)
+    assert torch.equal(at, torch.from_numpy(g["aligntext"]))
+    hasf0, f0_hat, logspc_hat, codeap_hat = vmodel(at.to(DEV))
+    f0, logspc, codeap = vmodel.predict(at.to(DEV))
+    torch.cuda.synchronize()
+    assert logspc.shape == g["logspc"].shape and codeap.shape == g["codeap"].shape and f0.shape == g["f0"].shape
+    for name, got, ref in (("hasf0", hasf0, g["hasf0_logits"]), ("logspc", logspc, g["logspc"]),
+                           ("codeap", codeap, g["codeap"]), ("f0_hat", f0_hat, g["f0_hat"])):
+        rep = orc.parity_report(torch.from_numpy(ref), got.cpu())
+        print(name, rep)
+        assert rep["max_abs_rel_std"] < 0.10 and rep["rms_rel_std"] < 0.02, (name, rep)
+    # voiced/unvoiced gate agrees wherever the fp32 logit is not within bf16 error of zero
+    safe = np.abs(g["hasf0_logits"]) > 2.5 * float(np.abs(hasf0.cpu().numpy() - g["hasf0_logits"]).max())
+    assert ((f0.cpu().numpy() == 0) == (g["f0"] == 0))[safe].all()
+    voiced = safe & (g["f0"] != 0)
+    rep = orc.parity_report(torch.from_numpy(g["f0"][voiced]), f0.cpu()[torch.from_numpy(voiced)])
+    assert rep["max_abs_rel_std"] < 0.10, rep

@@ -22,7 +22,7 @@ SIGNATURES = {
     "v100_conv1x1_f32out": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _p],
     "v100_dwconv1d_bf16": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
     "v100_dwconv1d_bf16_simt": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
-    "v100_convtranspose1d_k5s2_bf16": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_convtranspose1d_k5s2_bf16": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
     "v100_embedding_ncw_bf16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
     "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p],
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
@@ -57,9 +57,24 @@ def lib():
     return _lib
 
 
+# kernels launched per entry point (everything is one kernel except the transposed conv, which first
+# builds its shifted channel stack)
+KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
+KERNELS_PER_CALL["v100_convtranspose1d_k5s2_bf16"] = 2
+KERNELS_PER_CALL["v100_abi_version"] = 0
+
+stats = {"launches": 0}
+tracer = None  # optional object with before(name)/after(name), used by bench.py for per-kernel CUDA events
+
+
 def call(name, *args):
     """Invoke an entry point; non-zero status raises with the library's own message."""
     handle = lib()
+    if tracer is not None:
+        tracer.before(name)
     rc = getattr(handle, name)(*args)
+    if tracer is not None:
+        tracer.after(name)
     if rc != 0:
         raise V100Error(f"{name} failed (status {rc}): {handle.v100_last_error().decode()}")
+    stats["launches"] += KERNELS_PER_CALL[name]

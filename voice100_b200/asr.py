@@ -106,9 +106,40 @@ class AsrPipeline:
         return self.model.greedy(feats), self.model.output_length(audio_len)
 
     @torch.no_grad()
-    def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda"):
-        """Host (ideally pinned) buffers in, host tokens out: the end-to-end call a user makes."""
-        wav_d = waveform.to(device, non_blocking=True)
-        len_d = lengths.to(device, non_blocking=True)
-        tokens, out_len = self(wav_d, len_d)
-        return tokens.cpu(), out_len.cpu()
+    def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):
+        """Host buffers in (pin them for full PCIe speed), host tokens out: the end-to-end call a user makes.
+        The batch is cut into `chunks` groups of utterances; their H2D copies run on a side stream so that
+        chunk i+1 uploads while chunk i computes, and tokens come back with an async D2H per chunk.
+        -> (tokens int64 [B, T'] pinned host tensor, valid lengths int [B])."""
+        dev = torch.device(device)
+        B = waveform.shape[0]
+        n = max(1, min(chunks, B))
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._host_out = {}
+        T_out = (self.transform.num_frames(waveform.shape[1]) + 1) // 2
+        key = (B, T_out)
+        if key not in self._host_out:
+            self._host_out = {key: (torch.empty((B, T_out), dtype=torch.int64).pin_memory(),
+                                    torch.empty((B,), dtype=torch.int32).pin_memory())}
+        tok_h, len_h = self._host_out[key]
+        self._copy_stream.wait_stream(cur)
+        staged = []
+        for i in range(n):
+            a, b = B * i // n, B * (i + 1) // n
+            with torch.cuda.stream(self._copy_stream):
+                w = waveform[a:b].to(dev, non_blocking=True)
+                ln = lengths[a:b].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            staged.append((a, b, w, ln, ev))
+        for a, b, w, ln, ev in staged:
+            cur.wait_event(ev)
+            w.record_stream(cur)
+            ln.record_stream(cur)
+            tokens, out_len = self(w, ln)
+            tok_h[a:b].copy_(tokens, non_blocking=True)
+            len_h[a:b].copy_(out_len.to(torch.int32), non_blocking=True)
+        cur.synchronize()
+        return tok_h, len_h

@@ -129,9 +129,10 @@ int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const
   return dwconv1d_bf16(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, 1, STREAM(stream));
 }
 
-int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* y,
-                                   int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream) {
-  return convtranspose1d_k5s2_bf16(x, x_pitch, Wp, bias, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
+int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
+                                   void* workspace, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T,
+                                   void* stream) {
+  return convtranspose1d_k5s2_bf16(x, x_pitch, Wp, bias, workspace, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
 }
 
 int v100_embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V,

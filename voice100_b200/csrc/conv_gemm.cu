@@ -1,6 +1,8 @@
 // Pointwise / multi-tap Conv1d as a persistent, warp-specialised tcgen05 GEMM (sm_100a).
 //
-//   D[co][t] = sum_tap sum_ci  W[co][tap*C_in + ci] * X[b][ci][t + shift(tap)]
+//   D[acc(tap)][co][t] += sum_ci  W[co][tap*C_in + ci] * X[b][xrow(tap) + ci][t]
+// (1x1 conv: one tap; ConvTranspose1d k5/s2: five taps over a [x(t+1) | x(t) | x(t-1)] channel stack --
+//  TMA needs 16-byte aligned inner coordinates, so +-1 time shifts cannot be expressed as box offsets.)
 //
 // Operand roles: the WEIGHTS are the UMMA "A" operand (M = 128 output channels, K-major, 128B swizzle),
 // the ACTIVATIONS are the "B" operand (N = 128/256 time steps, MN-major because NCW keeps time
@@ -37,7 +39,7 @@ struct GemmParams {
   int C_out, C_in, B;
   int m_tiles, t_tiles, num_tiles, k_blocks;
   int n_taps;
-  int tap_shift[kMaxTaps];
+  int tap_xrow[kMaxTaps];   // first X channel row of the tap
   int tap_acc[kMaxTaps];
   const float* scale;
   const float* shift;
@@ -109,8 +111,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int iters_per_tile = p.n_taps * p.k_blocks;
-
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -122,7 +122,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         const int t_tile = r % p.t_tiles;
         const int b = r / p.t_tiles;
         for (int tap = 0; tap < p.n_taps; ++tap) {
-          const int t_in0 = t_tile * BLOCK_N + p.tap_shift[tap];
+          const int t_in0 = t_tile * BLOCK_N;
+          const int xrow0 = p.tap_xrow[tap];
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -131,7 +132,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             tma_load_2d(sa, &tm_w, &full_bar[stage], tap * p.C_in + kb * kBlockK, m_tile * kBlockM);
 #pragma unroll
             for (int a = 0; a < BLOCK_N / 64; ++a)
-              tma_load_3d(sb + a * kBAtomBytes, &tm_x, &full_bar[stage], t_in0 + a * 64, kb * kBlockK, b);
+              tma_load_3d(sb + a * kBAtomBytes, &tm_x, &full_bar[stage], t_in0 + a * 64, xrow0 + kb * kBlockK, b);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -404,7 +405,7 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
   p.t_tiles = (T + bn - 1) / bn;
   p.num_tiles = p.m_tiles * p.t_tiles * B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
-  p.n_taps = 1; p.tap_shift[0] = 0; p.tap_acc[0] = 0;
+  p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
   p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr;
   if (bn == 256) return launch_gemm<256, 1, OUT_BF16, 3>(tw, tx, ty, tr, p, stream);
   return launch_gemm<128, 1, OUT_BF16, 4>(tw, tx, ty, tr, p, stream);
@@ -428,24 +429,56 @@ int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* b
   p.t_tiles = (T + bn - 1) / bn;
   p.num_tiles = p.m_tiles * p.t_tiles * B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
-  p.n_taps = 1; p.tap_shift[0] = 0; p.tap_acc[0] = 0;
+  p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
   p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
   p.y32 = y; p.y32_pitch = y_pitch;
   if (bn == 256) return launch_gemm<256, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
   return launch_gemm<128, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
 }
 
-int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* y,
-                              int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream) {
+// xs[b][s*C + c][t] = x[b][c][t + 1 - s], s = 0,1,2, zero outside [0,T): the three time-shifted views the
+// transposed conv needs, stacked along channels so they become plain K offsets of one GEMM.
+__global__ void __launch_bounds__(256)
+shift_stack3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ xs, int C, int T, long long pitch) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int t0 = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (t0 >= pitch) return;
+  const unsigned short* row = reinterpret_cast<const unsigned short*>(x) + (static_cast<long long>(b) * C + c) * pitch;
+  unsigned short v[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int t = t0 - 1 + i;
+    v[i] = (t >= 0 && t < T) ? row[t] : 0;
+  }
+#pragma unroll
+  for (int s = 0; s < 3; ++s) {
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ow[i] = uint32_t(v[2 * i + 2 - s]) | (uint32_t(v[2 * i + 3 - s]) << 16);
+    *reinterpret_cast<uint4*>(xs + ((static_cast<long long>(b) * 3 + s) * C + c) * pitch + t0) = o;
+  }
+}
+
+int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
+                              void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream) {
   if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "convtranspose: non-positive size");
   if (C_in % 64 != 0) return fail(V100_E_UNSUPPORTED, "convtranspose: C_in=%d must be a multiple of 64", C_in);
   if (bias == nullptr || Wp == nullptr) return fail(V100_E_INVALID, "convtranspose: null W/bias");
+  if (B > 65535 || C_in > 65535) return fail(V100_E_UNSUPPORTED, "convtranspose: B or C_in too large for the grid");
   const int T_out = 2 * T - 1;
   if (int e = check_ncw(x, x_pitch, T, "convtranspose x")) return e;
+  if (int e = check_ncw(workspace, x_pitch, T, "convtranspose workspace")) return e;
   if (int e = check_ncw(y, y_pitch, T_out, "convtranspose y")) return e;
+  {
+    dim3 grid((unsigned)((x_pitch / 8 + 255) / 256), C_in, B);
+    shift_stack3_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+                                                  static_cast<__nv_bfloat16*>(workspace), C_in, T, x_pitch);
+    V100_CUDA(cudaGetLastError());
+  }
   CUtensorMap tw, tx, ty;
   if (int e = make_tmap_2d(&tw, Wp, int64_t(C_in) * 5, C_out, int64_t(C_in) * 5 * 2, 64, 128)) return e;
-  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&tx, workspace, T, int64_t(C_in) * 3, B, x_pitch * 2, int64_t(C_in) * 3 * x_pitch * 2, 64, 64)) return e;
   if (int e = make_tmap_3d(&ty, y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
@@ -456,10 +489,11 @@ int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, co
   // y[co][o] = b[co] + sum_{ci,k,t: o = 2t - 2 + k} x[ci][t] W[ci][co][k]   (tts.py:22, stride 2, padding 2)
   //   o = 2j   : (k,t) = (0,j+1) (2,j) (4,j-1)   -> accumulator 0
   //   o = 2j+1 : (k,t) = (1,j+1) (3,j)           -> accumulator 1
+  // x(t+1), x(t), x(t-1) are channel blocks 0, 1, 2 of the workspace.
   p.n_taps = 5;
-  const int shifts[5] = {+1, +1, 0, 0, -1};
+  const int blocks[5] = {0, 0, 1, 1, 2};
   const int accs[5] = {0, 1, 0, 1, 0};
-  for (int i = 0; i < 5; ++i) { p.tap_shift[i] = shifts[i]; p.tap_acc[i] = accs[i]; }
+  for (int i = 0; i < 5; ++i) { p.tap_xrow[i] = blocks[i] * C_in; p.tap_acc[i] = accs[i]; }
   p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
   return launch_gemm<128, 2, OUT_BF16, 4>(tw, tx, ty, ty, p, stream);
 }

@@ -31,8 +31,8 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
                  cudaStream_t stream);
 int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
                    int B, int C_in, int C_out, int T, cudaStream_t stream);
-int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* y,
-                              int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream);
+int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
+                              void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream);
 int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
                   int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int force_simt,
                   cudaStream_t stream);

@@ -138,8 +138,9 @@ def convtranspose_k5s2(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor) -> Ncw:
     C_out = Wp.shape[0]
     assert Wp.shape[1] == 5 * x.C
     y = empty_ncw(x.B, C_out, 2 * x.T - 1, x.data.device)
+    ws = torch.empty((x.B, 3 * x.C, x.pitch), device=x.data.device, dtype=torch.bfloat16)
     _lib.call("v100_convtranspose1d_k5s2_bf16", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
-              y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, _stream())
+              ws.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, _stream())
     return y
 
 
