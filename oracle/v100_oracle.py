@@ -201,6 +201,43 @@ def asr_forward(audio: torch.Tensor, sd: SD, calib=None) -> torch.Tensor:
     return logits.transpose(1, 2)
 
 
+def _q(t: torch.Tensor, dtype) -> torch.Tensor:
+    return t if dtype is None else t.to(dtype).float()
+
+
+def _fold(sd: SD, p: str):
+    scale = sd[p + ".weight"] / torch.sqrt(sd[p + ".running_var"] + BN_EPS)
+    return scale[None, :, None], (sd[p + ".bias"] - sd[p + ".running_mean"] * sd[p + ".weight"] /
+                                  torch.sqrt(sd[p + ".running_var"] + BN_EPS))[None, :, None]
+
+
+def inverted_residual_storage_model(x, sd, p, kernel_size, stride, use_residual, dtype):
+    """The same block with every tensor that the CUDA path STORES rounded to `dtype` (weights, the two
+    hidden activations, the block output) while all arithmetic in between stays fp32 (fp32 accumulation,
+    fp32 folded BN, fp32 residual add before the output rounding).  This is the numerical contract of
+    libv100; comparing the kernels with it separates 'bf16 storage error' (inherent, stated in the tests)
+    from implementation error (must be ~0)."""
+    s1, b1 = _fold(sd, p + ".conv.0.1")
+    s2, b2 = _fold(sd, p + ".conv.1.1")
+    s3, b3 = _fold(sd, p + ".conv.3")
+    h = F.conv1d(x, _q(sd[p + ".conv.0.0.weight"], dtype))
+    h = _q((h * s1 + b1).clamp(0.0, 6.0), dtype)
+    h = F.conv1d(h, _q(sd[p + ".conv.1.0.weight"], dtype), stride=stride, padding=(kernel_size - 1) // 2,
+                 groups=h.shape[1])
+    h = _q((h * s2 + b2).clamp(0.0, 6.0), dtype)
+    y = F.conv1d(h, _q(sd[p + ".conv.2.weight"], dtype)) * s3 + b3
+    return _q(x + y if use_residual else y, dtype)
+
+
+def asr_forward_storage_model(audio: torch.Tensor, sd: SD, dtype=torch.bfloat16) -> torch.Tensor:
+    """asr_forward with libv100's storage roundings (features, weights, activations in `dtype`)."""
+    x = _q(audio.transpose(1, 2), dtype)
+    for i, (k, s, r) in enumerate(_asr_blocks(sd)):
+        x = inverted_residual_storage_model(x, sd, f"encoder.layers.{i}", k, s, r, dtype)
+    logits = F.conv1d(x, _q(sd["decoder.layers.1.weight"], dtype), sd["decoder.layers.1.bias"])
+    return logits.transpose(1, 2)
+
+
 def asr_output_length(audio_len: torch.Tensor) -> torch.Tensor:
     """asr.py:81-82,118-122."""
     return torch.div(audio_len + 1, 2, rounding_mode="trunc")

@@ -11,8 +11,9 @@
 //    blocks live in registers for the whole row; the A fragments are plain coalesced 32-bit shared
 //    loads of the staged row (fragment word index = lane + 8q + {0,4,32,36}), and the D fragment is
 //    128 consecutive outputs, stored coalesced.  One warp per (batch, channel) row, 8 rows per CTA.
-//  * dw_simt_kernel: any stride / any k, plain CUDA cores.  Used for the stride-2 first block
-//    (0.4 % of the depthwise FLOPs) and exported for cross-checking.
+//  * dw_s2_kernel: stride 2 (the first encoder block, 0.4 % of the depthwise FLOPs, HBM-bound): CUDA cores
+//    over a shared-memory staged row.
+//  * dw_simt_kernel: any stride / any k, plain CUDA cores; last resort and exported for cross-checking.
 #include "common.cuh"
 #include "host.h"
 
@@ -113,6 +114,76 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   }
 }
 
+// Stride-2 depthwise conv (the first encoder block, asr.py:68): one warp per (batch, channel) row,
+// the row segment staged in shared memory with coalesced 16-byte loads, each lane producing outputs
+// o = oc0 + 32 r + lane so that the 32-bit input words (x[2o+2m], x[2o+2m+1]) are consecutive across lanes.
+constexpr int kS2Chunk = 512;                 // outputs per CTA pass
+constexpr int kS2Row = 2 * kS2Chunk + 96;     // staged inputs (halo <= 48 each side)
+constexpr int kS2MaxWords = 48;               // (k + 1) / 2 + 1 <= 48  ->  k <= 93
+
+__global__ void __launch_bounds__(kDwWarps * 32)
+dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
+             const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+             long long y_pitch, int C, int T_in, int T_out, int k, int act) {
+  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][kS2Row];
+  __shared__ __align__(8) float ws_all[kDwWarps][2 * kS2MaxWords];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * kDwWarps + warp;
+  if (c >= C) return;
+  const int b = blockIdx.z;
+  const int oc0 = blockIdx.x * kS2Chunk;
+  const int p = (k - 1) >> 1;
+  const int p8 = (p + 7) & ~7;
+  const int e = p8 - p;                       // xs[2*ol + j + e] = x[2*(oc0+ol) + j - p]
+  __nv_bfloat16* xs = xs_all[warp];
+  float* ws = ws_all[warp];
+  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
+  const int ia = 2 * oc0 - p8;
+  for (int v = lane; v < kS2Row / 8; v += 32) {
+    const int t = ia + v * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < T_in) {
+      val = *reinterpret_cast<const uint4*>(xrow + t);
+      if (t + 8 > T_in) {
+        uint32_t* u = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (t + i >= T_in) u[i >> 1] &= (i & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+      }
+    }
+    *reinterpret_cast<uint4*>(xs + v * 8) = val;
+  }
+  const int n_words = (k + e + 1) >> 1;       // taps j' = j + e in [e, k+e) -> words [0, n_words)
+  for (int i = lane; i < 2 * n_words; i += 32) {
+    const int j = i - e;
+    ws[i] = (j >= 0 && j < k) ? __bfloat162float(w[static_cast<long long>(c) * k + j]) : 0.0f;
+  }
+  __syncwarp();
+  const float sc = scale ? scale[c] : 1.0f, sh = shift[c];
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs);
+  const float2* w2 = reinterpret_cast<const float2*>(ws);
+  __nv_bfloat16* yrow = y + (static_cast<long long>(b) * C + c) * y_pitch;
+  for (int r0 = 0; r0 < kS2Chunk / 32 && oc0 + r0 * 32 < T_out; r0 += 4) {
+    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int m = 0; m < n_words; ++m) {
+      const float2 wm = w2[m];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v = xw[(r0 + u) * 32 + lane + m];
+        acc[u] = fmaf(wm.x, bf16_lo(v), acc[u]);
+        acc[u] = fmaf(wm.y, bf16_hi(v), acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int o = oc0 + (r0 + u) * 32 + lane;
+      float v = fmaf(acc[u], sc, sh);
+      if (act == V100_ACT_RELU6) v = fminf(fmaxf(v, 0.0f), 6.0f);
+      if (o < T_out) yrow[o] = __float2bfloat16(v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 dw_simt_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
                const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
@@ -179,6 +250,11 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
       case 5: launch_dw_mma<5>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
       default: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
     }
+  } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
+    dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
+    dw_s2_kernel<<<grid, kDwWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pitch,
+                                                     static_cast<const __nv_bfloat16*>(w), scale, shift,
+                                                     static_cast<__nv_bfloat16*>(y), y_pitch, C, T_in, T_out, k, act);
   } else {
     dim3 grid((T_out + 1023) / 1024, C, B);
     dw_simt_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pitch,
