@@ -73,49 +73,55 @@ def asr_work_model(B, T_in, hidden, embed, vocab, audio_size=64):
 
 
 class ClockSampler:
-    """Samples SM clock + throttle reasons of one GPU while the timed region runs (nvidia-smi loop)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock + throttle reasons of one GPU every 5 ms through NVML while the timed region runs
+    (nvidia-smi -lms cannot start fast enough for a sub-second region; it is the fallback)."""
+    BITS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self.reasons, self._stop, self.thread = index, [], set(), False, None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 8:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # "under load": the upper half of the samples (idle samples at either end drag the median down)
-        load = sm[len(sm) // 2:] if sm else []
-        return dict(sm_mhz=(load[len(load) // 2] if load else None), sm_max_mhz=(max(smax) if smax else None),
-                    reasons=sorted(reasons), samples=len(sm))
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                return dict(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), reasons=["nvml unavailable; single nvidia-smi sample after the run: " + f[2]])
+            except Exception:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no clock source available"])
+        self._stop = True
+        self.thread.join()
+        sm = sorted(self.samples)
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.sm_max, reasons=sorted(self.reasons),
+                    samples=len(sm))
 
 
 def cpu_oracle_throughput(min_seconds=10.0, batch=8, max_reps=6):

@@ -9,6 +9,12 @@
 // contiguous, 128B swizzle).  Accumulators live in TMEM (lane = output channel, column = time), double
 // buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
+// CG == 2 (cta_group::2): a CTA pair computes a 256-channel x 256-step tile.  Each CTA stages its own 128
+// weight rows and its own 128 time columns, the pair's leader issues one 256-row UMMA that reads both
+// CTAs' shared memory, and each CTA drains its own 128 accumulator rows.  Per output element this moves
+// 1.5x fewer operand bytes from L2 to shared memory than the single-CTA tile -- the first working
+// version of this kernel measured ~10.7 TB/s of L2->SM operand traffic, i.e. it was L2-bound.
+//
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warp 3 = idle, warps 4..11 = epilogue (two groups of four warps; warp%4 selects the TMEM
 // lane quadrant it is allowed to read).
@@ -21,6 +27,8 @@
 //   OUT_F32 : y = acc + bias -> fp32 NCW, direct 16-byte stores (the small biased heads).
 #include "common.cuh"
 #include "host.h"
+
+#include <cstdlib>
 
 namespace v100 {
 
@@ -49,9 +57,10 @@ struct GemmParams {
   long long y32_pitch;
 };
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG = 1>
 struct GemmCfg {
-  static constexpr int kStageBytes = kATileBytes + (BLOCK_N / 64) * kBAtomBytes;
+  static constexpr int kBCols = BLOCK_N / CG;  // time columns this CTA stages per k-block
+  static constexpr int kStageBytes = kATileBytes + (kBCols / 64) * kBAtomBytes;
   static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? 4 * kChunkBytes : 0;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = 1024 + STAGES * kStageBytes + kStagingBytes + kBarBytes;
@@ -62,12 +71,15 @@ struct GemmCfg {
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
-                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
-                 const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG>
+__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CUtensorMap& tm_x,
+                                               const CUtensorMap& tm_y, const CUtensorMap& tm_res,
+                                               const GemmParams& p) {
+  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES, CG>;
+  static_assert(CG == 1 || (N_ACC == 1 && OUT_MODE == OUT_BF16), "the CTA-pair path serves the plain bf16 conv");
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::kStageBytes;
@@ -97,17 +109,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], kEpiWarps * CG);  // the leader's copy collects both CTAs' epilogue warps
     }
     for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -116,38 +133,49 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const int m_tile = tile % p.m_tiles;
         const int r = tile / p.m_tiles;
         const int t_tile = r % p.t_tiles;
         const int b = r / p.t_tiles;
+        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM;
         for (int tap = 0; tap < p.n_taps; ++tap) {
-          const int t_in0 = t_tile * BLOCK_N;
+          const int t_in0 = t_tile * BLOCK_N + int(cta_rank) * Cfg::kBCols;
           const int xrow0 = p.tap_xrow[tap];
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kATileBytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(sa, &tm_w, &full_bar[stage], tap * p.C_in + kb * kBlockK, m_tile * kBlockM);
+            if constexpr (CG == 2) {
+              // both CTAs' bytes are credited to the LEADER's full barrier (the MMA issuer waits there)
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              tma_load_2d_cg2(sa, &tm_w, fb, tap * p.C_in + kb * kBlockK, m0);
 #pragma unroll
-            for (int a = 0; a < BLOCK_N / 64; ++a)
-              tma_load_3d(sb + a * kBAtomBytes, &tm_x, &full_bar[stage], t_in0 + a * 64, xrow0 + kb * kBlockK, b);
+              for (int a = 0; a < Cfg::kBCols / 64; ++a)
+                tma_load_3d_cg2(sb + a * kBAtomBytes, &tm_x, fb, t_in0 + a * 64, xrow0 + kb * kBlockK, b);
+            } else {
+              mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tma_load_2d(sa, &tm_w, &full_bar[stage], tap * p.C_in + kb * kBlockK, m0);
+#pragma unroll
+              for (int a = 0; a < Cfg::kBCols / 64; ++a)
+                tma_load_3d(sb + a * kBAtomBytes, &tm_x, &full_bar[stage], t_in0 + a * 64, xrow0 + kb * kBlockK, b);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      // kind::f16 instruction descriptor: D=f32, A=B=bf16, A K-major, B MN-major, M=128, N=BLOCK_N
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (the pair's leader only) =====================
+      // kind::f16 instruction descriptor: D=f32, A=B=bf16, A K-major, B MN-major, M=128*CG, N=BLOCK_N
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                                 (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+                                 (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((kBlockM * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         const int accbuf = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty[accbuf], acc_phase ^ 1);
@@ -168,14 +196,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
               // B: MN-major SW128 (64-time atoms 8 KB apart = LBO; 8-k-row groups 1024 B apart = SBO;
               //    16 k rows = 2048 B per K step)
               const uint64_t db = umma_desc(b_addr + k * 2048, kBAtomBytes, 1024);
-              umma_bf16(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+              if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+              else umma_bf16(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
             }
             used |= 1u << acc;
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if constexpr (CG == 2) umma_commit_cg2(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&tmem_full[accbuf]);
+        if constexpr (CG == 2) umma_commit_cg2(&tmem_full[accbuf]); else umma_commit(&tmem_full[accbuf]);
       }
     }
   } else if (warp >= 4) {
@@ -194,22 +224,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
       const uint32_t swz = uint32_t(row & 7);
       uint8_t* my_row = stg + row * 128;
 
-      if (p.has_res && elected && int(blockIdx.x) < p.num_tiles) {
-        const int tile = blockIdx.x;
+      const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+      if (p.has_res && elected && tile0 < p.num_tiles) {
+        const int tile = tile0;
         const int r = tile / p.m_tiles;
         mbar_expect_tx(&rbar[0], kChunkBytes);
-        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + g * 64, (tile % p.m_tiles) * kBlockM,
-                    r / p.t_tiles);
+        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + g * 64,
+                    ((tile % p.m_tiles) * CG + int(cta_rank)) * kBlockM, r / p.t_tiles);
       }
       int iter = 0;
       uint32_t n = 0;  // chunk sequence number of this group
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         const int m_tile = tile % p.m_tiles;
         const int r = tile / p.m_tiles;
         const int t_tile = r % p.t_tiles;
         const int b = r / p.t_tiles;
         const int accbuf = iter & 1;
-        const int ch = m_tile * kBlockM + row;
+        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM;
+        const int ch = m0 + row;
         const float sc = (p.scale != nullptr && ch < p.C_out) ? __ldg(p.scale + ch) : 1.0f;
         const float sh = (ch < p.C_out) ? __ldg(p.shift + ch) : 0.0f;
         mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
@@ -231,7 +263,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           if (i == CPG - 1) {  // this thread is done reading the accumulator buffer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[accbuf]);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
+              else mbar_arrive(&tmem_empty[accbuf]);
+            }
           }
           float f0[32], f1[32];
 #pragma unroll
@@ -279,18 +314,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
           fence_proxy_async();
           named_bar_sync(bar_done, 128);
           if (elected) {
-            tma_store_3d(&tm_y, stg + buf * kChunkBytes, t_tile * Cfg::kOutCols + c * 64, m_tile * kBlockM, b);
+            tma_store_3d(&tm_y, stg + buf * kChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
             tma_store_commit();
             tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
             if (p.has_res) {
               int ntile = tile, nc = c + 2;
-              if (i == CPG - 1) { ntile = tile + gridDim.x; nc = g; }
+              if (i == CPG - 1) { ntile = tile + tile_step; nc = g; }
               if (ntile < p.num_tiles) {
                 const int nr = ntile / p.m_tiles;
                 mbar_expect_tx(&rbar[buf ^ 1], kChunkBytes);
                 tma_load_3d(stg + (buf ^ 1) * kChunkBytes, &tm_res, &rbar[buf ^ 1],
-                            (nr % p.t_tiles) * Cfg::kOutCols + nc * 64, (ntile % p.m_tiles) * kBlockM,
-                            nr / p.t_tiles);
+                            (nr % p.t_tiles) * Cfg::kOutCols + nc * 64,
+                            ((ntile % p.m_tiles) * CG + int(cta_rank)) * kBlockM, nr / p.t_tiles);
               }
             }
           }
@@ -300,7 +335,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     } else {
       // fp32 NCW direct store, bias only; group g owns columns [g*BLOCK_N/2, (g+1)*BLOCK_N/2)
       int iter = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         const int m_tile = tile % p.m_tiles;
         const int r = tile / p.m_tiles;
         const int t_tile = r % p.t_tiles;
@@ -343,11 +378,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+}
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
+                 const GemmParams p) {
+  conv_gemm_body<BLOCK_N, N_ACC, OUT_MODE, STAGES, 1>(tm_w, tm_x, tm_y, tm_res, p);
+}
+
+// CTA-pair variant: 256 output channels x 256 time steps per cluster of two CTAs
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
+                      const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
+                      const GemmParams p) {
+  conv_gemm_body<256, 1, OUT_BF16, STAGES, 2>(tm_w, tm_x, tm_y, tm_res, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,6 +420,26 @@ static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUten
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tw, tx, ty, tr, p);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
+constexpr int kPairStages = 5;
+
+static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
+                            const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<256, 1, OUT_BF16, kPairStages, 2>;
+  auto kern = conv_gemm_pair_kernel<kPairStages>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V100_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured_dev = dev;
+  }
+  int pairs = num_sms() / 2;
+  if (p.num_tiles < pairs) pairs = p.num_tiles;
+  kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(tw, tx, ty, tr, p);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
@@ -401,12 +473,18 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
   if (int e = make_tmap_3d(&tr, res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
-  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
-  p.t_tiles = (T + bn - 1) / bn;
-  p.num_tiles = p.m_tiles * p.t_tiles * B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
   p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
   p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr;
+  p.t_tiles = (T + bn - 1) / bn;
+  static const int force_cg = getenv("V100_GEMM_CG") ? atoi(getenv("V100_GEMM_CG")) : 0;  // debugging / A-B runs
+  if (bn == 256 && C_out % (2 * kBlockM) == 0 && force_cg != 1) {
+    p.m_tiles = C_out / (2 * kBlockM);
+    p.num_tiles = p.m_tiles * p.t_tiles * B;
+    return launch_gemm_pair(tw, tx, ty, tr, p, stream);
+  }
+  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
+  p.num_tiles = p.m_tiles * p.t_tiles * B;
   if (bn == 256) return launch_gemm<256, 1, OUT_BF16, 3>(tw, tx, ty, tr, p, stream);
   return launch_gemm<128, 1, OUT_BF16, 4>(tw, tx, ty, tr, p, stream);
 }
