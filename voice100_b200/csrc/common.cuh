@@ -221,6 +221,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// clamp(x, 0, 6) and round to bf16 in two instructions: cvt with the relu modifier, then a packed min
+__device__ __forceinline__ uint32_t pack_bf16x2_relu6(float lo, float hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tcvt.rn.relu.bf16x2.f32 t, %1, %2;\n\tmin.bf16x2 %0, t, %3;\n\t}"
+      : "=r"(r)
+      : "f"(hi), "f"(lo), "r"(0x40C040C0u));  // 6.0 in both bf16 halves
+  return r;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

@@ -20,9 +20,9 @@
 // lane quadrant it is allowed to read).
 //
 // Epilogues:
-//   OUT_BF16: y = act(scale*acc + shift) (+ residual) -> bf16, staged in 128B-swizzled smem and written
-//             with TMA stores; the residual tile is TMA-loaded into the same staging buffer ahead of
-//             time.  With N_ACC == 2 (ConvTranspose1d k5 s2) the even/odd output phases are two
+//   OUT_BF16: y = act(scale*acc + shift) (+ residual) -> bf16.  Each epilogue warp stages its own
+//             [32 channels x 64 steps] sub-tiles in 128B-swizzled smem and TMA-stores them; the residual
+//             sub-tile is TMA-loaded into the same slot one chunk ahead.  With N_ACC == 2 (ConvTranspose1d k5 s2) the even/odd output phases are two
 //             accumulators interleaved here.
 //   OUT_F32 : y = acc + bias -> fp32 NCW, direct 16-byte stores (the small biased heads).
 #include "common.cuh"
@@ -36,7 +36,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kBAtomBytes = kBlockK * 64 * 2;       // 8 KB: 64 k-rows x 64 time steps
-constexpr int kChunkBytes = kBlockM * 64 * 2;       // 16 KB: 128 channels x 64 time steps (staging)
+constexpr int kChunkBytes = kBlockM * 64 * 2;       // 16 KB: 128 channels x 64 time steps
+constexpr int kWarpChunkBytes = 32 * 64 * 2;        // 4 KB: one epilogue warp's 32 channels x 64 time steps
 constexpr int kMaxTaps = 5;
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
@@ -88,8 +89,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint64_t* res_bar = bars + 2 * STAGES + 4;    // [2 groups][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;    // [8 epilogue warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,7 +112,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps * CG);  // the leader's copy collects both CTAs' epilogue warps
     }
-    for (int i = 0; i < 4; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -216,39 +217,41 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
 
     if constexpr (OUT_MODE == OUT_BF16) {
+      // Every epilogue warp is its own pipeline: it owns 32 accumulator rows (its TMEM lane quadrant) and
+      // the 64-column chunks c = h, h+2, ... of the tile; it stages each [32 x 64] bf16 sub-tile in its
+      // private, 128B-swizzled, double-buffered 4 KB smem slot and TMA-stores it.  No cross-warp barriers.
       constexpr int CPG = Cfg::kChunksPerGroup;
-      const bool elected = (row == 0);
-      uint8_t* stg = staging + g * 2 * kChunkBytes;
-      uint64_t* rbar = res_bar + g * 2;
-      const uint32_t bar_free = 1 + g * 2, bar_done = 2 + g * 2;
-      const uint32_t swz = uint32_t(row & 7);
-      uint8_t* my_row = stg + row * 128;
-
+      const int h = g;                                   // which half of the tile's chunks
+      uint8_t* stg = staging + (warp - 4) * 2 * kWarpChunkBytes;
+      uint64_t* rbar = res_bar + (warp - 4) * 2;
+      const uint32_t swz = uint32_t(lane & 7);
+      uint8_t* my_row = stg + lane * 128;
       const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
-      if (p.has_res && elected && tile0 < p.num_tiles) {
-        const int tile = tile0;
-        const int r = tile / p.m_tiles;
-        mbar_expect_tx(&rbar[0], kChunkBytes);
-        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + g * 64,
-                    ((tile % p.m_tiles) * CG + int(cta_rank)) * kBlockM, r / p.t_tiles);
+      const bool relu6 = p.act == V100_ACT_RELU6;
+
+      if (p.has_res && lane == 0 && tile0 < p.num_tiles) {
+        const int r = tile0 / p.m_tiles;
+        mbar_expect_tx(&rbar[0], kWarpChunkBytes);
+        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + h * 64,
+                    ((tile0 % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, r / p.t_tiles);
       }
       int iter = 0;
-      uint32_t n = 0;  // chunk sequence number of this group
+      uint32_t n = 0;  // chunk sequence number of this warp
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         const int m_tile = tile % p.m_tiles;
         const int r = tile / p.m_tiles;
         const int t_tile = r % p.t_tiles;
         const int b = r / p.t_tiles;
         const int accbuf = iter & 1;
-        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM;
-        const int ch = m0 + row;
+        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM + q * 32;
+        const int ch = m0 + lane;
         const float sc = (p.scale != nullptr && ch < p.C_out) ? __ldg(p.scale + ch) : 1.0f;
         const float sh = (ch < p.C_out) ? __ldg(p.shift + ch) : 0.0f;
         mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < CPG; ++i, ++n) {
-          const int c = g + 2 * i;  // 64-column output chunk of this tile
+          const int c = h + 2 * i;  // 64-column output chunk of this tile
           const int buf = n & 1;
           uint32_t v0[32], v1[32];
           const uint32_t col0 = accbuf * (N_ACC * BLOCK_N);
@@ -260,7 +263,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
             tmem_ld32(lane_addr + col0 + BLOCK_N + c * 32, v1);  // odd output phase
           }
           tmem_ld_wait();
-          if (i == CPG - 1) {  // this thread is done reading the accumulator buffer
+          if (i == CPG - 1) {  // this warp is done reading the accumulator buffer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -268,70 +271,72 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
               else mbar_arrive(&tmem_empty[accbuf]);
             }
           }
-          float f0[32], f1[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f0[j] = fmaf(__uint_as_float(v0[j]), sc, sh);
-            f1[j] = fmaf(__uint_as_float(v1[j]), sc, sh);
-            if (p.act == V100_ACT_RELU6) {
-              f0[j] = fminf(fmaxf(f0[j], 0.0f), 6.0f);
-              f1[j] = fminf(fmaxf(f1[j], 0.0f), 6.0f);
-            }
-          }
-          // staging buffer `buf` is free (its previous TMA store has been read out) ...
-          named_bar_sync(bar_free, 128);
-          // ... and, if there is a residual, holds this chunk's residual tile
+          // slot `buf` is free: lane 0 waited for its previous TMA store before the __syncwarp that ended
+          // the previous chunk.  With a residual it now holds this chunk's residual sub-tile.
           if (p.has_res) mbar_wait(&rbar[buf], (n >> 1) & 1);
-          uint8_t* rowp = my_row + buf * kChunkBytes;
+          uint8_t* rowp = my_row + buf * kWarpChunkBytes;
 #pragma unroll
           for (int k16 = 0; k16 < 8; ++k16) {
             uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4));
             float o[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
+              float a;
               if constexpr (N_ACC == 1) {
                 const int j = k16 * 8 + e;
-                o[e] = j < 32 ? f0[j] : f1[j - 32];
+                a = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
               } else {
                 const int j = k16 * 4 + (e >> 1);
-                o[e] = (e & 1) ? f1[j] : f0[j];
+                a = __uint_as_float((e & 1) ? v1[j] : v0[j]);
               }
+              o[e] = fmaf(a, sc, sh);
             }
-            if (p.has_res) {
+            uint4 w;
+            if (!p.has_res) {
+              if (relu6) {
+                w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
+                w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
+              } else {
+                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+                w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+              }
+            } else {
+              if (relu6) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
+              }
               const uint4 rr = *dst;
               o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
               o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
               o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
               o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
+              w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+              w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
             }
-            uint4 w;
-            w.x = pack_bf16x2(o[0], o[1]);
-            w.y = pack_bf16x2(o[2], o[3]);
-            w.z = pack_bf16x2(o[4], o[5]);
-            w.w = pack_bf16x2(o[6], o[7]);
             *dst = w;
           }
           fence_proxy_async();
-          named_bar_sync(bar_done, 128);
-          if (elected) {
-            tma_store_3d(&tm_y, stg + buf * kChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tm_y, stg + buf * kWarpChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
             tma_store_commit();
             tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
             if (p.has_res) {
               int ntile = tile, nc = c + 2;
-              if (i == CPG - 1) { ntile = tile + tile_step; nc = g; }
+              if (i == CPG - 1) { ntile = tile + tile_step; nc = h; }
               if (ntile < p.num_tiles) {
                 const int nr = ntile / p.m_tiles;
-                mbar_expect_tx(&rbar[buf ^ 1], kChunkBytes);
-                tma_load_3d(stg + (buf ^ 1) * kChunkBytes, &tm_res, &rbar[buf ^ 1],
+                mbar_expect_tx(&rbar[buf ^ 1], kWarpChunkBytes);
+                tma_load_3d(stg + (buf ^ 1) * kWarpChunkBytes, &tm_res, &rbar[buf ^ 1],
                             (nr % p.t_tiles) * Cfg::kOutCols + nc * 64,
-                            ((ntile % p.m_tiles) * CG + int(cta_rank)) * kBlockM, nr / p.t_tiles);
+                            ((ntile % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, nr / p.t_tiles);
               }
             }
           }
+          __syncwarp();
         }
       }
-      if (elected) tma_store_wait_all<0>();
+      if (lane == 0) tma_store_wait_all<0>();
     } else {
       // fp32 NCW direct store, bias only; group g owns columns [g*BLOCK_N/2, (g+1)*BLOCK_N/2)
       int iter = 0;
@@ -469,8 +474,8 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
   CUtensorMap tw, tx, ty, tr;
   if (int e = make_tmap_2d(&tw, W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
   if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
-  if (int e = make_tmap_3d(&ty, y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
-  if (int e = make_tmap_3d(&tr, res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&ty, y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
+  if (int e = make_tmap_3d(&tr, res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
@@ -557,7 +562,7 @@ int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, co
   CUtensorMap tw, tx, ty;
   if (int e = make_tmap_2d(&tw, Wp, int64_t(C_in) * 5, C_out, int64_t(C_in) * 5 * 2, 64, 128)) return e;
   if (int e = make_tmap_3d(&tx, workspace, T, int64_t(C_in) * 3, B, x_pitch * 2, int64_t(C_in) * 3 * x_pitch * 2, 64, 64)) return e;
-  if (int e = make_tmap_3d(&ty, y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&ty, y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
   p.m_tiles = (C_out + kBlockM - 1) / kBlockM;

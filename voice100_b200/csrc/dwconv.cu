@@ -8,9 +8,9 @@
 //        X_q[m][kk] = x[t0 - p + 8(m+2q) + kk - d]      (rows are 16-byte shifts of the time series)
 //        W_q[kk][n] = w[16q + kk - n - d]               (a Toeplitz block of the filter, zero outside)
 //    i.e. Q = ceil((k+7+d)/16) mma.sync.m16n8k16 (bf16 x bf16 -> fp32) per 128 outputs.  The Toeplitz
-//    blocks live in registers for the whole row; the A fragments are plain coalesced 32-bit shared
-//    loads of the staged row (fragment word index = lane + 8q + {0,4,32,36}), and the D fragment is
-//    128 consecutive outputs, stored coalesced.  One warp per (batch, channel) row, 8 rows per CTA.
+//    blocks live in registers while a warp walks 8 batch rows of its channel (rows are double-buffered
+//    in shared memory with cp.async); the A fragments are conflict-free 64-bit shared loads of the staged
+//    row and the D fragment is 128 consecutive outputs, stored coalesced.  8 channels per CTA.
 //  * dw_s2_kernel: stride 2 (the first encoder block, 0.4 % of the depthwise FLOPs, HBM-bound): CUDA cores
 //    over a shared-memory staged row.
 //  * dw_simt_kernel: any stride / any k, plain CUDA cores; last resort and exported for cross-checking.
@@ -31,86 +31,123 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint3
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
+  // 16-byte global->shared copy that bypasses registers; src-size 0 zero-fills the destination
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one set of Toeplitz fragments
+
+// Stage x[b][c][tcA .. tcA + kDwRow) into `xs` with zeros outside [0, T).  16-byte chunks never straddle 0
+// (tcA % 8 == 0); a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
+__device__ __forceinline__ void dw_stage_row(__nv_bfloat16* xs, const __nv_bfloat16* xrow, int tcA, int T, int lane) {
+#pragma unroll
+  for (int v = lane; v < kDwRow / 8; v += 32) {
+    const int t = tcA + v * 8;
+    const bool ok = t >= 0 && t < T;
+    cp_async_16(xs + v * 8, xrow + (ok ? t : 0), ok);
+  }
+  cp_async_commit();
+}
+__device__ __forceinline__ void dw_fix_tail(__nv_bfloat16* xs, int tcA, int T, int lane) {
+  const int i0 = T - tcA;               // first staged index that is past the end of the clip
+  if ((T & 7) != 0 && i0 > 0 && i0 < kDwRow) {
+    const int i = i0 + lane;
+    if (lane < 8 - (T & 7)) xs[i] = __float2bfloat16(0.0f);
+  }
+}
+
+// Toeplitz-on-tensor-cores depthwise FIR (see the header comment).  Fragment geometry, per 128 outputs:
+//   logical   X_q[m][kk] = xs[u0 + 4*e4 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],  wz[i] = w[i - d4]
+// with e = pl8 - p = 4*e4 + d4.  The kk axis of the mma is permuted (physical columns {2j,2j+1,2j+8,2j+9}
+// carry logical kk = 4j..4j+3) so that a thread's (a0,a2) pair is ONE aligned 64-bit shared load, and the
+// rows g+8 of step q are the rows g of step q+4: Q+4 LDS.64 feed the Q mma of a tile.
 template <int Q>
 __global__ void __launch_bounds__(kDwWarps * 32)
 dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-              long long y_pitch, int C, int T, int k, int act) {
-  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][kDwRow];
+              long long y_pitch, int B, int C, int T, int k, int act) {
+  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][2][kDwRow];
   __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * kDwWarps + warp;
-  const int b = blockIdx.z;
+  const int b0 = blockIdx.z * kDwRowsPerWarp;
+  const int nb = min(kDwRowsPerWarp, B - b0);
   const int tc0 = blockIdx.x * kDwChunk;
   const int p = (k - 1) >> 1;
   const int pl8 = (p + 7) & ~7;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
   const int e = pl8 - p;
-  const int eh = e >> 1, d = e & 1;
-  __nv_bfloat16* xs = xs_all[warp];
-  __nv_bfloat16* ws = ws_all[warp];
-  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
-
-  // stage the row segment [tc0 - pl8, tc0 - pl8 + kDwRow) with zeros outside [0, T)
+  const int e4 = e >> 2, d4 = e & 3;
   const int tcA = tc0 - pl8;
-#pragma unroll
-  for (int v = lane; v < kDwRow / 8; v += 32) {
-    const int t = tcA + v * 8;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (t >= 0 && t < T) {
-      val = *reinterpret_cast<const uint4*>(xrow + t);
-      if (t + 8 > T) {  // straddles the end of the clip: the pitch padding is not data
-        uint32_t* u = reinterpret_cast<uint32_t*>(&val);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (t + i >= T) u[i >> 1] &= (i & 1) ? 0x0000FFFFu : 0xFFFF0000u;
-      }
-    }
-    *reinterpret_cast<uint4*>(xs + v * 8) = val;
-  }
-  // zero-extended filter: ws[8 + i] = w[i - d] for 0 <= i - d < k
+  __nv_bfloat16* ws = ws_all[warp];
+  const __nv_bfloat16* xbase = x + static_cast<long long>(c) * x_pitch;
+  const long long xbstride = static_cast<long long>(C) * x_pitch;
+
+  dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane);   // first row in flight
+
+  // zero-extended filter: ws[8 + i] = w[i - d4] for 0 <= i - d4 < k; Toeplitz fragments stay in registers
   for (int i = lane; i < 16 * Q + 8; i += 32) {
-    const int j = i - 8 - d;
+    const int j = i - 8 - d4;
     ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
   }
   __syncwarp();
-
   const int g = lane >> 2, tg = lane & 3;
   uint32_t bf0[Q], bf1[Q];
   {
     const unsigned short* wsu = reinterpret_cast<const unsigned short*>(ws);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const int i0 = 8 + 16 * q + 2 * tg - g;
+      const int i0 = 8 + 16 * q + 4 * tg - g;
       bf0[q] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);
-      bf1[q] = uint32_t(wsu[i0 + 8]) | (uint32_t(wsu[i0 + 9]) << 16);
+      bf1[q] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);
     }
   }
   const float sc = scale ? scale[c] : 1.0f;
   const float sh = shift[c];
-  const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs) + eh + lane;
-  __nv_bfloat16* yrow = y + (static_cast<long long>(b) * C + c) * y_pitch;
-
+  const bool relu6 = act == V100_ACT_RELU6;
   const int n_tiles = min(kDwChunk / 128, (T - tc0 + 127) / 128);
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const uint32_t* xt = xw + tile * 64;
-    uint32_t A0[Q + 4], A2[Q + 4];
-#pragma unroll
-    for (int q = 0; q < Q + 4; ++q) {
-      A0[q] = xt[8 * q];
-      A2[q] = xt[8 * q + 4];
+
+  for (int r = 0; r < nb; ++r) {
+    __nv_bfloat16* xs = xs_all[warp][r & 1];
+    if (r + 1 < nb) {   // prefetch the next batch row of this channel into the other buffer
+      dw_stage_row(xs_all[warp][(r + 1) & 1], xbase + (b0 + r + 1) * xbstride, tcA, T, lane);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    __syncwarp();
+    dw_fix_tail(xs, tcA, T, lane);
+    __syncwarp();
+    const uint2* xw = reinterpret_cast<const uint2*>(xs) + e4 + 2 * g + tg;   // 64-bit word (4 elements) index
+    __nv_bfloat16* yrow = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch;
+#pragma unroll 2
+    for (int tile = 0; tile < n_tiles; ++tile) {
+      const uint2* xt = xw + tile * 32;
+      uint2 A[Q + 4];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) mma_bf16_16816(acc, A0[q], A0[q + 4], A2[q], A2[q + 4], bf0[q], bf1[q]);
+      for (int q = 0; q < Q + 4; ++q) A[q] = xt[4 * q];
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      acc[i] = fmaf(acc[i], sc, sh);
-      if (act == V100_ACT_RELU6) acc[i] = fminf(fmaxf(acc[i], 0.0f), 6.0f);
+      for (int q = 0; q < Q; ++q) mma_bf16_16816(acc, A[q].x, A[q + 4].x, A[q].y, A[q + 4].y, bf0[q], bf1[q]);
+      uint32_t o0, o1;
+      if (relu6) {
+        o0 = pack_bf16x2_relu6(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
+        o1 = pack_bf16x2_relu6(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
+      } else {
+        o0 = pack_bf16x2(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
+        o1 = pack_bf16x2(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
+      }
+      const int t = tc0 + tile * 128 + 2 * lane;
+      if (t < T) *reinterpret_cast<uint32_t*>(yrow + t) = o0;
+      if (t + 64 < T) *reinterpret_cast<uint32_t*>(yrow + t + 64) = o1;
     }
-    const int t = tc0 + tile * 128 + 2 * lane;
-    if (t < T) *reinterpret_cast<uint32_t*>(yrow + t) = pack_bf16x2(acc[0], acc[1]);
-    if (t + 64 < T) *reinterpret_cast<uint32_t*>(yrow + t + 64) = pack_bf16x2(acc[2], acc[3]);
+    __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
 }
 
@@ -221,10 +258,10 @@ dw_simt_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __n
 template <int Q>
 static void launch_dw_mma(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
                           void* y, int64_t y_pitch, int B, int C, int T, int k, int act, cudaStream_t stream) {
-  dim3 grid((T + kDwChunk - 1) / kDwChunk, C / kDwWarps, B);
+  dim3 grid((T + kDwChunk - 1) / kDwChunk, C / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
   dw_mma_kernel<Q><<<grid, kDwWarps * 32, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<const __nv_bfloat16*>(w), scale, shift,
-      static_cast<__nv_bfloat16*>(y), y_pitch, C, T, k, act);
+      static_cast<__nv_bfloat16*>(y), y_pitch, B, C, T, k, act);
 }
 
 int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
@@ -239,8 +276,8 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
     return fail(V100_E_INVALID, "dwconv: pitches must be multiples of 8 and >= T, bases 16-byte aligned");
   if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
   const int p = (k - 1) / 2;
-  const int d = (((p + 7) & ~7) - p) & 1;
-  const int Q = (k + 7 + d + 15) / 16;
+  const int d4 = (((p + 7) & ~7) - p) & 3;
+  const int Q = (k + 7 + d4 + 15) / 16;
   if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 6) {
     switch (Q) {
       case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
