@@ -260,10 +260,8 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from voice100_b200.dist import max_over_ranks
+    ms_max = max_over_ranks(ms, dev)
     audio_seconds_per_step = world * B * CLIP_SECONDS
     value = audio_seconds_per_step * K / (ms_max / 1e3)
 
@@ -337,10 +335,7 @@ def main():
         tok_h, len_h = pipe.transcribe_host(host_wav[i & 1], host_len, device=dev)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    te = torch.tensor([dt], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = audio_seconds_per_step * Ke / float(te.item())
+    e2e_value = audio_seconds_per_step * Ke / max_over_ranks(dt, dev)
     h2d = B * L * 4 + B * 4
     d2h = int(tok_h.numel() * 8 + len_h.numel() * len_h.element_size())
 
@@ -364,6 +359,7 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "roofline_all": roofline_all,
+            "launch_ms": [[w["kind"], round(m, 4)] for w, m in zip(work, per_launch)],
             "cpu_baseline": cpu,
         }))
     if world > 1:
