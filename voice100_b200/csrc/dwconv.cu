@@ -9,7 +9,7 @@
 //        W_q[kk][n] = w[16q + kk - n - d]               (a Toeplitz block of the filter, zero outside)
 //    i.e. Q = ceil((k+7+d)/16) mma.sync.m16n8k16 (bf16 x bf16 -> fp32) per 128 outputs.  The Toeplitz
 //    blocks live in registers while a warp walks 8 batch rows of its channel (rows are double-buffered
-//    in shared memory with cp.async); the A fragments are conflict-free 64-bit shared loads of the staged
+//    in shared memory with cp.async); each A fragment is one conflict-free ldmatrix.x4 of the staged
 //    row and the D fragment is 128 consecutive outputs, stored coalesced.  8 channels per CTA.
 //  * dw_s2_kernel: stride 2 (the first encoder block, 0.4 % of the depthwise FLOPs, HBM-bound): CUDA cores
 //    over a shared-memory staged row.
@@ -62,17 +62,24 @@ __device__ __forceinline__ void dw_fix_tail(__nv_bfloat16* xs, int tcA, int T, i
   }
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+
 // Toeplitz-on-tensor-cores depthwise FIR (see the header comment).  Fragment geometry, per 128 outputs:
-//   logical   X_q[m][kk] = xs[u0 + 4*e4 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],  wz[i] = w[i - d4]
-// with e = pl8 - p = 4*e4 + d4.  The kk axis of the mma is permuted (physical columns {2j,2j+1,2j+8,2j+9}
-// carry logical kk = 4j..4j+3) so that a thread's (a0,a2) pair is ONE aligned 64-bit shared load, and the
-// rows g+8 of step q are the rows g of step q+4: Q+4 LDS.64 feed the Q mma of a tile.
-template <int Q>
+//   X_q[m][kk] = xs[u0 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],   wz[i] = w[i - e],  e = pl8 - p
+// Row m of X_q is the 16-byte chunk m + 2q of the staged row, so the whole 16x16 A fragment of step q is ONE
+// ldmatrix.x4 (four 8x8 matrices = four runs of 128 contiguous bytes, conflict-free) landing directly in the
+// register order mma.sync wants; the Toeplitz B fragments stay in registers while the warp walks 8 batch rows
+// of its channel.  Per tile: Q ldmatrix + Q mma + 12 epilogue instructions.
+template <int Q, bool RELU6>
 __global__ void __launch_bounds__(kDwWarps * 32)
 dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-              long long y_pitch, int B, int C, int T, int k, int act) {
-  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][2][kDwRow];
+              long long y_pitch, int B, int C, int T, int k) {
+  __shared__ __align__(128) __nv_bfloat16 xs_all[kDwWarps][2][kDwRow];
   __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -82,8 +89,7 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   const int tc0 = blockIdx.x * kDwChunk;
   const int p = (k - 1) >> 1;
   const int pl8 = (p + 7) & ~7;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
-  const int e = pl8 - p;
-  const int e4 = e >> 2, d4 = e & 3;
+  const int e = pl8 - p;          // the sub-chunk shift is folded into the zero-extended filter
   const int tcA = tc0 - pl8;
   __nv_bfloat16* ws = ws_all[warp];
   const __nv_bfloat16* xbase = x + static_cast<long long>(c) * x_pitch;
@@ -91,9 +97,9 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
 
   dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane);   // first row in flight
 
-  // zero-extended filter: ws[8 + i] = w[i - d4] for 0 <= i - d4 < k; Toeplitz fragments stay in registers
+  // zero-extended filter: ws[8 + i] = w[i - e] for 0 <= i - e < k; Toeplitz fragments stay in registers
   for (int i = lane; i < 16 * Q + 8; i += 32) {
-    const int j = i - 8 - d4;
+    const int j = i - 8 - e;
     ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
   }
   __syncwarp();
@@ -103,15 +109,17 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
     const unsigned short* wsu = reinterpret_cast<const unsigned short*>(ws);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const int i0 = 8 + 16 * q + 4 * tg - g;
+      const int i0 = 8 + 16 * q + 2 * tg - g;
       bf0[q] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);
-      bf1[q] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);
+      bf1[q] = uint32_t(wsu[i0 + 8]) | (uint32_t(wsu[i0 + 9]) << 16);
     }
   }
   const float sc = scale ? scale[c] : 1.0f;
   const float sh = shift[c];
-  const bool relu6 = act == V100_ACT_RELU6;
   const int n_tiles = min(kDwChunk / 128, (T - tc0 + 127) / 128);
+  // ldmatrix row address of this lane: matrix (lane>>3) = {rows 0-7 | rows 8-15} x {kk 0-7 | kk 8-15}
+  const uint32_t lm_off = uint32_t(8 * (lane & 7) + ((lane >> 3) & 1) * 64 + (lane >> 4) * 8) * 2u;
+  const int rem0 = T - tc0 - 2 * lane;   // outputs left from this lane's first output position
 
   for (int r = 0; r < nb; ++r) {
     __nv_bfloat16* xs = xs_all[warp][r & 1];
@@ -124,28 +132,31 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
     __syncwarp();
     dw_fix_tail(xs, tcA, T, lane);
     __syncwarp();
-    const uint2* xw = reinterpret_cast<const uint2*>(xs) + e4 + 2 * g + tg;   // 64-bit word (4 elements) index
-    __nv_bfloat16* yrow = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch;
-#pragma unroll 2
+    uint32_t a_addr = smem_u32(xs) + lm_off;
+    uint32_t* yp = reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0) + lane;
+    int rem = rem0;
+#pragma unroll 1
     for (int tile = 0; tile < n_tiles; ++tile) {
-      const uint2* xt = xw + tile * 32;
-      uint2 A[Q + 4];
-#pragma unroll
-      for (int q = 0; q < Q + 4; ++q) A[q] = xt[4 * q];
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int q = 0; q < Q; ++q) mma_bf16_16816(acc, A[q].x, A[q + 4].x, A[q].y, A[q + 4].y, bf0[q], bf1[q]);
+      for (int q = 0; q < Q; ++q) {
+        uint32_t a0, a1, a2, a3;
+        ldmatrix_x4(a_addr + q * 32, a0, a1, a2, a3);
+        mma_bf16_16816(acc, a0, a1, a2, a3, bf0[q], bf1[q]);
+      }
       uint32_t o0, o1;
-      if (relu6) {
+      if (RELU6) {
         o0 = pack_bf16x2_relu6(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
         o1 = pack_bf16x2_relu6(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
       } else {
         o0 = pack_bf16x2(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
         o1 = pack_bf16x2(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
       }
-      const int t = tc0 + tile * 128 + 2 * lane;
-      if (t < T) *reinterpret_cast<uint32_t*>(yrow + t) = o0;
-      if (t + 64 < T) *reinterpret_cast<uint32_t*>(yrow + t + 64) = o1;
+      if (rem > 0) yp[0] = o0;
+      if (rem > 64) yp[32] = o1;
+      a_addr += 256;
+      yp += 64;
+      rem -= 128;
     }
     __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
@@ -259,9 +270,13 @@ template <int Q>
 static void launch_dw_mma(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
                           void* y, int64_t y_pitch, int B, int C, int T, int k, int act, cudaStream_t stream) {
   dim3 grid((T + kDwChunk - 1) / kDwChunk, C / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
-  dw_mma_kernel<Q><<<grid, kDwWarps * 32, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), x_pitch, static_cast<const __nv_bfloat16*>(w), scale, shift,
-      static_cast<__nv_bfloat16*>(y), y_pitch, B, C, T, k, act);
+  auto xp = static_cast<const __nv_bfloat16*>(x);
+  auto wp = static_cast<const __nv_bfloat16*>(w);
+  auto yp = static_cast<__nv_bfloat16*>(y);
+  if (act == V100_ACT_RELU6)
+    dw_mma_kernel<Q, true><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
+  else
+    dw_mma_kernel<Q, false><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
 }
 
 int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
@@ -276,16 +291,17 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
     return fail(V100_E_INVALID, "dwconv: pitches must be multiples of 8 and >= T, bases 16-byte aligned");
   if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
   const int p = (k - 1) / 2;
-  const int d4 = (((p + 7) & ~7) - p) & 3;
-  const int Q = (k + 7 + d4 + 15) / 16;
-  if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 6) {
+  const int e = ((p + 7) & ~7) - p;
+  const int Q = (k + 7 + e + 15) / 16;
+  if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7) {
     switch (Q) {
       case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
       case 2: launch_dw_mma<2>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
       case 3: launch_dw_mma<3>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
       case 4: launch_dw_mma<4>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
       case 5: launch_dw_mma<5>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      default: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 6: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      default: launch_dw_mma<7>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
     }
   } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
     dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
