@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libv100.so")
+# V100_LIB selects an alternate build of the same ABI (same-box A/B measurements, tools/build_rev.sh)
+LIB_PATH = os.path.abspath(os.environ["V100_LIB"]) if os.environ.get("V100_LIB") else os.path.join(_HERE, "libv100.so")
 
 _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 

@@ -39,8 +39,8 @@ constexpr int kBAtomBytes = kBlockK * 64 * 2;       // 8 KB: 64 k-rows x 64 time
 constexpr int kChunkBytes = kBlockM * 64 * 2;       // 16 KB: 128 channels x 64 time steps
 constexpr int kWarpChunkBytes = 32 * 64 * 2;        // 4 KB: one epilogue warp's 32 channels x 64 time steps
 constexpr int kMaxTaps = 5;
-constexpr int kEpiWarps = 16;                       // 4 TMEM lane quadrants x 4 column chunks
-constexpr int kGemmThreads = 128 + 32 * kEpiWarps;  // 640
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = 8;
 
 enum { OUT_BF16 = 0, OUT_F32 = 1 };
 
@@ -62,13 +62,12 @@ template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG = 1>
 struct GemmCfg {
   static constexpr int kBCols = BLOCK_N / CG;  // time columns this CTA stages per k-block
   static constexpr int kStageBytes = kATileBytes + (kBCols / 64) * kBAtomBytes;
-  static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? kEpiWarps * kWarpChunkBytes : 0;
+  static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? 4 * kChunkBytes : 0;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = 1024 + STAGES * kStageBytes + kStagingBytes + kBarBytes;
   static constexpr int kTmemCols = 2 * N_ACC * BLOCK_N;
   static constexpr int kOutCols = N_ACC * BLOCK_N;       // output time steps per tile
-  static constexpr int kChunks = kOutCols / 64;           // 64-column chunks per tile = active warps per quadrant
-  static constexpr int kActiveEpiWarps = OUT_MODE == OUT_BF16 ? 4 * kChunks : kEpiWarps;
+  static constexpr int kChunksPerGroup = kOutCols / 128;  // 64-column chunks per epilogue group per tile
   static_assert(kTmemCols == 512 || kTmemCols == 256, "TMEM allocation must be a power of two");
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
@@ -90,8 +89,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
   uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
-  uint64_t* res_bar = bars + 2 * STAGES + 4;    // [kEpiWarps]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + kEpiWarps);
+  uint64_t* res_bar = bars + 2 * STAGES + 4;    // [8 epilogue warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,9 +110,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], Cfg::kActiveEpiWarps * CG);  // the leader's copy collects both CTAs' warps
+      mbar_init(&tmem_empty[a], kEpiWarps * CG);  // the leader's copy collects both CTAs' epilogue warps
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -213,135 +212,133 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;             // TMEM lane quadrant this warp may access
-    const int g = (warp - 4) >> 2;      // column group 0..3
+    const int g = (warp - 4) >> 2;      // epilogue group
     const int row = q * 32 + lane;      // accumulator row == output channel within the tile
     const uint32_t lane_addr = tmem_base + (uint32_t(q * 32) << 16);
 
     if constexpr (OUT_MODE == OUT_BF16) {
-      // Every epilogue warp is its own pipeline: it owns 32 accumulator rows (its TMEM lane quadrant q) and
-      // the 64-column chunk c = g of every tile; it stages the [32 x 64] bf16 sub-tile in its private
-      // 128B-swizzled 4 KB smem slot and TMA-stores it.  No cross-warp barriers.  16 warps = 4 per SM
-      // sub-partition, which is what hides the TMEM-load / shared-store / TMA latencies of one chunk.
-      const int c = g;
-      if (c < Cfg::kChunks) {
-        uint8_t* stg = staging + (warp - 4) * kWarpChunkBytes;
-        uint64_t* rbar = res_bar + (warp - 4);
-        const uint32_t swz = uint32_t(lane & 7);
-        uint8_t* rowp = stg + lane * 128;
-        const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
-        const bool relu6 = p.act == V100_ACT_RELU6;
-        auto row0_of = [&](int tile) { return ((tile % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32; };
+      // Every epilogue warp is its own pipeline: it owns 32 accumulator rows (its TMEM lane quadrant) and
+      // the 64-column chunks c = h, h+2, ... of the tile; it stages each [32 x 64] bf16 sub-tile in its
+      // private, 128B-swizzled, double-buffered 4 KB smem slot and TMA-stores it.  No cross-warp barriers.
+      constexpr int CPG = Cfg::kChunksPerGroup;
+      const int h = g;                                   // which half of the tile's chunks
+      uint8_t* stg = staging + (warp - 4) * 2 * kWarpChunkBytes;
+      uint64_t* rbar = res_bar + (warp - 4) * 2;
+      const uint32_t swz = uint32_t(lane & 7);
+      uint8_t* my_row = stg + lane * 128;
+      const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+      const bool relu6 = p.act == V100_ACT_RELU6;
 
-        float sc = 1.0f, sh = 0.0f;
-        if (tile0 < p.num_tiles) {
-          const int ch = row0_of(tile0) + lane;
-          sc = (p.scale != nullptr && ch < p.C_out) ? __ldg(p.scale + ch) : 1.0f;
-          sh = (ch < p.C_out) ? __ldg(p.shift + ch) : 0.0f;
-          if (p.has_res && lane == 0) {
-            const int r = tile0 / p.m_tiles;
-            mbar_expect_tx(rbar, kWarpChunkBytes);
-            tma_load_3d(stg, &tm_res, rbar, (r % p.t_tiles) * Cfg::kOutCols + c * 64, row0_of(tile0), r / p.t_tiles);
-          }
-        }
-        int iter = 0;
-        for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
-          const int r = tile / p.m_tiles;
-          const int t_tile = r % p.t_tiles;
-          const int b = r / p.t_tiles;
-          const int accbuf = iter & 1;
-          const int m0 = row0_of(tile);
-          // next tile's BN scalars: issued now, consumed one tile later (keeps the L2 latency off the chain)
-          const int ntile = tile + tile_step;
-          float sc_n = 1.0f, sh_n = 0.0f;
-          if (ntile < p.num_tiles) {
-            const int chn = row0_of(ntile) + lane;
-            sc_n = (p.scale != nullptr && chn < p.C_out) ? __ldg(p.scale + chn) : 1.0f;
-            sh_n = (chn < p.C_out) ? __ldg(p.shift + chn) : 0.0f;
-          }
-          mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
-          tc_fence_after();
-          if (p.has_res) mbar_wait(rbar, iter & 1);   // the slot holds this tile's residual sub-tile
+      if (p.has_res && lane == 0 && tile0 < p.num_tiles) {
+        const int r = tile0 / p.m_tiles;
+        mbar_expect_tx(&rbar[0], kWarpChunkBytes);
+        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + h * 64,
+                    ((tile0 % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, r / p.t_tiles);
+      }
+      int iter = 0;
+      uint32_t n = 0;  // chunk sequence number of this warp
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
+        const int m_tile = tile % p.m_tiles;
+        const int r = tile / p.m_tiles;
+        const int t_tile = r % p.t_tiles;
+        const int b = r / p.t_tiles;
+        const int accbuf = iter & 1;
+        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM + q * 32;
+        const int ch = m0 + lane;
+        const float sc = (p.scale != nullptr && ch < p.C_out) ? __ldg(p.scale + ch) : 1.0f;
+        const float sh = (ch < p.C_out) ? __ldg(p.shift + ch) : 0.0f;
+        mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < CPG; ++i, ++n) {
+          const int c = h + 2 * i;  // 64-column output chunk of this tile
+          const int buf = n & 1;
+          uint32_t v0[32], v1[32];
           const uint32_t col0 = accbuf * (N_ACC * BLOCK_N);
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {             // 32 output columns at a time
-            uint32_t v[32];
-            if (hf == 0 && !p.has_res) {
-              // the previous tile's TMA store must have read the slot out before it is overwritten; waiting
-              // here (not right after issuing it) hides that latency behind the tmem_full wait
-              if (lane == 0) tma_store_wait_read<0>();
-              __syncwarp();
+          if constexpr (N_ACC == 1) {
+            tmem_ld32(lane_addr + col0 + c * 64, v0);
+            tmem_ld32(lane_addr + col0 + c * 64 + 32, v1);
+          } else {
+            tmem_ld32(lane_addr + col0 + c * 32, v0);            // even output phase
+            tmem_ld32(lane_addr + col0 + BLOCK_N + c * 32, v1);  // odd output phase
+          }
+          tmem_ld_wait();
+          if (i == CPG - 1) {  // this warp is done reading the accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
+              else mbar_arrive(&tmem_empty[accbuf]);
             }
-            if constexpr (N_ACC == 1) {
-              tmem_ld32(lane_addr + col0 + c * 64 + hf * 32, v);
-            } else {  // 16 even-phase + 16 odd-phase accumulator columns interleave to 32 outputs
-              tmem_ld16(lane_addr + col0 + c * 32 + hf * 16, &v[0]);
-              tmem_ld16(lane_addr + col0 + BLOCK_N + c * 32 + hf * 16, &v[16]);
-            }
-            tmem_ld_wait();
-            if (hf == 1) {  // this warp is done reading the accumulator buffer
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) {
-                if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
-                else mbar_arrive(&tmem_empty[accbuf]);
-              }
-            }
+          }
+          // slot `buf` is free: lane 0 waited for its previous TMA store before the __syncwarp that ended
+          // the previous chunk.  With a residual it now holds this chunk's residual sub-tile.
+          if (p.has_res) mbar_wait(&rbar[buf], (n >> 1) & 1);
+          uint8_t* rowp = my_row + buf * kWarpChunkBytes;
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-              uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(hf * 4 + k16) ^ swz) << 4));
-              float o[8];
+          for (int k16 = 0; k16 < 8; ++k16) {
+            uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4));
+            float o[8];
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float a;
-                if constexpr (N_ACC == 1) a = __uint_as_float(v[k16 * 8 + e]);
-                else a = __uint_as_float(v[(e & 1) * 16 + k16 * 4 + (e >> 1)]);
-                o[e] = fmaf(a, sc, sh);
-              }
-              uint4 w;
-              if (!p.has_res) {
-                if (relu6) {
-                  w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
-                  w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
-                } else {
-                  w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-                  w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-                }
+            for (int e = 0; e < 8; ++e) {
+              float a;
+              if constexpr (N_ACC == 1) {
+                const int j = k16 * 8 + e;
+                a = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
               } else {
-                if (relu6) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
-                }
-                const uint4 rr = *dst;
-                o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
-                o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
-                o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
-                o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
+                const int j = k16 * 4 + (e >> 1);
+                a = __uint_as_float((e & 1) ? v1[j] : v0[j]);
+              }
+              o[e] = fmaf(a, sc, sh);
+            }
+            uint4 w;
+            if (!p.has_res) {
+              if (relu6) {
+                w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
+                w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
+              } else {
                 w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
                 w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
               }
-              *dst = w;
+            } else {
+              if (relu6) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
+              }
+              const uint4 rr = *dst;
+              o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
+              o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
+              o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
+              o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
+              w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+              w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
             }
+            *dst = w;
           }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            tma_store_3d(&tm_y, stg, t_tile * Cfg::kOutCols + c * 64, m0, b);
+            tma_store_3d(&tm_y, stg + buf * kWarpChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
             tma_store_commit();
-            if (p.has_res && ntile < p.num_tiles) {
-              tma_store_wait_read<0>();   // the slot has been read out: refill it with the next residual
-              const int nr = ntile / p.m_tiles;
-              mbar_expect_tx(rbar, kWarpChunkBytes);
-              tma_load_3d(stg, &tm_res, rbar, (nr % p.t_tiles) * Cfg::kOutCols + c * 64, row0_of(ntile), nr / p.t_tiles);
+            tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
+            if (p.has_res) {
+              int ntile = tile, nc = c + 2;
+              if (i == CPG - 1) { ntile = tile + tile_step; nc = h; }
+              if (ntile < p.num_tiles) {
+                const int nr = ntile / p.m_tiles;
+                mbar_expect_tx(&rbar[buf ^ 1], kWarpChunkBytes);
+                tma_load_3d(stg + (buf ^ 1) * kWarpChunkBytes, &tm_res, &rbar[buf ^ 1],
+                            (nr % p.t_tiles) * Cfg::kOutCols + nc * 64,
+                            ((ntile % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, nr / p.t_tiles);
+              }
             }
           }
           __syncwarp();
-          sc = sc_n;
-          sh = sh_n;
         }
-        if (lane == 0) tma_store_wait_all<0>();
       }
+      if (lane == 0) tma_store_wait_all<0>();
     } else {
-      // fp32 NCW direct store, bias only; warp group g owns columns [g*BLOCK_N/4, (g+1)*BLOCK_N/4)
+      // fp32 NCW direct store, bias only; group g owns columns [g*BLOCK_N/2, (g+1)*BLOCK_N/2)
       int iter = 0;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
         const int m_tile = tile % p.m_tiles;
@@ -356,12 +353,12 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
         mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int cc = 0; cc < BLOCK_N / 128; ++cc) {
-          const int col = g * (BLOCK_N / 4) + cc * 32;
+        for (int cc = 0; cc < BLOCK_N / 64; ++cc) {
+          const int col = g * (BLOCK_N / 2) + cc * 32;
           uint32_t v[32];
           tmem_ld32(lane_addr + accbuf * (N_ACC * BLOCK_N) + col, v);
           tmem_ld_wait();
-          if (cc == BLOCK_N / 128 - 1) {
+          if (cc == BLOCK_N / 64 - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[accbuf]);
