@@ -20,7 +20,7 @@
 namespace v100 {
 
 constexpr int kDwChunk = 1024;            // outputs per CTA along time (8 mma tiles)
-constexpr int kDwRow = kDwChunk + 128;    // staged inputs per row (halo <= 48 left, <= 93 right)
+constexpr int kDwRow = kDwChunk + 256;    // staged inputs per row: 9 tiles of 128 + (Q+1)*16 halo
 constexpr int kDwWarps = 8;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -45,9 +45,9 @@ constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one 
 
 // Stage x[b][c][tcA .. tcA + kDwRow) into `xs` with zeros outside [0, T).  16-byte chunks never straddle 0
 // (tcA % 8 == 0); a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
-__device__ __forceinline__ void dw_stage_row(__nv_bfloat16* xs, const __nv_bfloat16* xrow, int tcA, int T, int lane) {
-#pragma unroll
-  for (int v = lane; v < kDwRow / 8; v += 32) {
+__device__ __forceinline__ void dw_stage_row(__nv_bfloat16* xs, const __nv_bfloat16* xrow, int tcA, int T, int lane,
+                                             int n_chunks) {
+  for (int v = lane; v < n_chunks; v += 32) {
     const int t = tcA + v * 8;
     const bool ok = t >= 0 && t < T;
     cp_async_16(xs + v * 8, xrow + (ok ? t : 0), ok);
@@ -69,11 +69,14 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
 }
 
 // Toeplitz-on-tensor-cores depthwise FIR (see the header comment).  Fragment geometry, per 128 outputs:
-//   X_q[m][kk] = xs[u0 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],   wz[i] = w[i - e],  e = pl8 - p
+//   X_q[m][kk] = xs[u0 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],   wz[i] = w[i - e1]
 // Row m of X_q is the 16-byte chunk m + 2q of the staged row, so the whole 16x16 A fragment of step q is ONE
 // ldmatrix.x4 (four 8x8 matrices = four runs of 128 contiguous bytes, conflict-free) landing directly in the
 // register order mma.sync wants; the Toeplitz B fragments stay in registers while the warp walks 8 batch rows
 // of its channel.  Per tile: Q ldmatrix + Q mma + 12 epilogue instructions.
+// Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory), e = pl8 - p in [0,8).
+// Tiles start s = e - (e & 1) outputs BEFORE tc0 (an even shift keeps the bf16x2 stores aligned), which leaves
+// only e1 = e & 1 to fold into the filter and keeps Q = ceil((k + 7 + e1) / 16) <= 6 for k <= 83.
 template <int Q, bool RELU6>
 __global__ void __launch_bounds__(kDwWarps * 32)
 dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
@@ -89,17 +92,22 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   const int tc0 = blockIdx.x * kDwChunk;
   const int p = (k - 1) >> 1;
   const int pl8 = (p + 7) & ~7;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
-  const int e = pl8 - p;          // the sub-chunk shift is folded into the zero-extended filter
+  const int e = pl8 - p;
+  const int e1 = e & 1;           // folded into the zero-extended filter
+  const int s = e - e1;           // tiles start s outputs before tc0
   const int tcA = tc0 - pl8;
   __nv_bfloat16* ws = ws_all[warp];
   const __nv_bfloat16* xbase = x + static_cast<long long>(c) * x_pitch;
   const long long xbstride = static_cast<long long>(C) * x_pitch;
 
-  dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane);   // first row in flight
+  const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
+  const int n_tiles = (len + s + 127) / 128;
+  const int n_chunks = min(kDwRow / 8, 16 * n_tiles + 2 * Q);   // 16-byte chunks the tiles actually read
+  dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane, n_chunks);   // first row in flight
 
-  // zero-extended filter: ws[8 + i] = w[i - e] for 0 <= i - e < k; Toeplitz fragments stay in registers
+  // zero-extended filter: ws[8 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
   for (int i = lane; i < 16 * Q + 8; i += 32) {
-    const int j = i - 8 - e;
+    const int j = i - 8 - e1;
     ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
   }
   __syncwarp();
@@ -116,15 +124,14 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   }
   const float sc = scale ? scale[c] : 1.0f;
   const float sh = shift[c];
-  const int n_tiles = min(kDwChunk / 128, (T - tc0 + 127) / 128);
   // ldmatrix row address of this lane: matrix (lane>>3) = {rows 0-7 | rows 8-15} x {kk 0-7 | kk 8-15}
   const uint32_t lm_off = uint32_t(8 * (lane & 7) + ((lane >> 3) & 1) * 64 + (lane >> 4) * 8) * 2u;
-  const int rem0 = T - tc0 - 2 * lane;   // outputs left from this lane's first output position
+  const int pos0 = 2 * lane - s;         // this lane's first output, relative to tc0 (may be negative)
 
   for (int r = 0; r < nb; ++r) {
     __nv_bfloat16* xs = xs_all[warp][r & 1];
     if (r + 1 < nb) {   // prefetch the next batch row of this channel into the other buffer
-      dw_stage_row(xs_all[warp][(r + 1) & 1], xbase + (b0 + r + 1) * xbstride, tcA, T, lane);
+      dw_stage_row(xs_all[warp][(r + 1) & 1], xbase + (b0 + r + 1) * xbstride, tcA, T, lane, n_chunks);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -133,8 +140,8 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
     dw_fix_tail(xs, tcA, T, lane);
     __syncwarp();
     uint32_t a_addr = smem_u32(xs) + lm_off;
-    uint32_t* yp = reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0) + lane;
-    int rem = rem0;
+    __nv_bfloat16* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
+    int pos = pos0;
 #pragma unroll 1
     for (int tile = 0; tile < n_tiles; ++tile) {
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -152,11 +159,11 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
         o0 = pack_bf16x2(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
         o1 = pack_bf16x2(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
       }
-      if (rem > 0) yp[0] = o0;
-      if (rem > 64) yp[32] = o1;
+      if (pos >= 0 && pos < len) *reinterpret_cast<uint32_t*>(yp) = o0;
+      if (pos + 64 >= 0 && pos + 64 < len) *reinterpret_cast<uint32_t*>(yp + 64) = o1;
       a_addr += 256;
-      yp += 64;
-      rem -= 128;
+      yp += 128;
+      pos += 128;
     }
     __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
@@ -291,8 +298,8 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
     return fail(V100_E_INVALID, "dwconv: pitches must be multiples of 8 and >= T, bases 16-byte aligned");
   if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
   const int p = (k - 1) / 2;
-  const int e = ((p + 7) & ~7) - p;
-  const int Q = (k + 7 + e + 15) / 16;
+  const int e1 = (((p + 7) & ~7) - p) & 1;
+  const int Q = (k + 7 + e1 + 15) / 16;
   if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7) {
     switch (Q) {
       case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
