@@ -121,3 +121,47 @@ def test_tts_matches_golden():
     voiced = safe & (g["f0"] != 0)
     rep = orc.parity_report(torch.from_numpy(g["f0"][voiced]), f0.cpu()[torch.from_numpy(voiced)])
     assert rep["max_abs_rel_std"] < 0.10, rep
+
+
+def test_asr_full_size_properties():
+    """BASELINE.json configs[1] at full size (asr_en_base, 256 x 15 s, ragged lengths): the CPU oracle cannot
+    run all of it in seconds, so check size-independent properties -- determinism, batch-composition
+    invariance (utterances are independent: the sharding assumption of the multi-GPU path), the length
+    formula -- plus the oracle on a sample of utterances."""
+    B, L = 256, 240000
+    g = torch.Generator(device=DEV).manual_seed(4321)
+    wav = 0.1 * torch.randn((B, L), device=DEV, generator=g)
+    lengths = torch.from_numpy(synth.ragged_lengths(B, 32000, L, seed=4321))
+    # weights: BN calibrated by the oracle on a small batch so activations stay O(1)
+    sd = orc.to_torch_sd(synth.asr_state_dict(64, 512, 29, 512, seed=4321, randomize_bn=True))
+    calib_audio, _ = orc.logmel_batch(wav[:2, :48000].cpu(), [48000, 48000])
+    sd = orc.calibrate_asr(sd, calib_audio)
+    model = _load(v.AudioToTextCTC(64, 512, 29, 512), sd)
+    pipe = v.AsrPipeline(v.MelSpectrogramAudioTransform().to(DEV), model)
+    len_d = lengths.to(DEV)
+    tokens, out_len = pipe(wav, len_d)
+    tokens2, _ = pipe(wav, len_d)
+    torch.cuda.synchronize()
+    assert tokens.shape == (B, 751) and torch.equal(tokens, tokens2)                       # deterministic
+    assert out_len.cpu().tolist() == [((1 + int(n) // 160) + 1) // 2 for n in lengths]     # asr.py:81-82
+    sub, _ = pipe(wav[40:48].contiguous(), len_d[40:48].contiguous())
+    assert torch.equal(sub, tokens[40:48])                                                 # batch-invariant
+    # host path (pinned buffers, chunked H2D, async D2H) returns the same tokens
+    tok_h, len_h = pipe.transcribe_host(wav.cpu().pin_memory(), lengths.pin_memory(), device=DEV)
+    assert torch.equal(tok_h, tokens.cpu()) and len_h.tolist() == out_len.cpu().tolist()
+    # oracle on a sample of utterances (features padded to the batch's frame count with BLANK_AUDIO)
+    for i in (0, 131, 255):
+        n = int(lengths[i])
+        feat = orc.logmel_clip(wav[i, :n].cpu())
+        audio = torch.full((1, 1501, 64), orc.BLANK_AUDIO)
+        audio[0, : feat.shape[0]] = feat
+        with torch.no_grad():
+            ref = orc.asr_forward(audio, sd)
+        valid = int(out_len[i])
+        # calibrate the gate on this utterance's own bf16 error via the logits path
+        logits = model(audio.to(DEV)).cpu()
+        rep = orc.parity_report(ref[:, :valid], logits[:, :valid])
+        raw, gated, frac = orc.token_agreement(ref[:, :valid], tokens[i:i + 1, :valid].cpu(), 2.5 * rep["max_abs"])
+        print("full-size utt", i, rep, raw, gated, frac)
+        assert rep["max_abs_rel_std"] < LOGIT_MAX_REL_STD and rep["rms_rel_std"] < LOGIT_RMS_REL_STD
+        assert gated == 1.0 and raw > 0.85

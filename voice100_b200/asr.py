@@ -106,25 +106,26 @@ class AsrPipeline:
         return self.model.greedy(feats), self.model.output_length(audio_len)
 
     @torch.no_grad()
-    def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):
-        """Host buffers in (pin them for full PCIe speed), host tokens out: the end-to-end call a user makes.
-        The batch is cut into `chunks` groups of utterances; their H2D copies run on a side stream so that
-        chunk i+1 uploads while chunk i computes, and tokens come back with an async D2H per chunk.
-        -> (tokens int64 [B, T'] pinned host tensor, valid lengths int [B])."""
+    def submit_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):
+        """Asynchronous end-to-end call: host buffers in (pin them for full PCIe speed), host tokens out.
+        The batch is cut into `chunks` groups of utterances whose H2D copies run on a side stream, so chunk
+        i+1 uploads while chunk i computes, and each chunk's tokens come back with an async D2H.  Returns a
+        ticket; `ticket.result()` waits for THIS batch only, so the next batch can be submitted (and start
+        uploading) before the previous one has finished computing.  Two tickets may be in flight."""
         dev = torch.device(device)
         B = waveform.shape[0]
         n = max(1, min(chunks, B))
         cur = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
             self._copy_stream = torch.cuda.Stream(dev)
-            self._host_out = {}
+            self._host_out, self._slot = {}, 0
         T_out = (self.transform.num_frames(waveform.shape[1]) + 1) // 2
-        key = (B, T_out)
+        key = (B, T_out, self._slot)
+        self._slot ^= 1                      # double-buffered pinned outputs: two tickets in flight
         if key not in self._host_out:
-            self._host_out = {key: (torch.empty((B, T_out), dtype=torch.int64).pin_memory(),
-                                    torch.empty((B,), dtype=torch.int32).pin_memory())}
+            self._host_out[key] = (torch.empty((B, T_out), dtype=torch.int64).pin_memory(),
+                                   torch.empty((B,), dtype=torch.int32).pin_memory())
         tok_h, len_h = self._host_out[key]
-        self._copy_stream.wait_stream(cur)
         staged = []
         for i in range(n):
             a, b = B * i // n, B * (i + 1) // n
@@ -141,5 +142,19 @@ class AsrPipeline:
             tokens, out_len = self(w, ln)
             tok_h[a:b].copy_(tokens, non_blocking=True)
             len_h[a:b].copy_(out_len.to(torch.int32), non_blocking=True)
-        cur.synchronize()
-        return tok_h, len_h
+        done = torch.cuda.Event()
+        done.record(cur)
+        return _Ticket(done, tok_h, len_h)
+
+    def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):
+        """Synchronous form of submit_host -> (tokens int64 [B, T'] pinned host tensor, valid lengths [B])."""
+        return self.submit_host(waveform, lengths, device, chunks).result()
+
+
+class _Ticket:
+    def __init__(self, event, tokens, lengths):
+        self._event, self._tokens, self._lengths = event, tokens, lengths
+
+    def result(self):
+        self._event.synchronize()
+        return self._tokens, self._lengths
