@@ -19,13 +19,14 @@ extern "C" void rfft512_power_host(const float* frame, float* power) {
   static cpx tw[512];
   for (int k = 0; k < 512; ++k) { tw[k].x = (float)cos(-2.0*M_PI*k/512.0); tw[k].y = (float)sin(-2.0*M_PI*k/512.0); }
   cpx A[256], B[256];
-  for (int n = 0; n < 256; ++n) { A[n].x = frame[2*n]; A[n].y = frame[2*n+1]; }
-  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 256, 1, i, tw);
-  for (int i = 0; i < 64; ++i) fft256_butterfly(B, A, 64, 4, i, tw);
-  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 16, 16, i, tw);
-  for (int i = 0; i < 64; ++i) fft256_butterfly(B, A, 4, 64, i, tw);
-  for (int k = 0; k <= 256; ++k) power[k] = rfft512_power(A, k, tw);
+  for (int n = 0; n < 256; ++n) { A[fswz(n)].x = frame[2*n]; A[fswz(n)].y = frame[2*n+1]; }
+  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 256, 1, i, fft256_twiddles(1, i, tw));
+  for (int i = 0; i < 64; ++i) fft256_butterfly(B, A, 64, 4, i, fft256_twiddles(4, i, tw));
+  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 16, 16, i, fft256_twiddles(16, i, tw));
+  for (int i = 0; i < 64; ++i) fft256_butterfly_last(B, A, i);
+  for (int k = 0; k <= 256; ++k) power[k] = rfft512_power(A, k, tw[k]);
 }
+extern "C" int fswz_host(int i) { return fswz(i); }
 """
 
 
@@ -60,6 +61,33 @@ def test_rfft512_power_matches_numpy(host_fft):
     tone = np.cos(2 * np.pi * 37 * np.arange(512) / 512).astype(np.float32)
     p = host_fft(tone)
     assert p.argmax() == 37 and abs(p[37] - 256.0 ** 2) < 1e-2 * 256.0 ** 2       # one bin, N/2 amplitude
+
+
+def test_swizzle_is_a_conflict_free_bijection(host_fft):
+    import glob
+    so = glob.glob(os.path.join(tempfile.gettempdir(), "*", "h.so"))
+    lib = ctypes.CDLL(sorted(so, key=os.path.getmtime)[-1])
+    f = [lib.fswz_host(i) for i in range(256)]
+    assert sorted(f) == list(range(256))
+
+    def wavefronts(addrs):           # 64-bit accesses: two half-warps, 16 bank pairs
+        tot = 0
+        for half in (addrs[:16], addrs[16:]):
+            banks = {}
+            for a in set(half):
+                banks.setdefault(a % 16, set()).add(a)
+            tot += max(len(v) for v in banks.values())
+        return tot
+    n, s = 256, 1
+    while n > 1:
+        m = n // 4
+        for base in (0, 32):
+            idx = [base + l for l in range(32)]
+            for j in range(4):
+                assert wavefronts([f[i % s + s * (i // s + j * m)] for i in idx]) == 2       # reads
+                assert wavefronts([f[i % s + s * (4 * (i // s) + j)] for i in idx]) == 2     # writes
+        n //= 4
+        s *= 4
 
 
 def test_frame_pipeline_matches_oracle(host_fft):

@@ -17,9 +17,11 @@ constexpr int kMelWarps = 8;
 constexpr int kMelFrames = 64;  // frames per CTA
 constexpr int kNMels = 64;
 constexpr int kNFft = 512, kWin = 400, kHop = 160, kWinLeft = (kNFft - kWin) / 2;  // data_modules.py:266-269
-constexpr int kMelSmemBytes = 512 * 8 + 2 * kMelWarps * 256 * 8 + kNMels * (kMelFrames + 1) * 4 + kWin * 4;
+constexpr int kMelMaxTaps = 24;   // longest mel filter (bins); the HTK bank at 512/16 kHz/64 needs 20
+constexpr int kMelSmemBytes = 512 * 8 + 2 * kMelWarps * 256 * 8 + kNMels * (kMelFrames + 1) * 4 + kWin * 4 +
+                              kMelMaxTaps * kNMels * 4;
 
-__global__ void __launch_bounds__(kMelWarps * 32)
+__global__ void __launch_bounds__(kMelWarps * 32, 3)
 logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, long long wav_pitch,
               const int32_t* __restrict__ fb_start, const int32_t* __restrict__ fb_count,
               const int32_t* __restrict__ fb_off, const float* __restrict__ fb_w, float log_offset, void* out, int T,
@@ -30,6 +32,7 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
   cpx (*bufB)[256] = bufA + kMelWarps;                                          // [kMelWarps][256]
   float (*tile)[kMelFrames + 1] = reinterpret_cast<float (*)[kMelFrames + 1]>(bufB + kMelWarps);  // [64][65]
   float* win = reinterpret_cast<float*>(tile + kNMels);                        // [kWin]
+  float (*melw)[kNMels] = reinterpret_cast<float (*)[kNMels]>(win + kWin);      // [kMelMaxTaps][64] tap-major
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -41,11 +44,32 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
     tw[k] = cpx{c, s};
   }
   for (int i = threadIdx.x; i < kWin; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(float(2 * i) / float(kWin));
+  for (int i = threadIdx.x; i < kMelMaxTaps * kNMels; i += blockDim.x) {   // melw[tap][filter], zero padded
+    const int tap = i / kNMels, m = i - tap * kNMels;
+    melw[tap][m] = tap < __ldg(fb_count + m) ? __ldg(fb_w + __ldg(fb_off + m) + tap) : 0.0f;
+  }
   __syncthreads();
+
+  // ---- per-lane constants, reused for the 8 frames this warp transforms ----
+  const tw3 t1a = fft256_twiddles(1, lane, tw), t1b = fft256_twiddles(1, lane + 32, tw);
+  const tw3 t2a = fft256_twiddles(4, lane, tw), t2b = fft256_twiddles(4, lane + 32, tw);
+  const cpx wlane = tw[lane];                  // exp(-2*pi*i*(lane + 32 i)/512) = wlane * tw[32 i]
+  float wv[16];                                // window taps of the samples this lane loads (0 outside 56..455)
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = 2 * (lane + 32 * u) + h;
+      wv[2 * u + h] = (m >= kWinLeft && m < kWinLeft + kWin) ? win[m - kWinLeft] : 0.0f;
+    }
+  const int s0a = __ldg(fb_start + lane), s0b = __ldg(fb_start + lane + 32);
+  const int cnta = __ldg(fb_count + lane), cntb = __ldg(fb_count + lane + 32);
+  const int cnt_max = max(__reduce_max_sync(0xffffffffu, cnta), __reduce_max_sync(0xffffffffu, cntb));
 
   const int L = len[b];
   const int n_frames = 1 + L / kHop;
   const float* x = wav + static_cast<long long>(b) * wav_pitch;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const float blank = out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(log_offset);
   cpx* A = bufA[warp];
   cpx* Bf = bufB[warp];
@@ -61,39 +85,60 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
     }
     // frame t covers reflect-padded samples [160 t, 160 t + 512) = clip samples 160 t - 256 + m
     const int base = kHop * t - kNFft / 2;
+    if (vec_ok && base + kWinLeft >= 0 && base + kWinLeft + kWin <= L) {
+      // interior frame: the 400 windowed samples are in range, 8-byte aligned pairs
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int n = lane + 32 * u;
-      float v[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int m = 2 * n + h;
-        float s = 0.0f;
-        if (m >= kWinLeft && m < kWinLeft + kWin) {
-          int i = base + m;
-          i = i < 0 ? -i : i;
-          i = i >= L ? 2 * (L - 1) - i : i;
-          s = __ldg(x + i) * win[m - kWinLeft];
-        }
-        v[h] = s;
+      for (int u = 0; u < 8; ++u) {
+        const int n = lane + 32 * u;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (2 * n >= kWinLeft && 2 * n < kWinLeft + kWin) v = __ldg(reinterpret_cast<const float2*>(x + base + 2 * n));
+        A[fswz(n)] = cpx{v.x * wv[2 * u], v.y * wv[2 * u + 1]};
       }
-      A[n] = cpx{v[0], v[1]};
-    }
-    __syncwarp();
-    fft256_butterfly(A, Bf, 256, 1, lane, tw);  fft256_butterfly(A, Bf, 256, 1, lane + 32, tw);  __syncwarp();
-    fft256_butterfly(Bf, A, 64, 4, lane, tw);   fft256_butterfly(Bf, A, 64, 4, lane + 32, tw);   __syncwarp();
-    fft256_butterfly(A, Bf, 16, 16, lane, tw);  fft256_butterfly(A, Bf, 16, 16, lane + 32, tw);  __syncwarp();
-    fft256_butterfly(Bf, A, 4, 64, lane, tw);   fft256_butterfly(Bf, A, 4, 64, lane + 32, tw);   __syncwarp();
-    for (int k = lane; k <= 256; k += 32) P[k] = rfft512_power(A, k, tw);
-    __syncwarp();
+    } else {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = lane + 32 * h;
-      const int s0 = __ldg(fb_start + m), cnt = __ldg(fb_count + m), off = __ldg(fb_off + m);
-      float acc = 0.0f;
-      for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(fb_w + off + i), P[s0 + i], acc);
-      tile[m][fl] = out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + log_offset);
+      for (int u = 0; u < 8; ++u) {
+        const int n = lane + 32 * u;
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m = 2 * n + h;
+          float sv = 0.0f;
+          if (m >= kWinLeft && m < kWinLeft + kWin) {
+            int i = base + m;
+            i = i < 0 ? -i : i;
+            i = i >= L ? 2 * (L - 1) - i : i;
+            sv = __ldg(x + i) * wv[2 * u + h];
+          }
+          v[h] = sv;
+        }
+        A[fswz(n)] = cpx{v[0], v[1]};
+      }
     }
+    __syncwarp();
+    fft256_butterfly(A, Bf, 256, 1, lane, t1a);   fft256_butterfly(A, Bf, 256, 1, lane + 32, t1b);   __syncwarp();
+    fft256_butterfly(Bf, A, 64, 4, lane, t2a);    fft256_butterfly(Bf, A, 64, 4, lane + 32, t2b);    __syncwarp();
+    // pass 3 has only 4 distinct twiddle sets per warp: broadcast shared loads instead of 12 more registers
+    fft256_butterfly(A, Bf, 16, 16, lane, fft256_twiddles(16, lane, tw));
+    fft256_butterfly(A, Bf, 16, 16, lane + 32, fft256_twiddles(16, lane + 32, tw));
+    __syncwarp();
+    fft256_butterfly_last(Bf, A, lane);           fft256_butterfly_last(Bf, A, lane + 32);           __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // exp(-2*pi*i*(32 i)/512) = exp(-i*pi*i/8): compile-time constants
+      float ci, si;
+      sincospif(-float(i) / 8.0f, &si, &ci);
+      P[lane + 32 * i] = rfft512_power(A, lane + 32 * i, cmul(wlane, cpx{ci, si}));
+    }
+    if (lane == 0) P[256] = rfft512_power(A, 256, cpx{-1.0f, 0.0f});
+    __syncwarp();
+    float acca = 0.0f, accb = 0.0f;
+    for (int i = 0; i < cnt_max; ++i) {   // melw is zero past each filter's own length; P stays in range
+      acca = fmaf(melw[i][lane], P[min(s0a + i, 256)], acca);
+      accb = fmaf(melw[i][lane + 32], P[min(s0b + i, 256)], accb);
+    }
+    (void)cnta; (void)cntb;
+    tile[lane][fl] = out_mode == V100_MEL_POWER_F32_NCW ? acca : logf(acca + log_offset);
+    tile[lane + 32][fl] = out_mode == V100_MEL_POWER_F32_NCW ? accb : logf(accb + log_offset);
     __syncwarp();
   }
   __syncthreads();
@@ -144,6 +189,7 @@ int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const
       fb_off == nullptr || fb_w == nullptr)
     return fail(V100_E_INVALID, "logmel: null pointer");
   if (B <= 0 || T <= 0 || B > 65535) return fail(V100_E_INVALID, "logmel: bad B=%d or T=%d", B, T);
+  if (wav_pitch & 1) return fail(V100_E_INVALID, "logmel: wav_pitch must be even (8-byte aligned sample pairs)");
   if (out_mode == V100_MEL_LOG_BF16_NCW) {
     if (out_pitch < T || (out_pitch & 7) || (reinterpret_cast<uintptr_t>(out) & 15))
       return fail(V100_E_INVALID, "logmel: bf16 NCW pitch must be >= T and a multiple of 8, base 16B aligned");
