@@ -189,7 +189,6 @@ int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const
       fb_off == nullptr || fb_w == nullptr)
     return fail(V100_E_INVALID, "logmel: null pointer");
   if (B <= 0 || T <= 0 || B > 65535) return fail(V100_E_INVALID, "logmel: bad B=%d or T=%d", B, T);
-  if (wav_pitch & 1) return fail(V100_E_INVALID, "logmel: wav_pitch must be even (8-byte aligned sample pairs)");
   if (out_mode == V100_MEL_LOG_BF16_NCW) {
     if (out_pitch < T || (out_pitch & 7) || (reinterpret_cast<uintptr_t>(out) & 15))
       return fail(V100_E_INVALID, "logmel: bf16 NCW pitch must be >= T and a multiple of 8, base 16B aligned");
