@@ -125,7 +125,7 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def cpu_oracle_throughput(min_seconds=10.0, batch=8, max_reps=6):
+def cpu_oracle_throughput(min_seconds=10.0, batch=8, max_reps=60):
     """The CPU oracle on a bounded sample of the workload: `batch` x 15 s clips per pass, repeated until
     `min_seconds` of CPU work has been timed.  -> (audio_s_per_s, threads, sample description)."""
     import torch
@@ -196,6 +196,62 @@ def run_reference(args):
     }))
 
 
+def run_tts(args):
+    """Secondary workload (BASELINE.json configs[2], tts_en_base): text [B,100] -> TextToAlignTextModel ->
+    host align_batch (seeded synthetic alignment) -> AlignTextToAudioModel.predict -> WORLD
+    parameters.  Metric: seconds of output audio (10 ms frames) per second.  Not the headline metric."""
+    import numpy as np
+    import torch
+    import voice100_b200 as v
+    from voice100_b200 import _lib, synth
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, Ltxt, V, H = args.batch, 100, 29, 512
+    amodel = v.TextToAlignTextModel(V, H)
+    amodel.load_state_dict({k: torch.from_numpy(np.asarray(t)) for k, t in synth.align_state_dict(V, H, seed=1234).items()})
+    vmodel = v.AlignTextToAudioModel(V, H)
+    vmodel.load_state_dict({k: torch.from_numpy(np.asarray(t)) for k, t in synth.audio_state_dict(V, H, seed=1234).items()})
+    amodel, vmodel = amodel.to(dev).eval(), vmodel.to(dev).eval()
+    text = torch.from_numpy(synth.text_tokens(B, Ltxt, V, seed=1234))
+    align = torch.from_numpy(synth.synthetic_alignment(B, Ltxt, seed=1234))
+    text_d = text.to(dev)
+    aligntext, at_len = v.align_batch(text, align)
+    at_d = aligntext.to(dev)
+    out_frames = float((2 * at_len.double() - 1).sum())          # valid output frames, 10 ms each
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W):
+        amodel(text_d); vmodel.predict(at_d)
+    torch.cuda.synchronize()
+    n0 = _lib.stats["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pred = amodel(text_d)
+        f0, logspc, codeap = vmodel.predict(at_d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = (_lib.stats["launches"] - n0) // K
+    # end to end: host text in, host WORLD parameters out, host alignment loop in between
+    t0 = time.perf_counter()
+    Ke = max(2, min(K, 5))
+    for _ in range(Ke):
+        pred_h = amodel(text.to(dev)).cpu()
+        at_h, _ = v.align_batch(text, align)                       # (the benchmark alignment, not exp(pred)-1)
+        f0, logspc, codeap = vmodel.predict(at_h.to(dev))
+        f0_h, logspc_h, codeap_h = f0.cpu(), logspc.cpu(), codeap.cpu()
+    dt = (time.perf_counter() - t0) / Ke
+    print(json.dumps({
+        "metric": "tts_output_audio_seconds_per_second", "value": round(out_frames * 0.01 / (ms * 1e-3), 1),
+        "unit": "audio-s/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"tts_en_base: TextToAlignTextModel + AlignTextToAudioModel(29,512), {B} x 100 tokens, "
+                               f"aligned text [{B},{aligntext.shape[1]}] -> WORLD [{B},{2 * aligntext.shape[1] - 1},259]"},
+        "e2e": {"value": round(out_frames * 0.01 / dt, 1), "unit": "audio-s/s", "note": "includes host align_batch, H2D of text and D2H of fp32 WORLD parameters",
+                "d2h_bytes_per_step": int(f0_h.numel() + logspc_h.numel() + codeap_h.numel()) * 4},
+        "gpu_launches": launches * K, "gpu_launches_per_step": launches}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,9 +260,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU (default: the metric's 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="asr", choices=["asr", "tts"], help="asr = the headline metric")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "tts":
+        return run_tts(args)
 
     import numpy as np
     import torch

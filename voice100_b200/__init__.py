@@ -11,5 +11,5 @@ every forward does, and fails loudly otherwise.
 from ._lib import V100Error, LIB_PATH  # noqa: F401
 from .data_modules import MelSpectrogramAudioTransform, BLANK_AUDIO, LOG_OFFSET, MELSPEC_DIM  # noqa: F401
 from .asr import AudioToTextCTC, ConvVoiceEncoder, LinearCharDecoder, AsrPipeline  # noqa: F401
-from .tts import TextToAlignTextModel, AlignTextToAudioModel, VoiceDecoder, WORLDNorm  # noqa: F401
+from .tts import TextToAlignTextModel, AlignTextToAudioModel, VoiceDecoder, WORLDNorm, align_batch  # noqa: F401
 from .text import CharTokenizer  # noqa: F401

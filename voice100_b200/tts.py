@@ -15,7 +15,7 @@ from ._lib import V100Error
 from .blocks import InvertedResidualParams, PreparedCache, require_eval_cuda, run_inverted_residual
 from .synth import ALIGN_KERNELS, VOICE_DECODER_POST_KERNELS, VOICE_DECODER_PRE_KERNELS
 
-__all__ = ["TextToAlignTextModel", "AlignTextToAudioModel", "VoiceDecoder", "WORLDNorm"]
+__all__ = ["TextToAlignTextModel", "AlignTextToAudioModel", "VoiceDecoder", "WORLDNorm", "align_batch"]
 
 
 def _head(conv: nn.Conv1d):
@@ -64,6 +64,40 @@ class TextToAlignTextModel(nn.Module):
                 raise IndexError("alignment runs past the aligned text (same failure as the reference)")
             out[s:e] = [tok] * (e - s)
         return torch.tensor(out, dtype=text.dtype)
+
+
+def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_value: int = 0):
+    """Vectorised host form of `TextToAlignTextModel.align` over a padded batch: text int64 [B, L],
+    align float [B, L, 2] (gap, duration per token, in 20 ms frames), optional text_len [B].
+    -> (aligntext int64 [B, T_max] padded with `pad_value`, aligntext_len int32 [B]).
+    Same arithmetic as the reference loop (tts.py:89-110): a float64 running sum of the float32 entries,
+    round-half-to-even, every token at least one frame, total length head + int(sum(align)) + tail."""
+    import numpy as np
+    text_np = text.detach().cpu().numpy()
+    al = align.detach().cpu().numpy().astype(np.float64)
+    B, L = text_np.shape
+    lens = np.full((B,), L, np.int64) if text_len is None else np.asarray(text_len.detach().cpu()).astype(np.int64)
+    outs = []
+    for b in range(B):
+        n = int(lens[b])
+        a = al[b, :n]
+        flat = a.reshape(-1)                                  # gap0, dur0, gap1, dur1, ...
+        t = head + np.cumsum(flat)                            # sequential double additions, like the loop
+        s = np.rint(t[0::2]).astype(np.int64)                 # python round() == rint (half to even)
+        e = np.rint(t[1::2]).astype(np.int64)
+        e = np.where(s == e, np.maximum(0, e + 1), e)
+        total = head + int(torch.sum(align[b, :n])) + tail    # the reference sums in float32 (torch.sum)
+        if n and (s.min() < 0 or e.max() > total):
+            raise IndexError("alignment runs past the aligned text (same failure as the reference)")
+        out = np.full((total,), 0, np.int64)
+        for i in range(n):                                    # later tokens overwrite earlier ones, as in the loop
+            out[s[i]:e[i]] = text_np[b, i]
+        outs.append(out)
+    T = max(len(o) for o in outs)
+    res = np.full((B, T), pad_value, np.int64)
+    for b, o in enumerate(outs):
+        res[b, :len(o)] = o
+    return torch.from_numpy(res), torch.tensor([len(o) for o in outs], dtype=torch.int32)
 
 
 class VoiceDecoder(nn.Module):
