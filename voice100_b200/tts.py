@@ -89,9 +89,14 @@ def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_va
         total = head + int(torch.sum(align[b, :n])) + tail    # the reference sums in float32 (torch.sum)
         if n and (s.min() < 0 or e.max() > total):
             raise IndexError("alignment runs past the aligned text (same failure as the reference)")
-        out = np.full((total,), 0, np.int64)
-        for i in range(n):                                    # later tokens overwrite earlier ones, as in the loop
-            out[s[i]:e[i]] = text_np[b, i]
+        # frame f belongs to the LAST token i with s_i <= f < e_i (later tokens overwrite earlier ones in the
+        # reference loop); s is non-decreasing, so that is one searchsorted per utterance
+        out = np.zeros((total,), np.int64)
+        if n:
+            f = np.arange(total)
+            i = np.searchsorted(s, f, side="right") - 1
+            ok = (i >= 0) & (f < e[np.maximum(i, 0)])
+            out[ok] = text_np[b, i[ok]]
         outs.append(out)
     T = max(len(o) for o in outs)
     res = np.full((B, T), pad_value, np.int64)
