@@ -44,7 +44,7 @@ def step(src, dst):
     mel = [i for i in ids if "logmel" in by_id[i]["name"]]
     start = mel[-2] if len(mel) >= 2 else mel[-1]          # one full step, away from the warm-up
     end = next((i for i in ids if i > start and "logmel" in by_id[i]["name"]), ids[-1] + 1)
-    sel = [i for i in ids if start <= i < end and "v100::" in by_id[i]["name"]]
+    sel = [i for i in ids if start <= i < end]
     tot = sum(by_id[i]["gpu__time_duration.sum"] for i in sel)
     out = ["# one ASR step (asr_en_base, 256 x 15 s) under ncu: cold-cache, serialised -- compare SHARES, not absolutes",
            "kernel,grid,block,duration_us,share,dram_read_MB,dram_write_MB"]

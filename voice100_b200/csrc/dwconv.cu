@@ -3,14 +3,11 @@
 // Two kernels:
 //  * dw_mma_kernel (stride 1, the hot one).  With k up to 83 taps the depthwise stage of
 //    ConvVoiceEncoder costs 72 MFLOP per audio-second -- on fp32 CUDA cores that is ~2.5x MORE time
-//    than its HBM traffic, so the FIR is evaluated on the tensor cores instead: for one channel,
-//        out[t0 + 8m + n] = sum_q sum_kk  X_q[m][kk] * W_q[kk][n],     m<16, n<8, kk<16
-//        X_q[m][kk] = x[t0 - p + 8(m+2q) + kk - d]      (rows are 16-byte shifts of the time series)
-//        W_q[kk][n] = w[16q + kk - n - d]               (a Toeplitz block of the filter, zero outside)
-//    i.e. Q = ceil((k+7+d)/16) mma.sync.m16n8k16 (bf16 x bf16 -> fp32) per 128 outputs.  The Toeplitz
-//    blocks live in registers while a warp walks 8 batch rows of its channel (rows are double-buffered
-//    in shared memory with cp.async); each A fragment is one conflict-free ldmatrix.x4 of the staged
-//    row and the D fragment is 128 consecutive outputs, stored coalesced.  8 channels per CTA.
+//    than its HBM traffic, so the FIR is evaluated on the tensor cores instead, as Toeplitz blocks of the
+//    filter times 16-sample columns of the time series (mma.sync.m16n8k16, bf16 x bf16 -> fp32,
+//    Q = ceil((k+15+e1)/16) <= 7 per 128 outputs; geometry in the comment above the kernel).  The Toeplitz
+//    blocks live in registers while a warp walks 8 batch rows of its channel; rows are double-buffered in
+//    shared memory with cp.async.  8 channels per CTA.
 //  * dw_s2_kernel: stride 2 (the first encoder block, 0.4 % of the depthwise FLOPs, HBM-bound): CUDA cores
 //    over a shared-memory staged row.
 //  * dw_simt_kernel: any stride / any k, plain CUDA cores; last resort and exported for cross-checking.
@@ -62,28 +59,25 @@ __device__ __forceinline__ void dw_fix_tail(__nv_bfloat16* xs, int tcA, int T, i
   }
 }
 
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-               : "r"(addr));
-}
-
-// Toeplitz-on-tensor-cores depthwise FIR (see the header comment).  Fragment geometry, per 128 outputs:
-//   X_q[m][kk] = xs[u0 + 8(m + 2q) + kk],   W_q[kk][n] = wz[16q + kk - n],   wz[i] = w[i - e1]
-// Row m of X_q is the 16-byte chunk m + 2q of the staged row, so the whole 16x16 A fragment of step q is ONE
-// ldmatrix.x4 (four 8x8 matrices = four runs of 128 contiguous bytes, conflict-free) landing directly in the
-// register order mma.sync wants; the Toeplitz B fragments stay in registers while the warp walks 8 batch rows
-// of its channel.  Per tile: Q ldmatrix + Q mma + 12 epilogue instructions.
-// Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory), e = pl8 - p in [0,8).
-// Tiles start s = e - (e & 1) outputs BEFORE tc0 (an even shift keeps the bf16x2 stores aligned), which leaves
-// only e1 = e & 1 to fold into the filter and keeps Q = ceil((k + 7 + e1) / 16) <= 6 for k <= 83.
+// Toeplitz-on-tensor-cores depthwise FIR.  Per tile of 128 outputs of one (batch, channel) row:
+//   D[m][n] = out[tau + m + 16 n] = sum_q sum_kk  W_q[m][kk] * X_q[kk][n],        m < 16, n < 8, kk < 16
+//   X_q[kk][n] = xs[128 tile + 16 (n + q) + kk]      (the DATA is the small "B" operand: 256 contiguous bytes)
+//   W_q[m][kk] = wz[16 q + kk - m],  wz[i] = w[i - e1]   (Toeplitz blocks of the filter = "A", in registers)
+// The mma's kk axis is permuted (physical rows {2j, 2j+1, 2j+8, 2j+9} carry logical kk = 4j .. 4j+3), so a
+// thread's (b0, b1) pair is ONE aligned 64-bit shared load at uint2 index 32 tile + 4 q + lane: consecutive
+// lanes read consecutive 8-byte words (conflict-free, 2 wavefronts per mma -- the ldmatrix form of this kernel
+// needed 4 and was shared-memory bound at 88 % of L1 throughput).  The D fragment holds outputs 16 apart;
+// one xor-shuffle pair regroups them into bf16x2 pairs that are stored as full 32-byte sectors.
+// Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory); tiles start
+// s = e - (e & 1) outputs before tc0 (e = pl8 - p), leaving e1 = e & 1 to fold into the zero-extended filter;
+// Q = ceil((k + 15 + e1) / 16) <= 7 for k <= 83.
 template <int Q, bool RELU6>
 __global__ void __launch_bounds__(kDwWarps * 32)
 dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
               long long y_pitch, int B, int C, int T, int k) {
   __shared__ __align__(128) __nv_bfloat16 xs_all[kDwWarps][2][kDwRow];
-  __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 8];
+  __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * kDwWarps + warp;
@@ -105,28 +99,30 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   const int n_chunks = min(kDwRow / 8, 16 * n_tiles + 2 * Q);   // 16-byte chunks the tiles actually read
   dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane, n_chunks);   // first row in flight
 
-  // zero-extended filter: ws[8 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
-  for (int i = lane; i < 16 * Q + 8; i += 32) {
-    const int j = i - 8 - e1;
+  // zero-extended filter: ws[16 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
+  for (int i = lane; i < 16 * Q + 16; i += 32) {
+    const int j = i - 16 - e1;
     ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
   }
   __syncwarp();
   const int g = lane >> 2, tg = lane & 3;
-  uint32_t bf0[Q], bf1[Q];
+  uint32_t af[Q][4];
   {
     const unsigned short* wsu = reinterpret_cast<const unsigned short*>(ws);
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-      const int i0 = 8 + 16 * q + 2 * tg - g;
-      bf0[q] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);
-      bf1[q] = uint32_t(wsu[i0 + 8]) | (uint32_t(wsu[i0 + 9]) << 16);
+      const int i0 = 16 + 16 * q + 4 * tg - g;   // wz[16q + kk - m] at m = g, kk = 4 tg
+      af[q][0] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);          // (m = g    , kk = 4tg, 4tg+1)
+      af[q][1] = uint32_t(wsu[i0 - 8]) | (uint32_t(wsu[i0 - 7]) << 16);      // (m = g + 8, kk = 4tg, 4tg+1)
+      af[q][2] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);      // (m = g    , kk = 4tg+2, 4tg+3)
+      af[q][3] = uint32_t(wsu[i0 - 6]) | (uint32_t(wsu[i0 - 5]) << 16);      // (m = g + 8, kk = 4tg+2, 4tg+3)
     }
   }
   const float sc = scale ? scale[c] : 1.0f;
   const float sh = shift[c];
-  // ldmatrix row address of this lane: matrix (lane>>3) = {rows 0-7 | rows 8-15} x {kk 0-7 | kk 8-15}
-  const uint32_t lm_off = uint32_t(8 * (lane & 7) + ((lane >> 3) & 1) * 64 + (lane >> 4) * 8) * 2u;
-  const int pos0 = 2 * lane - s;         // this lane's first output, relative to tc0 (may be negative)
+  const bool even = (g & 1) == 0;
+  // after the pair exchange this lane stores outputs (t, t+1) and (t+16, t+17), t relative to tc0:
+  const int pos0 = 32 * tg + (even ? g : g + 7) - s;
 
   for (int r = 0; r < nb; ++r) {
     __nv_bfloat16* xs = xs_all[warp][r & 1];
@@ -139,7 +135,7 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
     __syncwarp();
     dw_fix_tail(xs, tcA, T, lane);
     __syncwarp();
-    uint32_t a_addr = smem_u32(xs) + lm_off;
+    const uint2* xw = reinterpret_cast<const uint2*>(xs) + lane;
     __nv_bfloat16* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
     int pos = pos0;
 #pragma unroll 1
@@ -147,21 +143,28 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
       float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        uint32_t a0, a1, a2, a3;
-        ldmatrix_x4(a_addr + q * 32, a0, a1, a2, a3);
-        mma_bf16_16816(acc, a0, a1, a2, a3, bf0[q], bf1[q]);
+        const uint2 bq = xw[4 * q];
+        mma_bf16_16816(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
+      // acc = out[tau + g + 32tg + {0, 16}], out[tau + g + 8 + 32tg + {0, 16}]; trade with lane g^1 so that even
+      // g holds (g, g+1) of the first pair of rows and odd g holds (g-1+8, g+8) of the second
+      const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
+      const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
+      const float lo0 = even ? acc[0] : r0, hi0 = even ? r0 : acc[2];
+      const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
       uint32_t o0, o1;
       if (RELU6) {
-        o0 = pack_bf16x2_relu6(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
-        o1 = pack_bf16x2_relu6(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
+        o0 = pack_bf16x2_relu6(lo0, hi0);
+        o1 = pack_bf16x2_relu6(lo1, hi1);
       } else {
-        o0 = pack_bf16x2(fmaf(acc[0], sc, sh), fmaf(acc[1], sc, sh));
-        o1 = pack_bf16x2(fmaf(acc[2], sc, sh), fmaf(acc[3], sc, sh));
+        o0 = pack_bf16x2(lo0, hi0);
+        o1 = pack_bf16x2(lo1, hi1);
       }
       if (pos >= 0 && pos < len) *reinterpret_cast<uint32_t*>(yp) = o0;
-      if (pos + 64 >= 0 && pos + 64 < len) *reinterpret_cast<uint32_t*>(yp + 64) = o1;
-      a_addr += 256;
+      if (pos + 16 >= 0 && pos + 16 < len) *reinterpret_cast<uint32_t*>(yp + 16) = o1;
+      xw += 32;
       yp += 128;
       pos += 128;
     }
@@ -299,7 +302,7 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
   if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
   const int p = (k - 1) / 2;
   const int e1 = (((p + 7) & ~7) - p) & 1;
-  const int Q = (k + 7 + e1 + 15) / 16;
+  const int Q = (k + 15 + e1 + 15) / 16;
   if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7) {
     switch (Q) {
       case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
