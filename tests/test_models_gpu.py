@@ -165,3 +165,19 @@ def test_asr_full_size_properties():
         print("full-size utt", i, rep, raw, gated, frac)
         assert rep["max_abs_rel_std"] < LOGIT_MAX_REL_STD and rep["rms_rel_std"] < LOGIT_RMS_REL_STD
         assert gated == 1.0 and raw > 0.85
+
+
+def test_cuda_graph_replay_matches_eager():
+    """BASELINE.json configs[0] shape (asr_en_small, 8 x 10 s) captured into a CUDA graph."""
+    B, L = 8, 160000
+    model = _load(v.AudioToTextCTC(64, 256, 29, 256), synth.asr_state_dict(64, 256, 29, 256, seed=5, randomize_bn=True))
+    pipe = v.AsrPipeline(v.MelSpectrogramAudioTransform().to(DEV), model)
+    run = pipe.graphed(B, L, device=DEV)
+    for seed in (1, 2):
+        wav = torch.from_numpy(synth.noise_waveform(B, L, seed=seed)).to(DEV)
+        lengths = torch.from_numpy(synth.ragged_lengths(B, 20000, L, seed=seed)).to(DEV)
+        tok_e, len_e = pipe(wav, lengths)
+        tok_g, len_g = run(wav, lengths)
+        torch.cuda.synchronize()
+        assert tok_g.shape == (B, 501)
+        assert torch.equal(tok_e, tok_g) and torch.equal(len_e, len_g)
