@@ -372,18 +372,33 @@ def main():
         else:
             entry.update(bound="hbm", frac=round(gbs / peaks["hbm_gbs"], 4))
         roofline_all[kind] = entry
+    traffic = {}
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):   # newest round first
+        if name.endswith("_traffic.json"):
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                traffic = json.load(f)
+            break
+    tcls = traffic.get("per_kernel_class", {})
+    for kind, entry in roofline_all.items():
+        if kind in tcls:
+            entry["dram_bytes_per_step_ncu"] = tcls[kind]["dram_bytes_per_step"]
+            entry["algorithmic_bytes_per_step"] = classes[kind]["bytes"]
     dom = max(classes, key=lambda k: classes[k]["ms"])
     dc = classes[dom]
     if dom == "gemm":
         ach = dc["flops"] / dc["launches"] / (dc["ms"] / dc["launches"] * 1e-3) / 1e12
         roofline = dict(kernel="conv_gemm_kernel (tcgen05)", bound="tensor", achieved=round(ach, 2),
                         peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(ach / peaks["tf_sustained"], 4),
-                        traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                        traffic=(tcls["gemm"]["dram_bytes_per_launch"] if "gemm" in tcls else None),
+                        traffic_note="ncu dram__bytes_read+write per launch, mean over the step's GEMM launches (%s); "
+                                     "algorithmic bytes per launch: %.0f" % (traffic.get("source", "n/a"), dc["bytes"] / dc["launches"]),
+                        peak_source=peaks["source"] + ", sustained bf16",
                         note="mean over the %d GEMM launches of a step (algorithmic FLOPs / CUDA-event time)" % dc["launches"])
     else:
         ach = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
         roofline = dict(kernel=dom, bound="hbm", achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",
-                        frac=round(ach / peaks["hbm_gbs"], 4), traffic=None, peak_source=peaks["source"])
+                        frac=round(ach / peaks["hbm_gbs"], 4),
+                        traffic=(tcls[dom]["dram_bytes_per_launch"] if dom in tcls else None), peak_source=peaks["source"])
 
     # ---- end to end: pinned host waveforms in, host tokens out ----
     host_wav = [torch.empty((B, L), dtype=torch.float32).pin_memory() for _ in range(2)]
