@@ -297,10 +297,13 @@ def main():
     model = model.to(dev).eval()
     pipe = v.AsrPipeline(v.MelSpectrogramAudioTransform().to(dev), model)
 
-    # device-resident inputs: two rotating batches, each 245 MB (> the 126 MB L2), 0.1*N(0,1)
+    # device-resident inputs: 0.1*N(0,1); one batch is 245 MB (> the 126 MB L2) and every step streams
+    # ~23 GB of activations through HBM in between, so nothing of the input survives in L2 across steps
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     wavs = [0.1 * torch.randn((B, L), device=dev, generator=g) for _ in range(2)]
     lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+    run = pipe.graphed(B, L, device=dev)       # the public API's CUDA-graph form of the whole path
+    run.waveform.copy_(wavs[0])
 
     def barrier():
         if world > 1:
@@ -308,7 +311,7 @@ def main():
         torch.cuda.synchronize()
 
     for i in range(W):
-        pipe(wavs[i & 1], lengths)
+        run.graph.replay()
     n0 = _lib.stats["launches"]
     pipe(wavs[0], lengths)
     launches_per_step = _lib.stats["launches"] - n0
@@ -319,7 +322,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(K):
-        tokens, out_len = pipe(wavs[i & 1], lengths)
+        run.graph.replay()                      # 30 kernels of libv100 per replay
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -437,7 +440,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "clip_seconds": CLIP_SECONDS,
                        "parallelism": f"dp{world} (utterance-sharded, no data-path collective)",
-                       "l2": "inputs rotate between two 245 MB batches and every activation tensor exceeds the 126 MB L2"},
+                       "launch": "CUDA graph replay (AsrPipeline.graphed)",
+                       "l2": "the 245 MB input batch and every activation tensor exceed the 126 MB L2; ~23 GB stream through HBM per step"},
             "e2e": {"value": round(e2e_value, 1), "unit": "audio-s/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": Ke},
             "gpu_launches": launches_per_step * K,
