@@ -137,6 +137,16 @@ int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null
                       int B, int V, int T, void* stream);
 
 /*
+ * CTC collapse on the device: per row, within the first valid_len[b] tokens (all T when valid_len is
+ * NULL), drop tokens equal to their predecessor, then drop `blank`; survivors are written in order to
+ * out[b][0..out_len[b]) and the rest of the row is filled with `blank`.  Replaces the id-level effect of
+ * CharTokenizer/BasicTokenizer.merge_repeated (voice100/text.py:99-104,140-145) so that only collapsed
+ * ids need to cross PCIe.  tokens/out int64 [B][T] (distinct buffers).
+ */
+int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len,
+                      int B, int T, int blank, void* stream);
+
+/*
  * WORLD head tail: fp32 NCW [B][260][pitch] -> hasf0[B][T], f0[B][T], logspc[B][T][257],
  * codeap[B][T][1], with std*x+mean and f0 := 0 where hasf0 < 0 when `unnormalize` != 0.
  * Replaces split + WORLDNorm.unnormalize + where (tts.py:181-190,196-200; _layers_v1.py:131-138).

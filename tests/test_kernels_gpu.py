@@ -209,6 +209,30 @@ def test_layout_and_head_kernels():
     assert torch.equal(f2, v[:, 1]) and torch.equal(l2, v[:, 2:259].transpose(1, 2))
 
 
+def test_ctc_collapse_matches_reference_text_rule():
+    from voice100_b200.text import CharTokenizer
+    tok = CharTokenizer()
+    g = torch.Generator().manual_seed(3)
+    B, T = 37, 101
+    # runs of repeated ids with blanks in between, like greedy CTC output
+    base = torch.randint(0, 29, (B, T), generator=g)
+    rep = torch.randint(0, 3, (B, T), generator=g)
+    tokens = torch.where(rep > 0, torch.roll(base, 1, dims=1), base)
+    tokens[:, ::7] = 0
+    valid = torch.randint(0, T + 1, (B,), generator=g)
+    valid[0], valid[1] = 0, T
+    ids, counts = K.ctc_collapse(tokens.to(DEV), valid.to(DEV))
+    torch.cuda.synchronize()
+    for b in range(B):
+        seq = tokens[b, : int(valid[b])].tolist()
+        text = tok.decode(seq)
+        ref = tok.merge_repeated(text)
+        got = tok.decode(ids[b, : int(counts[b])].tolist())
+        # merge_repeated additionally maps the single string " " to "" (text.py:102-103); ids keep the space
+        assert got == ref or (ref == "" and got == " "), (b, text, ref, got)
+        assert (ids[b, int(counts[b]):] == 0).all()
+
+
 def test_errors_are_loud():
     from voice100_b200 import V100Error
     x = K.empty_ncw(1, 60, 16, DEV)     # C_in not a multiple of 8

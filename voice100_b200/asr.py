@@ -106,6 +106,13 @@ class AsrPipeline:
         return self.model.greedy(feats), self.model.output_length(audio_len)
 
     @torch.no_grad()
+    def transcribe_ids(self, waveform: torch.Tensor, lengths: torch.Tensor, blank: int = 0):
+        """waveform -> CTC-collapsed token ids on the device: (ids int64 [B, T'] blank-padded, counts int32 [B]).
+        `tokenizer.decode(ids[b, :counts[b]])` is then the final text (no merge_repeated pass needed)."""
+        tokens, out_len = self(waveform, lengths)
+        return K.ctc_collapse(tokens, out_len, blank)
+
+    @torch.no_grad()
     def _capture(self, batch: int, samples: int, dev):
         """-> (graph, static waveform, static lengths, static tokens, static out_len) for one fixed shape."""
         wav_s = torch.zeros((batch, samples), dtype=torch.float32, device=dev)

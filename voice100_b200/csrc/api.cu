@@ -145,6 +145,11 @@ int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null
   return ctc_finalize(y_ncw, y_pitch, logits_or_null, tokens, B, V, T, STREAM(stream));
 }
 
+int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
+                      int blank, void* stream) {
+  return ctc_collapse(tokens, valid_len, out, out_len, B, T, blank, STREAM(stream));
+}
+
 int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0,
                         float* f0, float* logspc, float* codeap, int B, int T, int unnormalize, void* stream) {
   return world_finalize(y_ncw, y_pitch, mean, std, hasf0, f0, logspc, codeap, B, T, unnormalize, STREAM(stream));

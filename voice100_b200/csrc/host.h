@@ -46,6 +46,8 @@ int embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y
                        cudaStream_t stream);
 int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* tokens, int B, int V, int T,
                  cudaStream_t stream);
+int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
+                 int blank, cudaStream_t stream);
 int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0, float* f0,
                    float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream);
 int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream);

@@ -134,6 +134,43 @@ int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* to
   return 0;
 }
 
+// CTC collapse on the device (voice100/text.py:99-104 merge_repeated, minus the string handling): within the
+// valid prefix of each row drop a token equal to its predecessor, then drop blanks (id 0).  One warp per row:
+// keep-flags -> ballot -> prefix popcount gives each survivor its output slot, order preserved.
+__global__ void __launch_bounds__(128)
+ctc_collapse_kernel(const int64_t* __restrict__ tokens, const int64_t* __restrict__ valid_len,
+                    int64_t* __restrict__ out, int32_t* __restrict__ out_len, int B, int T, int blank) {
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int64_t* in = tokens + static_cast<long long>(row) * T;
+  int64_t* o = out + static_cast<long long>(row) * T;
+  int n = valid_len ? static_cast<int>(valid_len[row]) : T;
+  n = n < 0 ? 0 : (n > T ? T : n);
+  int written = 0;
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int t = t0 + lane;
+    const int64_t cur = t < n ? in[t] : blank;
+    const int64_t prev = (t > 0 && t < n) ? in[t - 1] : -1;
+    const bool keep = t < n && cur != prev && cur != blank;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) o[written + __popc(m & ((1u << lane) - 1u))] = cur;
+    written += __popc(m);
+  }
+  for (int t = written + lane; t < T; t += 32) o[t] = blank;   // pad the tail with blanks
+  if (lane == 0) out_len[row] = written;
+}
+
+int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
+                 int blank, cudaStream_t stream) {
+  if (tokens == nullptr || out == nullptr || out_len == nullptr) return fail(V100_E_INVALID, "ctc_collapse: null pointer");
+  if (B <= 0 || T <= 0) return fail(V100_E_INVALID, "ctc_collapse: bad sizes");
+  if (tokens == out) return fail(V100_E_INVALID, "ctc_collapse: in-place collapse is not supported");
+  ctc_collapse_kernel<<<(B + 3) / 4, 128, 0, stream>>>(tokens, valid_len, out, out_len, B, T, blank);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // fp32 NCW [B][C][pitch] -> [B][T][C] through a 32x32 tile.
 __global__ void __launch_bounds__(256)
 ncw_to_ntc_kernel(const float* __restrict__ y, long long pitch, float* __restrict__ out, int C, int T) {

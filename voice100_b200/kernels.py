@@ -162,6 +162,18 @@ def ctc_finalize(y: Ncw, want_logits: bool = True):
     return logits, tokens
 
 
+def ctc_collapse(tokens: torch.Tensor, valid_len: torch.Tensor = None, blank: int = 0):
+    """tokens int64 [B, T] (+ valid lengths) -> (collapsed ids int64 [B, T] blank-padded, counts int32 [B])."""
+    _cuda(tokens, torch.int64)
+    B, T = tokens.shape
+    out = torch.empty_like(tokens)
+    out_len = torch.empty((B,), device=tokens.device, dtype=torch.int32)
+    vl = None if valid_len is None else valid_len.to(device=tokens.device, dtype=torch.int64).contiguous()
+    _lib.call("v100_ctc_collapse", tokens.data_ptr(), _ptr(vl), out.data_ptr(), out_len.data_ptr(), B, T, int(blank),
+              _stream())
+    return out, out_len
+
+
 def world_finalize(y: Ncw, mean, std, unnormalize: bool):
     B, T, dev = y.B, y.T, y.data.device
     assert y.C == 260
