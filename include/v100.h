@@ -10,8 +10,11 @@
  * Conventions
  *  - every pointer is a DEVICE pointer owned by the caller; the library allocates nothing;
  *  - activations are "NCW with pitch": x[b][c][t] at  base + (b*C + c)*pitch + t,  t < T,
- *    bf16 unless stated, pitch % 8 == 0 (16-byte rows) and base 16-byte aligned.  This is the
+ *    16-bit unless stated, pitch % 8 == 0 (16-byte rows) and base 16-byte aligned.  This is the
  *    reference's own layout inside ConvVoiceEncoder/VoiceDecoder (asr.py:111, tts.py:174);
+ *  - `dtype` selects the 16-bit storage type of activations and weights: V100_DTYPE_BF16 (default of
+ *    the Python modules) or V100_DTYPE_F16 (same tensor-core throughput, 3 more mantissa bits);
+ *    accumulation, folded BatchNorm, ReLU6 and residual adds are fp32 either way;
  *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it and are
  *    CUDA-graph capturable;
  *  - return value 0 = ok; <0 = V100_E_* below; >0 = a cudaError_t.  v100_last_error() returns a
@@ -27,11 +30,14 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 1
+#define V100_ABI_VERSION 2
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
 #define V100_E_DRIVER    (-3)   /* could not resolve cuTensorMapEncodeTiled / wrong device    */
+
+#define V100_DTYPE_BF16 0
+#define V100_DTYPE_F16  1
 
 #define V100_ACT_NONE  0
 #define V100_ACT_RELU6 1
@@ -40,6 +46,7 @@ extern "C" {
 #define V100_MEL_LOG_BF16_NCW  0  /* log(mel+offset), bf16 [B][64][pitch], frames >= n_i = log(offset)  */
 #define V100_MEL_LOG_F32_NTC   1  /* log(mel+offset), fp32 [B][T][64]  (the reference's feature layout) */
 #define V100_MEL_POWER_F32_NCW 2  /* mel power, fp32 [B][64][pitch]    (MelSpectrogram.forward layout)  */
+#define V100_MEL_LOG_F16_NCW   3  /* as 0 with fp16 storage                                             */
 
 int v100_abi_version(void);
 const char* v100_last_error(void);
@@ -60,30 +67,31 @@ int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch,
                 void* out, int T, int64_t out_pitch, int out_mode, void* stream);
 
 /*
- * fp32 [B][T][C] features -> bf16 NCW [B][C][pitch].  Replaces the transpose at the top of
- * AudioToTextCTC.forward (voice100/models/asr.py:111) plus the bf16 cast.
+ * fp32 [B][T][C] features -> 16-bit NCW [B][C][pitch].  Replaces the transpose at the top of
+ * AudioToTextCTC.forward (voice100/models/asr.py:111) plus the storage cast.
  */
-int v100_ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, void* stream);
+int v100_ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, void* stream);
 
 /*
- * Dense fp32 NCW [B][C][T] <-> pitched bf16 NCW.  Entry/exit casts of ConvVoiceEncoder.forward
+ * Dense fp32 NCW [B][C][T] <-> pitched 16-bit NCW.  Entry/exit casts of ConvVoiceEncoder.forward
  * (voice100/models/asr.py:78-79) and VoiceDecoder.forward (tts.py:28-29) when those sub-modules are
  * called on their own with the reference's fp32 NCW tensors.
  */
-int v100_ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, void* stream);
-int v100_ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, void* stream);
+int v100_ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, void* stream);
+int v100_ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, void* stream);
 
 /*
- * Pointwise (1x1) Conv1d as a bf16 tcgen05 GEMM with TMA-staged tiles and TMEM accumulators:
+ * Pointwise (1x1) Conv1d as a tcgen05 GEMM (bf16 or fp16 operands, fp32 accumulate) with TMA-staged
+ * tiles and TMEM accumulators:
  *   y[b][co][t] = act(scale[co] * sum_ci W[co][ci] * x[b][ci][t] + shift[co]) (+ res[b][co][t])
  * Replaces Conv1d(k=1,bias=False) + BatchNorm1d(eval) + ReLU6 and the residual add of
  * InvertedResidual (voice100/models/asr.py:27-37,45-59); scale/shift are the folded BN.
- *   W bf16 [C_out][C_in] row-major, C_in % 8 == 0;  x, y, res bf16 NCW;  scale/shift fp32 [C_out]
+ *   W [C_out][C_in] row-major, C_in % 8 == 0;  x, y, res NCW (all of `dtype`);  scale/shift fp32 [C_out]
  *   (scale may be NULL = 1);  res may be NULL; res shares y's pitch.
  */
-int v100_conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale,
-                      const float* shift, const void* res, void* y, int64_t y_pitch,
-                      int B, int C_in, int C_out, int T, int act, void* stream);
+int v100_conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale,
+                 const float* shift, const void* res, void* y, int64_t y_pitch,
+                 int B, int C_in, int C_out, int T, int act, int dtype, void* stream);
 
 /*
  * Same GEMM, fp32 NCW output and bias only:  y[b][co][t] = sum_ci W[co][ci] x[b][ci][t] + bias[co].
@@ -91,42 +99,43 @@ int v100_conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float
  * Conv1d(512->2) (tts.py:77) and VoiceDecoder's Conv1d(256->260) (tts.py:26).
  */
 int v100_conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias,
-                        float* y, int64_t y_pitch, int B, int C_in, int C_out, int T, void* stream);
+                        float* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int dtype, void* stream);
 
 /*
  * Depthwise Conv1d + folded BN + ReLU6:
  *   y[b][c][o] = act(scale[c] * sum_j w[c][j] * x[b][c][o*stride + j - (k-1)/2] + shift[c])
  * with zero padding, k odd, T_out = (T_in-1)/stride + 1.  Replaces ConvBNActivate with
- * groups=C (voice100/models/asr.py:27-37,49).  w bf16 [C][k].
+ * groups=C (voice100/models/asr.py:27-37,49).  w [C][k] of `dtype`.
  */
-int v100_dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale,
-                       const float* shift, void* y, int64_t y_pitch,
-                       int B, int C, int T_in, int k, int stride, int act, void* stream);
+int v100_dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale,
+                  const float* shift, void* y, int64_t y_pitch,
+                  int B, int C, int T_in, int k, int stride, int act, int dtype, void* stream);
 
 /* Same contract, always the plain CUDA-core kernel (any stride).  Used for stride != 1 internally;
  * exported so the tests can cross-check the tensor-core kernel against it on the device. */
-int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const float* scale,
-                            const float* shift, void* y, int64_t y_pitch,
-                            int B, int C, int T_in, int k, int stride, int act, void* stream);
+int v100_dwconv1d_simt(const void* x, int64_t x_pitch, const void* w, const float* scale,
+                       const float* shift, void* y, int64_t y_pitch,
+                       int B, int C, int T_in, int k, int stride, int act, int dtype, void* stream);
 
 /*
  * ConvTranspose1d(C_in -> C_out, kernel 5, stride 2, padding 2) + bias as a two-phase tcgen05
  * GEMM (even outputs: taps 0,2,4; odd outputs: taps 1,3; two TMEM accumulators interleaved in the
  * epilogue).  Replaces VoiceDecoder.layers[4] (voice100/models/tts.py:22).
- *   Wp bf16 [C_out][5*C_in], Wp[co][tap*C_in + ci] = weight[ci][co][tap];  y bf16 NCW, T_out = 2T-1;
- *   workspace: caller-provided bf16 [B][3*C_in][x_pitch] scratch (the x(t+1) | x(t) | x(t-1) stack:
+ *   Wp [C_out][5*C_in], Wp[co][tap*C_in + ci] = weight[ci][co][tap];  y NCW, T_out = 2T-1;
+ *   workspace: caller-provided 16-bit [B][3*C_in][x_pitch] scratch (the x(t+1) | x(t) | x(t-1) stack:
  *   TMA box coordinates must be 16-byte aligned, so one-step time shifts are materialised once).
  */
-int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
-                                   void* workspace, void* y, int64_t y_pitch,
-                                   int B, int C_in, int C_out, int T, void* stream);
+int v100_convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
+                              void* workspace, void* y, int64_t y_pitch,
+                              int B, int C_in, int C_out, int T, int dtype, void* stream);
 
 /*
  * Embedding lookup into NCW: y[b][c][t] = table[ids[b][t]][c].  Replaces nn.Embedding +
- * transpose (voice100/models/tts.py:81-83,174-175).  ids int64 [B][T]; table bf16 [V][C].
+ * transpose (voice100/models/tts.py:81-83,174-175).  ids int64 [B][T]; table [V][C] of 16-bit elements
+ * (either storage type: the rows are copied, not converted).
  */
-int v100_embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch,
-                            int B, int T, int V, int C, void* stream);
+int v100_embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch,
+                         int B, int T, int V, int C, void* stream);
 
 /*
  * CTC head tail: fp32 NCW logits [B][V][pitch] -> logits [B][T][V] fp32 (optional) and greedy

@@ -16,13 +16,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def ncw(x_f32: torch.Tensor) -> K.Ncw:
-    """fp32 [B,C,T] on device -> pitched bf16 Ncw with NaN poison in the pitch padding."""
+def ncw(x_f32: torch.Tensor, dtype=torch.bfloat16) -> K.Ncw:
+    """fp32 [B,C,T] on device -> pitched 16-bit Ncw with NaN poison in the pitch padding."""
     B, C, T = x_f32.shape
-    out = K.empty_ncw(B, C, T, x_f32.device)
+    out = K.empty_ncw(B, C, T, x_f32.device, dtype)
     out.data.fill_(float("nan"))
-    out.data[:, :, :T] = x_f32.to(torch.bfloat16)
+    out.data[:, :, :T] = x_f32.to(dtype)
     return out
+
+
+DTYPES = [torch.bfloat16, torch.float16]
+OUT_TOL = {torch.bfloat16: 1.2e-2, torch.float16: 1.5e-3}   # relative to max|ref|: the output rounding
 
 
 def rel_err(got, ref):
@@ -50,13 +54,14 @@ def rnd(*shape, seed=0, scale=1.0):
     (2, 72, 200, 333, 1, False),       # K not a multiple of 64, C_out not a multiple of 128
     (40, 128, 384, 520, 0, True),      # > 148 tiles: persistent loop + both TMEM buffers reused
 ])
-def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res, dtype):
     x = rnd(B, C_in, T, seed=1)
-    W = rnd(C_out, C_in, seed=2, scale=1.0 / math.sqrt(C_in)).to(torch.bfloat16)
+    W = rnd(C_out, C_in, seed=2, scale=1.0 / math.sqrt(C_in)).to(dtype)
     scale = (torch.rand(C_out, device=DEV) + 0.5)
     shift = torch.randn(C_out, device=DEV) * 0.3
     r = rnd(B, C_out, T, seed=3) if res else None
-    xn, rn = ncw(x), (ncw(r) if res else None)
+    xn, rn = ncw(x, dtype), (ncw(r, dtype) if res else None)
     y = K.conv1x1(xn, W, scale, shift, act, rn)
     torch.cuda.synchronize()
     ref = torch.einsum("oc,bct->bot", W.float(), xn.valid().float()) * scale[None, :, None] + shift[None, :, None]
@@ -66,15 +71,16 @@ def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res):
         ref = ref + rn.valid().float()
     got = y.valid().float()
     assert torch.isfinite(got).all()
-    assert rel_err(got, ref) < 1.2e-2, rel_err(got, ref)   # bf16 output rounding is 2^-8 relative
+    assert rel_err(got, ref) < OUT_TOL[dtype], rel_err(got, ref)   # output rounding: 2^-8 (bf16) / 2^-11 (fp16)
 
 
 @pytest.mark.parametrize("B,C_in,C_out,T", [(2, 256, 29, 751), (3, 512, 44, 100), (2, 256, 260, 277), (1, 512, 2, 24)])
-def test_conv1x1_f32out_matches_torch(B, C_in, C_out, T):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv1x1_f32out_matches_torch(B, C_in, C_out, T, dtype):
     x = rnd(B, C_in, T, seed=4)
-    W = rnd(C_out, C_in, seed=5, scale=1.0 / math.sqrt(C_in)).to(torch.bfloat16)
+    W = rnd(C_out, C_in, seed=5, scale=1.0 / math.sqrt(C_in)).to(dtype)
     bias = torch.randn(C_out, device=DEV)
-    xn = ncw(x)
+    xn = ncw(x, dtype)
     y = K.conv1x1_f32(xn, W, bias)
     torch.cuda.synchronize()
     ref = torch.einsum("oc,bct->bot", W.float(), xn.valid().float()) + bias[None, :, None]
@@ -82,17 +88,18 @@ def test_conv1x1_f32out_matches_torch(B, C_in, C_out, T):
 
 
 @pytest.mark.parametrize("B,C_in,C_out,T", [(2, 512, 256, 277), (1, 64, 128, 40), (3, 128, 64, 130)])
-def test_convtranspose_matches_torch(B, C_in, C_out, T):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_convtranspose_matches_torch(B, C_in, C_out, T, dtype):
     x = rnd(B, C_in, T, seed=6)
-    w = rnd(C_in, C_out, 5, seed=7, scale=1.0 / math.sqrt(C_in * 2.5)).to(torch.bfloat16)
+    w = rnd(C_in, C_out, 5, seed=7, scale=1.0 / math.sqrt(C_in * 2.5)).to(dtype)
     bias = torch.randn(C_out, device=DEV)
-    xn = ncw(x)
+    xn = ncw(x, dtype)
     wp = w.permute(1, 2, 0).reshape(C_out, 5 * C_in).contiguous()
     y = K.convtranspose_k5s2(xn, wp, bias)
     torch.cuda.synchronize()
     ref = F.conv_transpose1d(xn.valid().float(), w.float(), bias, stride=2, padding=2)
     assert y.T == 2 * T - 1 == ref.shape[2]
-    assert rel_err(y.valid().float(), ref) < 1.2e-2
+    assert rel_err(y.valid().float(), ref) < OUT_TOL[dtype]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -100,38 +107,43 @@ def test_convtranspose_matches_torch(B, C_in, C_out, T):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("k", [5, 7, 11, 17, 19, 27, 29, 33, 35, 51, 59, 65, 67, 75, 83])
 @pytest.mark.parametrize("T", [751, 96])
-def test_dwconv_mma_matches_torch(k, T):
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_mma_matches_torch(k, T, dtype):
     B, C = 2, 64
     x = rnd(B, C, T, seed=k).abs()
-    w = rnd(C, k, seed=k + 1, scale=1.0 / math.sqrt(k)).to(torch.bfloat16)
+    w = rnd(C, k, seed=k + 1, scale=1.0 / math.sqrt(k)).to(dtype)
     scale, shift = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
-    xn = ncw(x)
+    xn = ncw(x, dtype)
     ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], padding=(k - 1) // 2, groups=C)
     ref = (ref * scale[None, :, None] + shift[None, :, None]).clamp(0, 6)
     for simt in (False, True):
         y = K.dwconv(xn, w, scale, shift, k, 1, K.ACT_RELU6, simt=simt)
         torch.cuda.synchronize()
         assert y.T == T
-        assert rel_err(y.valid().float(), ref) < 1.2e-2, ("simt" if simt else "mma", rel_err(y.valid().float(), ref))
+        assert rel_err(y.valid().float(), ref) < OUT_TOL[dtype], ("simt" if simt else "mma", rel_err(y.valid().float(), ref))
 
 
-def test_dwconv_long_rows_and_stride2():
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_long_rows_and_stride2(dtype):
     B, C, T, k = 2, 16, 3001, 83                       # 60 s clip: three 1024-output chunks per row
     x = rnd(B, C, T, seed=9)
-    w = rnd(C, k, seed=10, scale=0.1).to(torch.bfloat16)
+    w = rnd(C, k, seed=10, scale=0.1).to(dtype)
     shift = torch.zeros(C, device=DEV)
-    xn = ncw(x)
+    xn = ncw(x, dtype)
     y = K.dwconv(xn, w, None, shift, k, 1, K.ACT_NONE)
     ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], padding=41, groups=C)
-    assert rel_err(y.valid().float(), ref) < 1.2e-2
+    assert rel_err(y.valid().float(), ref) < OUT_TOL[dtype]
     B, C, T, k = 3, 256, 1501, 11                      # asr layer 0: stride 2
     x = rnd(B, C, T, seed=11)
-    w = rnd(C, k, seed=12, scale=0.3).to(torch.bfloat16)
-    xn = ncw(x)
+    w = rnd(C, k, seed=12, scale=0.3).to(dtype)
+    xn = ncw(x, dtype)
     y = K.dwconv(xn, w, None, torch.zeros(C, device=DEV), k, 2, K.ACT_RELU6)
     ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], stride=2, padding=5, groups=C).clamp(0, 6)
     assert y.T == 751 == ref.shape[2]
-    assert rel_err(y.valid().float(), ref) < 1.2e-2
+    assert rel_err(y.valid().float(), ref) < OUT_TOL[dtype]
+    for simt in (False, True):                         # the any-shape kernel agrees too
+        y2 = K.dwconv(xn, w, None, torch.zeros(C, device=DEV), k, 2, K.ACT_RELU6, simt=simt)
+        assert rel_err(y2.valid().float(), ref) < OUT_TOL[dtype]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -182,10 +194,11 @@ def test_logmel_ragged_batch_bf16_ncw():
 # ------------------------------------------------------------------------------------------------
 def test_layout_and_head_kernels():
     x = rnd(3, 101, 64, seed=20)
-    y = K.ntc_f32_to_ncw(x)
-    assert torch.equal(y.valid().float(), x.transpose(1, 2).to(torch.bfloat16).float())
     z = rnd(2, 40, 77, seed=21)
-    assert torch.equal(K.ncw_to_f32(K.ncw_from_f32(z)), z.to(torch.bfloat16).float())
+    for dtype in DTYPES:
+        y = K.ntc_f32_to_ncw(x, dtype)
+        assert torch.equal(y.valid().float(), x.transpose(1, 2).to(dtype).float())
+        assert torch.equal(K.ncw_to_f32(K.ncw_from_f32(z, dtype)), z.to(dtype).float())
     ids = torch.randint(0, 29, (3, 45), device=DEV)
     table = rnd(29, 64, seed=22).to(torch.bfloat16)
     e = K.embedding_ncw(ids, table)

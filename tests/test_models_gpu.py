@@ -61,6 +61,47 @@ def test_asr_matches_golden(name):
     assert rep2["rms_rel_std"] < MODEL_RMS_REL_STD, rep2
 
 
+def test_asr_fp16_storage_is_8x_tighter():
+    """The same kernels with fp16 storage (3 more mantissa bits): the end-to-end error drops by the expected
+    factor, which pins the bf16 numbers above on the storage format and not on the kernels."""
+    sd, wav, lengths, g = asr_case("asr_en_small")
+    audio_size, embed, vocab, hidden = [int(x) for x in g["cfg"][:4]]
+    ref = torch.from_numpy(g["logits"])
+    len_d = torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    tr = v.MelSpectrogramAudioTransform().to(DEV)
+    reps = {}
+    for dtype in (torch.bfloat16, torch.float16):
+        model = _load(v.AudioToTextCTC(audio_size, embed, vocab, hidden), sd).set_storage_dtype(dtype)
+        tokens, _ = v.AsrPipeline(tr, model)(wav.to(DEV), len_d)
+        audio, _ = tr.logmel_batch(wav.to(DEV), len_d)
+        logits = model(audio).cpu()
+        reps[dtype] = orc.parity_report(ref, logits)
+        raw, gated, frac = orc.token_agreement(ref, tokens.cpu(), 2.5 * reps[dtype]["max_abs"])
+        print(dtype, reps[dtype], raw, gated, frac)
+        assert gated == 1.0
+        if dtype == torch.float16:
+            # STATED fp16 tolerance: rms <= 1.5 % and max <= 8 % of the logit std, raw token agreement >= 0.96
+            assert reps[dtype]["rms_rel_std"] < 0.015 and reps[dtype]["max_abs_rel_std"] < 0.08 and raw > 0.96
+            audio_ref, _ = orc.logmel_batch(wav, lengths)
+            with torch.no_grad():
+                model_ref = orc.asr_forward_storage_model(audio_ref, sd, torch.float16)
+            assert orc.parity_report(model_ref, logits)["rms_rel_std"] < 0.005
+    assert reps[torch.float16]["rms_rel_std"] < reps[torch.bfloat16]["rms_rel_std"] / 4
+
+
+def test_tts_fp16_storage():
+    sd_a, sd_v, text, align, g = tts_case()
+    V, H = int(g["cfg"][0]), int(g["cfg"][1])
+    vmodel = _load(v.AlignTextToAudioModel(V, H), sd_v).set_storage_dtype(torch.float16)
+    amodel = _load(v.TextToAlignTextModel(V, H), sd_a).set_storage_dtype(torch.float16)
+    rep = orc.parity_report(torch.from_numpy(g["align_pred"]), amodel(text.to(DEV)).cpu())
+    assert rep["rms_rel_std"] < 0.004, rep
+    f0, logspc, codeap = vmodel.predict(torch.from_numpy(g["aligntext"]).to(DEV))
+    rep = orc.parity_report(torch.from_numpy(g["logspc"]), logspc.cpu())
+    print("fp16 logspc", rep)
+    assert rep["rms_rel_std"] < 0.004 and rep["max_abs_rel_std"] < 0.03, rep
+
+
 def test_asr_base_live_oracle():
     """asr_en_base size, BN calibrated on the batch, CUDA path vs the oracle run live on the host."""
     B, L = 4, 16000 * 3

@@ -16,22 +16,22 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "v100_abi_version": [],
     "v100_logmel": [_p, _p, _i, _l, _p, _p, _p, _p, _f, _p, _i, _l, _i, _p],
-    "v100_ntc_f32_to_ncw_bf16": [_p, _p, _i, _i, _i, _l, _p],
-    "v100_ncw_f32_to_bf16": [_p, _p, _l, _i, _i, _i, _p],
-    "v100_ncw_bf16_to_f32": [_p, _l, _p, _i, _i, _i, _p],
-    "v100_conv1x1_bf16": [_p, _l, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
-    "v100_conv1x1_f32out": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _p],
-    "v100_dwconv1d_bf16": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
-    "v100_dwconv1d_bf16_simt": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
-    "v100_convtranspose1d_k5s2_bf16": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _p],
-    "v100_embedding_ncw_bf16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_ntc_f32_to_ncw16": [_p, _p, _i, _i, _i, _l, _i, _p],
+    "v100_ncw_f32_to_16": [_p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_ncw_16_to_f32": [_p, _l, _p, _i, _i, _i, _i, _p],
+    "v100_conv1x1": [_p, _l, _p, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _p],
+    "v100_conv1x1_f32out": [_p, _l, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "v100_dwconv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
+    "v100_dwconv1d_simt": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
+    "v100_convtranspose1d_k5s2": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
+    "v100_embedding_ncw16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
     "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p],
     "v100_ctc_collapse": [_p, _p, _p, _p, _i, _i, _i, _p],
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 _lib = None
 
 
@@ -62,7 +62,7 @@ def lib():
 # kernels launched per entry point (everything is one kernel except the transposed conv, which first
 # builds its shifted channel stack)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
-KERNELS_PER_CALL["v100_convtranspose1d_k5s2_bf16"] = 2
+KERNELS_PER_CALL["v100_convtranspose1d_k5s2"] = 2
 KERNELS_PER_CALL["v100_abi_version"] = 0
 
 stats = {"launches": 0}

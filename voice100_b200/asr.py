@@ -12,19 +12,20 @@ from torch import nn
 
 from . import kernels as K
 from ._lib import V100Error
-from .blocks import InvertedResidualParams, PreparedCache, require_eval_cuda, run_inverted_residual
+from .blocks import (InvertedResidualParams, PreparedCache, StorageDtypeMixin, require_eval_cuda,
+                     run_inverted_residual)
 from .synth import asr_encoder_blocks
 
 __all__ = ["AudioToTextCTC", "ConvVoiceEncoder", "LinearCharDecoder"]
 
 
-class ConvVoiceEncoder(nn.Module):
+class ConvVoiceEncoder(StorageDtypeMixin, nn.Module):
     def __init__(self, in_channels: int, out_channels: int, hidden_size: int):
         super().__init__()
         self.layers = nn.Sequential(*[
             InvertedResidualParams(ci, co, k, s, r)
             for ci, co, k, s, r in asr_encoder_blocks(in_channels, out_channels, hidden_size)])
-        self._prepared = PreparedCache(self, lambda: [blk.prepare() for blk in self.layers])
+        self._prepared = PreparedCache(self, lambda: [blk.prepare(self.storage_dtype) for blk in self.layers])
 
     def run(self, x: K.Ncw) -> K.Ncw:
         for w in self._prepared.get():
@@ -34,19 +35,19 @@ class ConvVoiceEncoder(nn.Module):
     def forward(self, embed: torch.Tensor) -> torch.Tensor:
         """fp32 NCW [B, in_channels, T] -> fp32 NCW [B, out_channels, (T+1)//2]."""
         require_eval_cuda(self, embed)
-        return K.ncw_to_f32(self.run(K.ncw_from_f32(embed.float().contiguous())))
+        return K.ncw_to_f32(self.run(K.ncw_from_f32(embed.float().contiguous(), self.storage_dtype)))
 
     def output_length(self, embed_len: torch.Tensor) -> torch.Tensor:
         return torch.div(embed_len + 1, 2, rounding_mode="trunc")
 
 
-class LinearCharDecoder(nn.Module):
+class LinearCharDecoder(StorageDtypeMixin, nn.Module):
     def __init__(self, in_channels: int, out_channels: int):
         super().__init__()
         # index 0 is Dropout(0.2) in the reference (identity in eval); index 1 carries the weights
         self.layers = nn.Sequential(nn.Identity(), nn.Conv1d(in_channels, out_channels, 1, bias=True))
         self._prepared = PreparedCache(self, lambda: (
-            self.layers[1].weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(),
+            self.layers[1].weight.detach()[:, :, 0].to(self.storage_dtype).contiguous(),
             self.layers[1].bias.detach().float().contiguous()))
 
     def run(self, x: K.Ncw) -> K.Ncw:
@@ -56,11 +57,11 @@ class LinearCharDecoder(nn.Module):
     def forward(self, enc_out: torch.Tensor) -> torch.Tensor:
         """fp32 NCW [B, embed, T] -> fp32 NCW logits [B, V, T]."""
         require_eval_cuda(self, enc_out)
-        y = self.run(K.ncw_from_f32(enc_out.float().contiguous()))
+        y = self.run(K.ncw_from_f32(enc_out.float().contiguous(), self.storage_dtype))
         return y.valid().contiguous()
 
 
-class AudioToTextCTC(nn.Module):
+class AudioToTextCTC(StorageDtypeMixin, nn.Module):
     def __init__(self, audio_size: int, embed_size: int, vocab_size: int, hidden_size: int,
                  learning_rate: float = 1e-3, weight_decay: float = 0.0):
         super().__init__()
@@ -77,7 +78,7 @@ class AudioToTextCTC(nn.Module):
     def forward(self, audio: torch.Tensor) -> torch.Tensor:
         """audio fp32 [B, T, audio_size] -> logits fp32 [B, (T+1)//2, vocab_size]."""
         require_eval_cuda(self, audio)
-        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous()), True)[0]
+        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous(), self.storage_dtype), True)[0]
 
     def greedy(self, audio) -> torch.Tensor:
         """CTC best-path tokens int64 [B, (T+1)//2] = forward(audio).argmax(-1) without materialising the
@@ -86,7 +87,7 @@ class AudioToTextCTC(nn.Module):
             require_eval_cuda(self, audio.data)
             return self._run(audio, False)[1]
         require_eval_cuda(self, audio)
-        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous()), False)[1]
+        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous(), self.storage_dtype), False)[1]
 
     def output_length(self, audio_len: torch.Tensor) -> torch.Tensor:
         return self.encoder.output_length(audio_len)
@@ -102,7 +103,7 @@ class AsrPipeline:
     @torch.no_grad()
     def __call__(self, waveform: torch.Tensor, lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """device waveform fp32 [B, L], lengths [B] -> (tokens int64 [B, T'], valid lengths int [B])."""
-        feats, audio_len = self.transform.logmel_batch(waveform, lengths, ncw_bf16=True)
+        feats, audio_len = self.transform.logmel_batch(waveform, lengths, ncw_dtype=self.model.storage_dtype)
         return self.model.greedy(feats), self.model.output_length(audio_len)
 
     @torch.no_grad()

@@ -43,16 +43,16 @@ class InvertedResidualParams(nn.Module):
     def forward(self, *a, **k):  # pragma: no cover
         raise V100Error("InvertedResidualParams only stores weights; run the owning model's forward")
 
-    def prepare(self):
-        """-> dict of device tensors the kernels consume (bf16 weights, fp32 folded BN)."""
+    def prepare(self, dtype=torch.bfloat16):
+        """-> dict of device tensors the kernels consume (16-bit weights, fp32 folded BN)."""
         e, d, p, bn3 = self.conv[0], self.conv[1], self.conv[2], self.conv[3]
         s1, b1 = fold_bn(e[1])
         s2, b2 = fold_bn(d[1])
         s3, b3 = fold_bn(bn3)
         return dict(
-            w1=e[0].weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(), s1=s1, b1=b1,
-            wd=d[0].weight.detach()[:, 0, :].to(torch.bfloat16).contiguous(), s2=s2, b2=b2,
-            w2=p.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(), s3=s3, b3=b3,
+            w1=e[0].weight.detach()[:, :, 0].to(dtype).contiguous(), s1=s1, b1=b1,
+            wd=d[0].weight.detach()[:, 0, :].to(dtype).contiguous(), s2=s2, b2=b2,
+            w2=p.weight.detach()[:, :, 0].to(dtype).contiguous(), s3=s3, b3=b3,
             k=self.kernel_size, stride=self.stride, res=self.use_residual)
 
 
@@ -70,12 +70,27 @@ class PreparedCache:
         self._owner, self._build, self._key, self._val = owner, build, None, None
 
     def get(self):
-        key = tuple((t.data_ptr(), t._version) for t in list(self._owner.parameters()) + list(self._owner.buffers()))
+        key = (getattr(self._owner, "storage_dtype", None),) + tuple(
+            (t.data_ptr(), t._version) for t in list(self._owner.parameters()) + list(self._owner.buffers()))
         if key != self._key:
             with torch.no_grad():
                 self._val = self._build()
             self._key = key
         return self._val
+
+
+class StorageDtypeMixin:
+    """`storage_dtype` = the 16-bit type activations and weights are stored in: torch.bfloat16 (default, the
+    type BASELINE.json's north_star names) or torch.float16 (same tensor-core speed, 8x smaller storage error;
+    safe here because every stored activation is bounded by ReLU6 / BatchNorm)."""
+    storage_dtype = torch.bfloat16
+
+    def set_storage_dtype(self, dtype):
+        K.dt(dtype)
+        for m in self.modules():
+            if isinstance(m, StorageDtypeMixin):
+                m.storage_dtype = dtype
+        return self
 
 
 def require_eval_cuda(module: nn.Module, *tensors: torch.Tensor):

@@ -46,12 +46,12 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                  const cuuint32_t* box) {
+static int encode(CUtensorMap* m, CUtensorMapDataType type, const void* base, int rank, const cuuint64_t* dims,
+                  const cuuint64_t* strides, const cuuint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t ones[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, ones,
+  CUresult r = fn(m, type, rank, const_cast<void*>(base), dims, strides, box, ones,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -61,19 +61,19 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   return 0;
 }
 
-int make_tmap_2d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1) {
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1) {
   const cuuint64_t dims[2] = {cuuint64_t(d0), cuuint64_t(d1)};
   const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
   const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
-  return encode(m, base, 2, dims, strides, box);
+  return encode(m, type, base, 2, dims, strides, box);
 }
 
-int make_tmap_3d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
+int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
                  int64_t stride2_bytes, int box0, int box1) {
   const cuuint64_t dims[3] = {cuuint64_t(d0), cuuint64_t(d1), cuuint64_t(d2)};
   const cuuint64_t strides[2] = {cuuint64_t(stride1_bytes), cuuint64_t(stride2_bytes)};
   const cuuint32_t box[3] = {cuuint32_t(box0), cuuint32_t(box1), 1};
-  return encode(m, base, 3, dims, strides, box);
+  return encode(m, type, base, 3, dims, strides, box);
 }
 
 }  // namespace v100
@@ -93,51 +93,50 @@ int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, 
                 STREAM(stream));
 }
 
-int v100_ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, void* stream) {
-  return ntc_f32_to_ncw_bf16(x, y, B, T, C, y_pitch, STREAM(stream));
+int v100_ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, void* stream) {
+  return ntc_f32_to_ncw16(x, y, B, T, C, y_pitch, dtype, STREAM(stream));
 }
 
-int v100_ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, void* stream) {
-  return ncw_f32_to_bf16(x, y, y_pitch, B, C, T, STREAM(stream));
+int v100_ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, void* stream) {
+  return ncw_f32_to_16(x, y, y_pitch, B, C, T, dtype, STREAM(stream));
 }
 
-int v100_ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, void* stream) {
-  return ncw_bf16_to_f32(x, x_pitch, y, B, C, T, STREAM(stream));
+int v100_ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, void* stream) {
+  return ncw_16_to_f32(x, x_pitch, y, B, C, T, dtype, STREAM(stream));
 }
 
-int v100_conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
-                      const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act,
-                      void* stream) {
-  return conv1x1_bf16(x, x_pitch, W, scale, shift, res, y, y_pitch, B, C_in, C_out, T, act, STREAM(stream));
+int v100_conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
+                 const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act, int dtype,
+                 void* stream) {
+  return conv1x1(x, x_pitch, W, scale, shift, res, y, y_pitch, B, C_in, C_out, T, act, dtype, STREAM(stream));
 }
 
 int v100_conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
-                        int B, int C_in, int C_out, int T, void* stream) {
-  return conv1x1_f32out(x, x_pitch, W, bias, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
+                        int B, int C_in, int C_out, int T, int dtype, void* stream) {
+  return conv1x1_f32out(x, x_pitch, W, bias, y, y_pitch, B, C_in, C_out, T, dtype, STREAM(stream));
 }
 
-int v100_dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
-                       int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, void* stream) {
-  return dwconv1d_bf16(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, 0, STREAM(stream));
+int v100_dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
+                  int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype, void* stream) {
+  return dwconv1d(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, dtype, 0, STREAM(stream));
 }
 
-// Same contract as v100_dwconv1d_bf16 but always the plain CUDA-core kernel (any stride); exported so the
-// tests can cross-check the tensor-core kernel against it on the GPU.
-int v100_dwconv1d_bf16_simt(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
-                            void* y, int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act,
-                            void* stream) {
-  return dwconv1d_bf16(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, 1, STREAM(stream));
+// Same contract as v100_dwconv1d but always the plain CUDA-core kernel (any stride); exported so the tests can
+// cross-check the tensor-core kernel against it on the GPU.
+int v100_dwconv1d_simt(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
+                       void* y, int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype,
+                       void* stream) {
+  return dwconv1d(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, dtype, 1, STREAM(stream));
 }
 
-int v100_convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias,
-                                   void* workspace, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T,
-                                   void* stream) {
-  return convtranspose1d_k5s2_bf16(x, x_pitch, Wp, bias, workspace, y, y_pitch, B, C_in, C_out, T, STREAM(stream));
+int v100_convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
+                              void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int dtype, void* stream) {
+  return convtranspose1d_k5s2(x, x_pitch, Wp, bias, workspace, y, y_pitch, B, C_in, C_out, T, dtype, STREAM(stream));
 }
 
-int v100_embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V,
-                            int C, void* stream) {
-  return embedding_ncw_bf16(ids, table, y, y_pitch, B, T, V, C, STREAM(stream));
+int v100_embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
+                         void* stream) {
+  return embedding_ncw16(ids, table, y, y_pitch, B, T, V, C, STREAM(stream));
 }
 
 int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null, int64_t* tokens, int B, int V,

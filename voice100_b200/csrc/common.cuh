@@ -244,4 +244,44 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu6(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+// ------------------------------------------------------------------------------------------
+// 16-bit storage types.  bf16 is the default (BASELINE.json north_star); fp16 is an option with the same
+// tensor-core throughput and 3 more mantissa bits (every stored activation of this network is bounded by
+// ReLU6 / BatchNorm, so the narrower exponent is not a risk).  DT_* mirror V100_DTYPE_* in include/v100.h.
+// ------------------------------------------------------------------------------------------
+constexpr int DT_BF16 = 0, DT_F16 = 1;
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu6(float lo, float hi) {
+  uint32_t r;
+  asm("{\n\t.reg .b32 t;\n\tcvt.rn.relu.f16x2.f32 t, %1, %2;\n\tmin.f16x2 %0, t, %3;\n\t}"
+      : "=r"(r)
+      : "f"(hi), "f"(lo), "r"(0x46004600u));  // 6.0 in both fp16 halves
+  return r;
+}
+__device__ __forceinline__ float f16_lo(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float f16_hi(uint32_t v) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(r) : "r"(v));
+  return r;
+}
+template <int DT> __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return DT == DT_F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+template <int DT> __device__ __forceinline__ uint32_t pack2_relu6(float lo, float hi) {
+  return DT == DT_F16 ? pack_f16x2_relu6(lo, hi) : pack_bf16x2_relu6(lo, hi);
+}
+template <int DT> __device__ __forceinline__ float unpack_lo(uint32_t v) { return DT == DT_F16 ? f16_lo(v) : bf16_lo(v); }
+template <int DT> __device__ __forceinline__ float unpack_hi(uint32_t v) { return DT == DT_F16 ? f16_hi(v) : bf16_hi(v); }
+template <int DT> __device__ __forceinline__ float h2f(unsigned short v) { return unpack_lo<DT>(uint32_t(v)); }
+template <int DT> __device__ __forceinline__ unsigned short f2h(float v) { return static_cast<unsigned short>(pack2<DT>(v, 0.0f) & 0xFFFFu); }
+
 }  // namespace v100

@@ -54,6 +54,7 @@ struct GemmParams {
   const float* shift;
   int act;
   int has_res;
+  int dtype;                // DT_BF16 / DT_F16: storage type of x, W, y, res
   float* y32;
   long long y32_pitch;
 };
@@ -171,8 +172,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
     if (lane == 0 && leader) {
       // ===================== MMA issuer (the pair's leader only) =====================
       // kind::f16 instruction descriptor: D=f32, A=B=bf16, A K-major, B MN-major, M=128*CG, N=BLOCK_N
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                                 (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((kBlockM * CG) >> 4) << 24);
+      // (format code: 1 = bf16, 0 = fp16)
+      const uint32_t fmt = p.dtype == DT_F16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (0u << 15) | (1u << 16) |
+                             (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t((kBlockM * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -228,6 +231,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
       uint8_t* my_row = stg + lane * 128;
       const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
       const bool relu6 = p.act == V100_ACT_RELU6;
+      const bool f16 = p.dtype == DT_F16;
 
       if (p.has_res && lane == 0 && tile0 < p.num_tiles) {
         const int r = tile0 / p.m_tiles;
@@ -294,8 +298,16 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
             uint4 w;
             if (!p.has_res) {
               if (relu6) {
-                w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
-                w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
+                if (f16) {
+                  w.x = pack_f16x2_relu6(o[0], o[1]); w.y = pack_f16x2_relu6(o[2], o[3]);
+                  w.z = pack_f16x2_relu6(o[4], o[5]); w.w = pack_f16x2_relu6(o[6], o[7]);
+                } else {
+                  w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
+                  w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
+                }
+              } else if (f16) {
+                w.x = pack_f16x2(o[0], o[1]); w.y = pack_f16x2(o[2], o[3]);
+                w.z = pack_f16x2(o[4], o[5]); w.w = pack_f16x2(o[6], o[7]);
               } else {
                 w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
                 w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
@@ -306,12 +318,21 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
                 for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
               }
               const uint4 rr = *dst;
-              o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
-              o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
-              o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
-              o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
-              w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-              w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+              if (f16) {
+                o[0] += f16_lo(rr.x); o[1] += f16_hi(rr.x);
+                o[2] += f16_lo(rr.y); o[3] += f16_hi(rr.y);
+                o[4] += f16_lo(rr.z); o[5] += f16_hi(rr.z);
+                o[6] += f16_lo(rr.w); o[7] += f16_hi(rr.w);
+                w.x = pack_f16x2(o[0], o[1]); w.y = pack_f16x2(o[2], o[3]);
+                w.z = pack_f16x2(o[4], o[5]); w.w = pack_f16x2(o[6], o[7]);
+              } else {
+                o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
+                o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
+                o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
+                o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
+                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+                w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+              }
             }
             *dst = w;
           }
@@ -461,9 +482,19 @@ static int check_ncw(const void* p, int64_t pitch, int T, const char* what) {
   return 0;
 }
 
-int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
-                 const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act,
-                 cudaStream_t stream) {
+static int check_dtype(int dtype, const char* what) {
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(V100_E_INVALID, "%s: dtype must be V100_DTYPE_BF16 or V100_DTYPE_F16", what);
+  return 0;
+}
+
+static CUtensorMapDataType tmap_type(int dtype) {
+  return dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+
+int conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
+            const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act, int dtype,
+            cudaStream_t stream) {
+  if (int e = check_dtype(dtype, "conv1x1")) return e;
   if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "conv1x1: non-positive size");
   if (C_in % 8 != 0) return fail(V100_E_UNSUPPORTED, "conv1x1: C_in=%d must be a multiple of 8", C_in);
   if (shift == nullptr || W == nullptr) return fail(V100_E_INVALID, "conv1x1: null W/shift");
@@ -472,15 +503,15 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
   if (res != nullptr) if (int e = check_ncw(res, y_pitch, T, "conv1x1 res")) return e;
   const int bn = pick_block_n(T);
   CUtensorMap tw, tx, ty, tr;
-  if (int e = make_tmap_2d(&tw, W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
-  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
-  if (int e = make_tmap_3d(&ty, y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
-  if (int e = make_tmap_3d(&tr, res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
+  if (int e = make_tmap_2d(&tw, tmap_type(dtype), W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, tmap_type(dtype), x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&ty, tmap_type(dtype), y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
+  if (int e = make_tmap_3d(&tr, tmap_type(dtype), res ? res : y, T, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
   p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
-  p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr;
+  p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr; p.dtype = dtype;
   p.t_tiles = (T + bn - 1) / bn;
   static const int force_cg = getenv("V100_GEMM_CG") ? atoi(getenv("V100_GEMM_CG")) : 0;  // debugging / A-B runs
   if (bn == 256 && C_out % (2 * kBlockM) == 0 && force_cg != 1) {
@@ -495,7 +526,8 @@ int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* sca
 }
 
 int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
-                   int B, int C_in, int C_out, int T, cudaStream_t stream) {
+                   int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream) {
+  if (int e = check_dtype(dtype, "conv1x1_f32out")) return e;
   if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "conv1x1_f32out: non-positive size");
   if (C_in % 8 != 0) return fail(V100_E_UNSUPPORTED, "conv1x1_f32out: C_in=%d must be a multiple of 8", C_in);
   if (bias == nullptr || W == nullptr || y == nullptr) return fail(V100_E_INVALID, "conv1x1_f32out: null pointer");
@@ -504,8 +536,8 @@ int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* b
     return fail(V100_E_INVALID, "conv1x1_f32out: y pitch must be >= T and a multiple of 4, base 16B aligned");
   const int bn = pick_block_n(T);
   CUtensorMap tw, tx;
-  if (int e = make_tmap_2d(&tw, W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
-  if (int e = make_tmap_3d(&tx, x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_2d(&tw, tmap_type(dtype), W, C_in, C_out, int64_t(C_in) * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, tmap_type(dtype), x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 64)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
   p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
@@ -513,7 +545,7 @@ int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* b
   p.num_tiles = p.m_tiles * p.t_tiles * B;
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
   p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
-  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
+  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0; p.dtype = dtype;
   p.y32 = y; p.y32_pitch = y_pitch;
   if (bn == 256) return launch_gemm<256, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
   return launch_gemm<128, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
@@ -543,8 +575,9 @@ shift_stack3_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
-int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
-                              void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream) {
+int convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
+                         void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream) {
+  if (int e = check_dtype(dtype, "convtranspose")) return e;
   if (B <= 0 || C_in <= 0 || C_out <= 0 || T <= 0) return fail(V100_E_INVALID, "convtranspose: non-positive size");
   if (C_in % 64 != 0) return fail(V100_E_UNSUPPORTED, "convtranspose: C_in=%d must be a multiple of 64", C_in);
   if (bias == nullptr || Wp == nullptr) return fail(V100_E_INVALID, "convtranspose: null W/bias");
@@ -560,9 +593,9 @@ int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, co
     V100_CUDA(cudaGetLastError());
   }
   CUtensorMap tw, tx, ty;
-  if (int e = make_tmap_2d(&tw, Wp, int64_t(C_in) * 5, C_out, int64_t(C_in) * 5 * 2, 64, 128)) return e;
-  if (int e = make_tmap_3d(&tx, workspace, T, int64_t(C_in) * 3, B, x_pitch * 2, int64_t(C_in) * 3 * x_pitch * 2, 64, 64)) return e;
-  if (int e = make_tmap_3d(&ty, y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
+  if (int e = make_tmap_2d(&tw, tmap_type(dtype), Wp, int64_t(C_in) * 5, C_out, int64_t(C_in) * 5 * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, tmap_type(dtype), workspace, T, int64_t(C_in) * 3, B, x_pitch * 2, int64_t(C_in) * 3 * x_pitch * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&ty, tmap_type(dtype), y, T_out, C_out, B, y_pitch * 2, int64_t(C_out) * y_pitch * 2, 64, 32)) return e;
   GemmParams p{};
   p.C_out = C_out; p.C_in = C_in; p.B = B;
   p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
@@ -577,7 +610,7 @@ int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, co
   const int blocks[5] = {0, 0, 1, 1, 2};
   const int accs[5] = {0, 1, 0, 1, 0};
   for (int i = 0; i < 5; ++i) { p.tap_xrow[i] = blocks[i] * C_in; p.tap_acc[i] = accs[i]; }
-  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0;
+  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0; p.dtype = dtype;
   return launch_gemm<128, 2, OUT_BF16, 4>(tw, tx, ty, ty, p, stream);
 }
 

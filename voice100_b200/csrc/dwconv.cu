@@ -20,12 +20,20 @@ constexpr int kDwChunk = 1024;            // outputs per CTA along time (8 mma t
 constexpr int kDwRow = kDwChunk + 256;    // staged inputs per row: 9 tiles of 128 + (Q+1)*16 halo
 constexpr int kDwWarps = 8;
 
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                               uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+template <int DT>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  if constexpr (DT == DT_F16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
 }
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
@@ -42,7 +50,7 @@ constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one 
 
 // Stage x[b][c][tcA .. tcA + kDwRow) into `xs` with zeros outside [0, T).  16-byte chunks never straddle 0
 // (tcA % 8 == 0); a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
-__device__ __forceinline__ void dw_stage_row(__nv_bfloat16* xs, const __nv_bfloat16* xrow, int tcA, int T, int lane,
+__device__ __forceinline__ void dw_stage_row(unsigned short* xs, const unsigned short* xrow, int tcA, int T, int lane,
                                              int n_chunks) {
   for (int v = lane; v < n_chunks; v += 32) {
     const int t = tcA + v * 8;
@@ -51,11 +59,11 @@ __device__ __forceinline__ void dw_stage_row(__nv_bfloat16* xs, const __nv_bfloa
   }
   cp_async_commit();
 }
-__device__ __forceinline__ void dw_fix_tail(__nv_bfloat16* xs, int tcA, int T, int lane) {
+__device__ __forceinline__ void dw_fix_tail(unsigned short* xs, int tcA, int T, int lane) {
   const int i0 = T - tcA;               // first staged index that is past the end of the clip
   if ((T & 7) != 0 && i0 > 0 && i0 < kDwRow) {
     const int i = i0 + lane;
-    if (lane < 8 - (T & 7)) xs[i] = __float2bfloat16(0.0f);
+    if (lane < 8 - (T & 7)) xs[i] = 0;
   }
 }
 
@@ -71,13 +79,13 @@ __device__ __forceinline__ void dw_fix_tail(__nv_bfloat16* xs, int tcA, int T, i
 // Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory); tiles start
 // s = e - (e & 1) outputs before tc0 (e = pl8 - p), leaving e1 = e & 1 to fold into the zero-extended filter;
 // Q = ceil((k + 15 + e1) / 16) <= 7 for k <= 83.
-template <int Q, bool RELU6>
+template <int Q, bool RELU6, int DT>
 __global__ void __launch_bounds__(kDwWarps * 32)
-dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
-              const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
+              const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
               long long y_pitch, int B, int C, int T, int k) {
-  __shared__ __align__(128) __nv_bfloat16 xs_all[kDwWarps][2][kDwRow];
-  __shared__ __align__(16) __nv_bfloat16 ws_all[kDwWarps][16 * Q + 16];
+  __shared__ __align__(128) unsigned short xs_all[kDwWarps][2][kDwRow];
+  __shared__ __align__(16) unsigned short ws_all[kDwWarps][16 * Q + 16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * kDwWarps + warp;
@@ -90,8 +98,8 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   const int e1 = e & 1;           // folded into the zero-extended filter
   const int s = e - e1;           // tiles start s outputs before tc0
   const int tcA = tc0 - pl8;
-  __nv_bfloat16* ws = ws_all[warp];
-  const __nv_bfloat16* xbase = x + static_cast<long long>(c) * x_pitch;
+  unsigned short* ws = ws_all[warp];
+  const unsigned short* xbase = x + static_cast<long long>(c) * x_pitch;
   const long long xbstride = static_cast<long long>(C) * x_pitch;
 
   const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
@@ -102,13 +110,13 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   // zero-extended filter: ws[16 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
   for (int i = lane; i < 16 * Q + 16; i += 32) {
     const int j = i - 16 - e1;
-    ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : __float2bfloat16(0.0f);
+    ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : static_cast<unsigned short>(0);
   }
   __syncwarp();
   const int g = lane >> 2, tg = lane & 3;
   uint32_t af[Q][4];
   {
-    const unsigned short* wsu = reinterpret_cast<const unsigned short*>(ws);
+    const unsigned short* wsu = ws;
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
       const int i0 = 16 + 16 * q + 4 * tg - g;   // wz[16q + kk - m] at m = g, kk = 4 tg
@@ -125,7 +133,7 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
   const int pos0 = 32 * tg + (even ? g : g + 7) - s;
 
   for (int r = 0; r < nb; ++r) {
-    __nv_bfloat16* xs = xs_all[warp][r & 1];
+    unsigned short* xs = xs_all[warp][r & 1];
     if (r + 1 < nb) {   // prefetch the next batch row of this channel into the other buffer
       dw_stage_row(xs_all[warp][(r + 1) & 1], xbase + (b0 + r + 1) * xbstride, tcA, T, lane, n_chunks);
       cp_async_wait<1>();
@@ -136,7 +144,7 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
     dw_fix_tail(xs, tcA, T, lane);
     __syncwarp();
     const uint2* xw = reinterpret_cast<const uint2*>(xs) + lane;
-    __nv_bfloat16* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
+    unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
     int pos = pos0;
 #pragma unroll 1
     for (int tile = 0; tile < n_tiles; ++tile) {
@@ -144,7 +152,7 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
         const uint2 bq = xw[4 * q];
-        mma_bf16_16816(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
+        mma_16816<DT>(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
@@ -156,11 +164,11 @@ dw_mma_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv
       const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
       uint32_t o0, o1;
       if (RELU6) {
-        o0 = pack_bf16x2_relu6(lo0, hi0);
-        o1 = pack_bf16x2_relu6(lo1, hi1);
+        o0 = pack2_relu6<DT>(lo0, hi0);
+        o1 = pack2_relu6<DT>(lo1, hi1);
       } else {
-        o0 = pack_bf16x2(lo0, hi0);
-        o1 = pack_bf16x2(lo1, hi1);
+        o0 = pack2<DT>(lo0, hi0);
+        o1 = pack2<DT>(lo1, hi1);
       }
       if (pos >= 0 && pos < len) *reinterpret_cast<uint32_t*>(yp) = o0;
       if (pos + 16 >= 0 && pos + 16 < len) *reinterpret_cast<uint32_t*>(yp + 16) = o1;
@@ -179,11 +187,12 @@ constexpr int kS2Chunk = 512;                 // outputs per CTA pass
 constexpr int kS2Row = 2 * kS2Chunk + 96;     // staged inputs (halo <= 48 each side)
 constexpr int kS2MaxWords = 48;               // (k + 1) / 2 + 1 <= 48  ->  k <= 93
 
+template <int DT>
 __global__ void __launch_bounds__(kDwWarps * 32)
-dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
-             const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+dw_s2_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
+             const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
              long long y_pitch, int C, int T_in, int T_out, int k, int act) {
-  __shared__ __align__(16) __nv_bfloat16 xs_all[kDwWarps][kS2Row];
+  __shared__ __align__(16) unsigned short xs_all[kDwWarps][kS2Row];
   __shared__ __align__(8) float ws_all[kDwWarps][2 * kS2MaxWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * kDwWarps + warp;
@@ -193,9 +202,9 @@ dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_
   const int p = (k - 1) >> 1;
   const int p8 = (p + 7) & ~7;
   const int e = p8 - p;                       // xs[2*ol + j + e] = x[2*(oc0+ol) + j - p]
-  __nv_bfloat16* xs = xs_all[warp];
+  unsigned short* xs = xs_all[warp];
   float* ws = ws_all[warp];
-  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
+  const unsigned short* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
   const int ia = 2 * oc0 - p8;
   for (int v = lane; v < kS2Row / 8; v += 32) {
     const int t = ia + v * 8;
@@ -214,13 +223,13 @@ dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_
   const int n_words = (k + e + 1) >> 1;       // taps j' = j + e in [e, k+e) -> words [0, n_words)
   for (int i = lane; i < 2 * n_words; i += 32) {
     const int j = i - e;
-    ws[i] = (j >= 0 && j < k) ? __bfloat162float(w[static_cast<long long>(c) * k + j]) : 0.0f;
+    ws[i] = (j >= 0 && j < k) ? h2f<DT>(w[static_cast<long long>(c) * k + j]) : 0.0f;
   }
   __syncwarp();
   const float sc = scale ? scale[c] : 1.0f, sh = shift[c];
   const uint32_t* xw = reinterpret_cast<const uint32_t*>(xs);
   const float2* w2 = reinterpret_cast<const float2*>(ws);
-  __nv_bfloat16* yrow = y + (static_cast<long long>(b) * C + c) * y_pitch;
+  unsigned short* yrow = y + (static_cast<long long>(b) * C + c) * y_pitch;
   for (int r0 = 0; r0 < kS2Chunk / 32 && oc0 + r0 * 32 < T_out; r0 += 4) {
     float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     for (int m = 0; m < n_words; ++m) {
@@ -228,8 +237,8 @@ dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t v = xw[(r0 + u) * 32 + lane + m];
-        acc[u] = fmaf(wm.x, bf16_lo(v), acc[u]);
-        acc[u] = fmaf(wm.y, bf16_hi(v), acc[u]);
+        acc[u] = fmaf(wm.x, unpack_lo<DT>(v), acc[u]);
+        acc[u] = fmaf(wm.y, unpack_hi<DT>(v), acc[u]);
       }
     }
 #pragma unroll
@@ -237,28 +246,29 @@ dw_s2_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_
       const int o = oc0 + (r0 + u) * 32 + lane;
       float v = fmaf(acc[u], sc, sh);
       if (act == V100_ACT_RELU6) v = fminf(fmaxf(v, 0.0f), 6.0f);
-      if (o < T_out) yrow[o] = __float2bfloat16(v);
+      if (o < T_out) yrow[o] = f2h<DT>(v);
     }
   }
 }
 
+template <int DT>
 __global__ void __launch_bounds__(128)
-dw_simt_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __nv_bfloat16* __restrict__ w,
-               const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+dw_simt_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
+               const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
                long long y_pitch, int C, int T_in, int T_out, int k, int stride, int act) {
   const int c = blockIdx.y, b = blockIdx.z;
   const int o0 = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (o0 >= T_out) return;
   const int p = (k - 1) >> 1;
-  const __nv_bfloat16* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
-  const __nv_bfloat16* wrow = w + static_cast<long long>(c) * k;
+  const unsigned short* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
+  const unsigned short* wrow = w + static_cast<long long>(c) * k;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < k; ++j) {
-    const float wj = __bfloat162float(wrow[j]);
+    const float wj = h2f<DT>(wrow[j]);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
       const int i = (o0 + r) * stride + j - p;
-      if (i >= 0 && i < T_in) acc[r] = fmaf(wj, __bfloat162float(xrow[i]), acc[r]);
+      if (i >= 0 && i < T_in) acc[r] = fmaf(wj, h2f<DT>(xrow[i]), acc[r]);
     }
   }
   const float sc = scale ? scale[c] : 1.0f, sh = shift[c];
@@ -270,28 +280,36 @@ dw_simt_kernel(const __nv_bfloat16* __restrict__ x, long long x_pitch, const __n
       v0 = fminf(fmaxf(v0, 0.0f), 6.0f);
       v1 = fminf(fmaxf(v1, 0.0f), 6.0f);
     }
-    o[r >> 1] = pack_bf16x2(v0, v1);
+    o[r >> 1] = pack2<DT>(v0, v1);
   }
   // o0 % 8 == 0 and pitch % 8 == 0, so the 16-byte store stays inside the row's pitch
   *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * C + c) * y_pitch + o0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-template <int Q>
-static void launch_dw_mma(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
-                          void* y, int64_t y_pitch, int B, int C, int T, int k, int act, cudaStream_t stream) {
+template <int Q, int DT>
+static void launch_dw_mma_dt(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
+                             void* y, int64_t y_pitch, int B, int C, int T, int k, int act, cudaStream_t stream) {
   dim3 grid((T + kDwChunk - 1) / kDwChunk, C / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
-  auto xp = static_cast<const __nv_bfloat16*>(x);
-  auto wp = static_cast<const __nv_bfloat16*>(w);
-  auto yp = static_cast<__nv_bfloat16*>(y);
+  auto xp = static_cast<const unsigned short*>(x);
+  auto wp = static_cast<const unsigned short*>(w);
+  auto yp = static_cast<unsigned short*>(y);
   if (act == V100_ACT_RELU6)
-    dw_mma_kernel<Q, true><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
+    dw_mma_kernel<Q, true, DT><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
   else
-    dw_mma_kernel<Q, false><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
+    dw_mma_kernel<Q, false, DT><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
 }
 
-int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
-                  int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int force_simt,
-                  cudaStream_t stream) {
+template <int Q>
+static void launch_dw_mma(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,
+                          void* y, int64_t y_pitch, int B, int C, int T, int k, int act, int dtype, cudaStream_t stream) {
+  if (dtype == DT_F16) launch_dw_mma_dt<Q, DT_F16>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T, k, act, stream);
+  else launch_dw_mma_dt<Q, DT_BF16>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T, k, act, stream);
+}
+
+int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
+             int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype, int force_simt,
+             cudaStream_t stream) {
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(V100_E_INVALID, "dwconv: dtype must be V100_DTYPE_BF16 or V100_DTYPE_F16");
   if (B <= 0 || C <= 0 || T_in <= 0 || k <= 0 || stride <= 0) return fail(V100_E_INVALID, "dwconv: non-positive size");
   if ((k & 1) == 0) return fail(V100_E_UNSUPPORTED, "dwconv: kernel size %d must be odd", k);
   if (x == nullptr || w == nullptr || shift == nullptr || y == nullptr) return fail(V100_E_INVALID, "dwconv: null pointer");
@@ -303,26 +321,31 @@ int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* sc
   const int p = (k - 1) / 2;
   const int e1 = (((p + 7) & ~7) - p) & 1;
   const int Q = (k + 15 + e1 + 15) / 16;
+  auto xp = static_cast<const unsigned short*>(x);
+  auto wp = static_cast<const unsigned short*>(w);
+  auto yp = static_cast<unsigned short*>(y);
   if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7) {
     switch (Q) {
-      case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      case 2: launch_dw_mma<2>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      case 3: launch_dw_mma<3>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      case 4: launch_dw_mma<4>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      case 5: launch_dw_mma<5>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      case 6: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
-      default: launch_dw_mma<7>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, stream); break;
+      case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      case 2: launch_dw_mma<2>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      case 3: launch_dw_mma<3>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      case 4: launch_dw_mma<4>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      case 5: launch_dw_mma<5>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      case 6: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
+      default: launch_dw_mma<7>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
     }
   } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
     dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
-    dw_s2_kernel<<<grid, kDwWarps * 32, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pitch,
-                                                     static_cast<const __nv_bfloat16*>(w), scale, shift,
-                                                     static_cast<__nv_bfloat16*>(y), y_pitch, C, T_in, T_out, k, act);
+    if (dtype == DT_F16)
+      dw_s2_kernel<DT_F16><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, act);
+    else
+      dw_s2_kernel<DT_BF16><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, act);
   } else {
     dim3 grid((T_out + 1023) / 1024, C, B);
-    dw_simt_kernel<<<grid, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), x_pitch,
-                                             static_cast<const __nv_bfloat16*>(w), scale, shift,
-                                             static_cast<__nv_bfloat16*>(y), y_pitch, C, T_in, T_out, k, stride, act);
+    if (dtype == DT_F16)
+      dw_simt_kernel<DT_F16><<<grid, 128, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, stride, act);
+    else
+      dw_simt_kernel<DT_BF16><<<grid, 128, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, stride, act);
   }
   V100_CUDA(cudaGetLastError());
   return 0;

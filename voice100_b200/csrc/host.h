@@ -21,29 +21,28 @@ int num_sms();
       return ::v100::fail(static_cast<int>(e__), "%s -> %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
-// bf16 tensor maps, 128-byte swizzle, zero fill out of bounds.  Dimensions innermost first.
-int make_tmap_2d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
-int make_tmap_3d(CUtensorMap* m, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
+// 16-bit tensor maps, 128-byte swizzle, zero fill out of bounds.  Dimensions innermost first.
+int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
+int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
                  int64_t stride2_bytes, int box0, int box1);
 
-int conv1x1_bf16(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift,
-                 const void* res, void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act,
-                 cudaStream_t stream);
+int conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, const float* shift, const void* res,
+            void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, int act, int dtype, cudaStream_t stream);
 int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* bias, float* y, int64_t y_pitch,
-                   int B, int C_in, int C_out, int T, cudaStream_t stream);
-int convtranspose1d_k5s2_bf16(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
-                              void* y, int64_t y_pitch, int B, int C_in, int C_out, int T, cudaStream_t stream);
-int dwconv1d_bf16(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
-                  int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int force_simt,
-                  cudaStream_t stream);
+                   int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream);
+int convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
+                         int64_t y_pitch, int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream);
+int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
+             int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype, int force_simt,
+             cudaStream_t stream);
 int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const int32_t* fb_start,
            const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T,
            int64_t out_pitch, int out_mode, cudaStream_t stream);
-int ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, cudaStream_t stream);
-int ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, cudaStream_t stream);
-int ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, cudaStream_t stream);
-int embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
-                       cudaStream_t stream);
+int ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, cudaStream_t stream);
+int ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream);
+int ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, cudaStream_t stream);
+int embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
+                    cudaStream_t stream);
 int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* tokens, int B, int V, int T,
                  cudaStream_t stream);
 int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,

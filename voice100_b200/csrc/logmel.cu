@@ -144,17 +144,22 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
   __syncthreads();
 
   const int tid = threadIdx.x;
-  if (out_mode == V100_MEL_LOG_BF16_NCW) {
+  if (out_mode == V100_MEL_LOG_BF16_NCW || out_mode == V100_MEL_LOG_F16_NCW) {
     const int m = tid >> 2, fs = (tid & 3) * 16;
-    __nv_bfloat16* row = static_cast<__nv_bfloat16*>(out) + (static_cast<long long>(b) * kNMels + m) * out_pitch;
+    unsigned short* row = static_cast<unsigned short*>(out) + (static_cast<long long>(b) * kNMels + m) * out_pitch;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int t = f0 + fs + 8 * h;
       if (t < out_pitch) {
         const float* s = &tile[m][fs + 8 * h];
         uint4 v;
-        v.x = pack_bf16x2(s[0], s[1]); v.y = pack_bf16x2(s[2], s[3]);
-        v.z = pack_bf16x2(s[4], s[5]); v.w = pack_bf16x2(s[6], s[7]);
+        if (out_mode == V100_MEL_LOG_F16_NCW) {
+          v.x = pack_f16x2(s[0], s[1]); v.y = pack_f16x2(s[2], s[3]);
+          v.z = pack_f16x2(s[4], s[5]); v.w = pack_f16x2(s[6], s[7]);
+        } else {
+          v.x = pack_bf16x2(s[0], s[1]); v.y = pack_bf16x2(s[2], s[3]);
+          v.z = pack_bf16x2(s[4], s[5]); v.w = pack_bf16x2(s[6], s[7]);
+        }
         *reinterpret_cast<uint4*>(row + t) = v;
       }
     }
@@ -189,9 +194,9 @@ int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const
       fb_off == nullptr || fb_w == nullptr)
     return fail(V100_E_INVALID, "logmel: null pointer");
   if (B <= 0 || T <= 0 || B > 65535) return fail(V100_E_INVALID, "logmel: bad B=%d or T=%d", B, T);
-  if (out_mode == V100_MEL_LOG_BF16_NCW) {
+  if (out_mode == V100_MEL_LOG_BF16_NCW || out_mode == V100_MEL_LOG_F16_NCW) {
     if (out_pitch < T || (out_pitch & 7) || (reinterpret_cast<uintptr_t>(out) & 15))
-      return fail(V100_E_INVALID, "logmel: bf16 NCW pitch must be >= T and a multiple of 8, base 16B aligned");
+      return fail(V100_E_INVALID, "logmel: 16-bit NCW pitch must be >= T and a multiple of 8, base 16B aligned");
   } else if (out_mode == V100_MEL_POWER_F32_NCW) {
     if (out_pitch < T || (out_pitch & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
       return fail(V100_E_INVALID, "logmel: fp32 NCW pitch must be >= T and a multiple of 4, base 16B aligned");

@@ -7,8 +7,9 @@
 namespace v100 {
 
 // fp32 [B][T][C] -> bf16 NCW [B][C][pitch] through a 32x32 shared tile (AudioToTextCTC.forward's transpose).
+template <int DT>
 __global__ void __launch_bounds__(256)
-ntc_to_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int T, int C, long long y_pitch) {
+ntc_to_ncw_kernel(const float* __restrict__ x, unsigned short* __restrict__ y, int T, int C, long long y_pitch) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -19,62 +20,74 @@ ntc_to_ncw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, in
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
     const int c = c0 + r, t = t0 + tx;
-    if (c < C && t < T) y[(static_cast<long long>(b) * C + c) * y_pitch + t] = __float2bfloat16(tile[tx][r]);
+    if (c < C && t < T) y[(static_cast<long long>(b) * C + c) * y_pitch + t] = f2h<DT>(tile[tx][r]);
   }
 }
 
-int ntc_f32_to_ncw_bf16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, cudaStream_t stream) {
+static int check_dt(int dtype, const char* what) {
+  if (dtype != DT_BF16 && dtype != DT_F16) return fail(V100_E_INVALID, "%s: dtype must be V100_DTYPE_BF16 or V100_DTYPE_F16", what);
+  return 0;
+}
+
+int ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, cudaStream_t stream) {
+  if (int e = check_dt(dtype, "ntc_to_ncw")) return e;
   if (x == nullptr || y == nullptr) return fail(V100_E_INVALID, "ntc_to_ncw: null pointer");
   if (B <= 0 || T <= 0 || C <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "ntc_to_ncw: bad sizes");
   dim3 grid((T + 31) / 32, (C + 31) / 32, B);
-  ntc_to_ncw_kernel<<<grid, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), T, C, y_pitch);
+  if (dtype == DT_F16) ntc_to_ncw_kernel<DT_F16><<<grid, 256, 0, stream>>>(x, static_cast<unsigned short*>(y), T, C, y_pitch);
+  else ntc_to_ncw_kernel<DT_BF16><<<grid, 256, 0, stream>>>(x, static_cast<unsigned short*>(y), T, C, y_pitch);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
 
 // Dense NCW casts between the caller's fp32 [B][C][T] tensors and the pitched bf16 working layout
 // (entry/exit of ConvVoiceEncoder.forward / VoiceDecoder.forward when used as stand-alone modules).
+template <int DT>
 __global__ void __launch_bounds__(256)
-ncw_cast_kernel(const float* __restrict__ xf, const __nv_bfloat16* __restrict__ xb, float* __restrict__ yf,
-                __nv_bfloat16* __restrict__ yb, long long rows, int T, long long pitch) {
+ncw_cast_kernel(const float* __restrict__ xf, const unsigned short* __restrict__ xb, float* __restrict__ yf,
+                unsigned short* __restrict__ yb, long long rows, int T, long long pitch) {
   const long long total = rows * T;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const long long r = i / T;
     const int t = int(i - r * T);
-    if (yb) yb[r * pitch + t] = __float2bfloat16(xf[i]);
-    else yf[i] = __bfloat162float(xb[r * pitch + t]);
+    if (yb) yb[r * pitch + t] = f2h<DT>(xf[i]);
+    else yf[i] = h2f<DT>(xb[r * pitch + t]);
   }
 }
 
-int ncw_f32_to_bf16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, cudaStream_t stream) {
+int ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream) {
+  if (int e = check_dt(dtype, "ncw_f32_to_16")) return e;
   if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || T <= 0 || y_pitch < T)
-    return fail(V100_E_INVALID, "ncw_f32_to_bf16: bad arguments");
+    return fail(V100_E_INVALID, "ncw_f32_to_16: bad arguments");
   const long long rows = static_cast<long long>(B) * C;
   const int grid = int(std::min<long long>((rows * T + 255) / 256, 148LL * 16));
-  ncw_cast_kernel<<<grid, 256, 0, stream>>>(x, nullptr, nullptr, static_cast<__nv_bfloat16*>(y), rows, T, y_pitch);
+  if (dtype == DT_F16) ncw_cast_kernel<DT_F16><<<grid, 256, 0, stream>>>(x, nullptr, nullptr, static_cast<unsigned short*>(y), rows, T, y_pitch);
+  else ncw_cast_kernel<DT_BF16><<<grid, 256, 0, stream>>>(x, nullptr, nullptr, static_cast<unsigned short*>(y), rows, T, y_pitch);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
 
-int ncw_bf16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, cudaStream_t stream) {
+int ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, cudaStream_t stream) {
+  if (int e = check_dt(dtype, "ncw_16_to_f32")) return e;
   if (x == nullptr || y == nullptr || B <= 0 || C <= 0 || T <= 0 || x_pitch < T)
-    return fail(V100_E_INVALID, "ncw_bf16_to_f32: bad arguments");
+    return fail(V100_E_INVALID, "ncw_16_to_f32: bad arguments");
   const long long rows = static_cast<long long>(B) * C;
   const int grid = int(std::min<long long>((rows * T + 255) / 256, 148LL * 16));
-  ncw_cast_kernel<<<grid, 256, 0, stream>>>(nullptr, static_cast<const __nv_bfloat16*>(x), y, nullptr, rows, T, x_pitch);
+  if (dtype == DT_F16) ncw_cast_kernel<DT_F16><<<grid, 256, 0, stream>>>(nullptr, static_cast<const unsigned short*>(x), y, nullptr, rows, T, x_pitch);
+  else ncw_cast_kernel<DT_BF16><<<grid, 256, 0, stream>>>(nullptr, static_cast<const unsigned short*>(x), y, nullptr, rows, T, x_pitch);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
 
 // y[b][c][t] = table[ids[b][t]][c]; one thread = one channel x 8 time steps (16-byte store).
 __global__ void __launch_bounds__(256)
-embedding_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
-                 __nv_bfloat16* __restrict__ y, long long y_pitch, int T, int V, int C) {
+embedding_kernel(const int64_t* __restrict__ ids, const unsigned short* __restrict__ table,
+                 unsigned short* __restrict__ y, long long y_pitch, int T, int V, int C) {
   const int b = blockIdx.z;
   const int c = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int t0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
   if (c >= C || t0 >= T) return;
-  const unsigned short* tab = reinterpret_cast<const unsigned short*>(table);
+  const unsigned short* tab = table;
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 8; i += 2) {
@@ -91,15 +104,15 @@ embedding_kernel(const int64_t* __restrict__ ids, const __nv_bfloat16* __restric
   *reinterpret_cast<uint4*>(y + (static_cast<long long>(b) * C + c) * y_pitch + t0) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-int embedding_ncw_bf16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
+int embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
                        cudaStream_t stream) {
   if (ids == nullptr || table == nullptr || y == nullptr) return fail(V100_E_INVALID, "embedding: null pointer");
   if (B <= 0 || T <= 0 || V <= 0 || C <= 0 || B > 65535) return fail(V100_E_INVALID, "embedding: bad sizes");
   if (y_pitch < T || (y_pitch & 7) || (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(V100_E_INVALID, "embedding: pitch must be >= T and a multiple of 8, base 16B aligned");
   dim3 grid((T + 255) / 256, (C + 7) / 8, B);
-  embedding_kernel<<<grid, 256, 0, stream>>>(ids, static_cast<const __nv_bfloat16*>(table),
-                                             static_cast<__nv_bfloat16*>(y), y_pitch, T, V, C);
+  embedding_kernel<<<grid, 256, 0, stream>>>(ids, static_cast<const unsigned short*>(table),
+                                             static_cast<unsigned short*>(y), y_pitch, T, V, C);
   V100_CUDA(cudaGetLastError());
   return 0;
 }

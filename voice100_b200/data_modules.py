@@ -93,17 +93,19 @@ class MelSpectrogramAudioTransform(nn.Module):
         out = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, K.MEL_POWER_F32_NCW)
         return out.valid().reshape(*lead, self.n_mels, T)
 
-    def logmel_batch(self, waveform: torch.Tensor, lengths: torch.Tensor, ncw_bf16: bool = False):
+    def logmel_batch(self, waveform: torch.Tensor, lengths: torch.Tensor, ncw_bf16: bool = False, ncw_dtype=None):
         """waveform fp32 [B, L_max], lengths [B] samples ->
-        (audio fp32 [B, T_max, 64] padded with BLANK_AUDIO  |  Ncw bf16 [B, 64, pitch] when ncw_bf16,
-         audio_len int32 [B])."""
+        (audio fp32 [B, T_max, 64] padded with BLANK_AUDIO  |  16-bit Ncw [B, 64, pitch] when `ncw_dtype`
+         (torch.bfloat16 / torch.float16) or `ncw_bf16` is given,  audio_len int32 [B])."""
+        if ncw_bf16 and ncw_dtype is None:
+            ncw_dtype = torch.bfloat16
         if not waveform.is_cuda:
             raise V100Error("MelSpectrogramAudioTransform runs only on CUDA tensors (no CPU path)")
         wav = waveform.to(torch.float32).contiguous()
         lengths = lengths.to(device=wav.device, dtype=torch.int32).contiguous()
         T = self.num_frames(wav.shape[1])
-        out = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T,
-                       K.MEL_LOG_BF16_NCW if ncw_bf16 else K.MEL_LOG_F32_NTC)
+        mode = K.MEL_LOG_F32_NTC if ncw_dtype is None else (K.MEL_LOG_F16_NCW if K.dt(ncw_dtype) == 1 else K.MEL_LOG_BF16_NCW)
+        out = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, mode)
         return out, 1 + torch.div(lengths, self.hop_length, rounding_mode="trunc")
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:

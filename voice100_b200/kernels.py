@@ -13,7 +13,16 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_RELU6 = 0, 1
-MEL_LOG_BF16_NCW, MEL_LOG_F32_NTC, MEL_POWER_F32_NCW = 0, 1, 2
+MEL_LOG_BF16_NCW, MEL_LOG_F32_NTC, MEL_POWER_F32_NCW, MEL_LOG_F16_NCW = 0, 1, 2, 3
+DTYPE_CODE = {torch.bfloat16: 0, torch.float16: 1}   # V100_DTYPE_*
+
+
+def dt(t) -> int:
+    """V100_DTYPE_* code of a storage tensor / torch dtype; anything but bf16/fp16 is an error."""
+    d = t if isinstance(t, torch.dtype) else t.dtype
+    if d not in DTYPE_CODE:
+        raise _lib.V100Error(f"storage dtype must be torch.bfloat16 or torch.float16, got {d}")
+    return DTYPE_CODE[d]
 
 
 def _stream():
@@ -67,8 +76,8 @@ def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: i
     """wav fp32 [B, L]; lengths int32 [B] (device); fb = (start, count, off, w) device tensors."""
     _cuda(wav, torch.float32), _cuda(lengths, torch.int32)
     B = wav.shape[0]
-    if mode == MEL_LOG_BF16_NCW:
-        out = empty_ncw(B, 64, T, wav.device)
+    if mode in (MEL_LOG_BF16_NCW, MEL_LOG_F16_NCW):
+        out = empty_ncw(B, 64, T, wav.device, torch.bfloat16 if mode == MEL_LOG_BF16_NCW else torch.float16)
         optr, pitch = out.data.data_ptr(), out.pitch
     elif mode == MEL_POWER_F32_NCW:
         out = Ncw(torch.empty((B, 64, pitch_of(T, 4)), device=wav.device, dtype=torch.float32), T)
@@ -82,65 +91,67 @@ def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: i
     return out
 
 
-def ntc_f32_to_ncw(x: torch.Tensor) -> Ncw:
+def ntc_f32_to_ncw(x: torch.Tensor, dtype=torch.bfloat16) -> Ncw:
     _cuda(x, torch.float32)
     B, T, Cc = x.shape
-    y = empty_ncw(B, Cc, T, x.device)
-    _lib.call("v100_ntc_f32_to_ncw_bf16", x.data_ptr(), y.data.data_ptr(), B, T, Cc, y.pitch, _stream())
+    y = empty_ncw(B, Cc, T, x.device, dtype)
+    _lib.call("v100_ntc_f32_to_ncw16", x.data_ptr(), y.data.data_ptr(), B, T, Cc, y.pitch, dt(dtype), _stream())
     return y
 
 
-def ncw_from_f32(x: torch.Tensor) -> Ncw:
+def ncw_from_f32(x: torch.Tensor, dtype=torch.bfloat16) -> Ncw:
     _cuda(x, torch.float32)
     B, Cc, T = x.shape
-    y = empty_ncw(B, Cc, T, x.device)
-    _lib.call("v100_ncw_f32_to_bf16", x.data_ptr(), y.data.data_ptr(), y.pitch, B, Cc, T, _stream())
+    y = empty_ncw(B, Cc, T, x.device, dtype)
+    _lib.call("v100_ncw_f32_to_16", x.data_ptr(), y.data.data_ptr(), y.pitch, B, Cc, T, dt(dtype), _stream())
     return y
 
 
 def ncw_to_f32(x: Ncw) -> torch.Tensor:
     y = torch.empty((x.B, x.C, x.T), device=x.data.device, dtype=torch.float32)
-    _lib.call("v100_ncw_bf16_to_f32", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, _stream())
+    _lib.call("v100_ncw_16_to_f32", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, dt(x.data), _stream())
     return y
 
 
 def conv1x1(x: Ncw, W: torch.Tensor, scale, shift, act: int, res: Ncw = None) -> Ncw:
     C_out, C_in = W.shape
     assert C_in == x.C, (C_in, x.C)
-    y = empty_ncw(x.B, C_out, x.T, x.data.device)
+    assert W.dtype == x.data.dtype, "weights and activations must share the storage dtype"
+    y = empty_ncw(x.B, C_out, x.T, x.data.device, x.data.dtype)
     if res is not None:
-        assert res.data.shape == y.data.shape and res.T == x.T
-    _lib.call("v100_conv1x1_bf16", x.data.data_ptr(), x.pitch, W.data_ptr(), _ptr(scale), shift.data_ptr(),
+        assert res.data.shape == y.data.shape and res.T == x.T and res.data.dtype == x.data.dtype
+    _lib.call("v100_conv1x1", x.data.data_ptr(), x.pitch, W.data_ptr(), _ptr(scale), shift.data_ptr(),
               None if res is None else res.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, C_in, C_out, x.T,
-              act, _stream())
+              act, dt(x.data), _stream())
     return y
 
 
 def conv1x1_f32(x: Ncw, W: torch.Tensor, bias: torch.Tensor) -> Ncw:
     C_out, C_in = W.shape
-    assert C_in == x.C
+    assert C_in == x.C and W.dtype == x.data.dtype
     y = Ncw(torch.empty((x.B, C_out, x.pitch), device=x.data.device, dtype=torch.float32), x.T)
     _lib.call("v100_conv1x1_f32out", x.data.data_ptr(), x.pitch, W.data_ptr(), bias.data_ptr(), y.data.data_ptr(),
-              y.pitch, x.B, C_in, C_out, x.T, _stream())
+              y.pitch, x.B, C_in, C_out, x.T, dt(x.data), _stream())
     return y
 
 
 def dwconv(x: Ncw, w: torch.Tensor, scale, shift, k: int, stride: int, act: int, simt: bool = False) -> Ncw:
     T_out = (x.T - 1) // stride + 1
-    y = empty_ncw(x.B, x.C, T_out, x.data.device)
-    _lib.call("v100_dwconv1d_bf16_simt" if simt else "v100_dwconv1d_bf16", x.data.data_ptr(), x.pitch,
+    assert w.dtype == x.data.dtype
+    y = empty_ncw(x.B, x.C, T_out, x.data.device, x.data.dtype)
+    _lib.call("v100_dwconv1d_simt" if simt else "v100_dwconv1d", x.data.data_ptr(), x.pitch,
               w.data_ptr(), _ptr(scale), shift.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, k, stride,
-              act, _stream())
+              act, dt(x.data), _stream())
     return y
 
 
 def convtranspose_k5s2(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor) -> Ncw:
     C_out = Wp.shape[0]
-    assert Wp.shape[1] == 5 * x.C
-    y = empty_ncw(x.B, C_out, 2 * x.T - 1, x.data.device)
-    ws = torch.empty((x.B, 3 * x.C, x.pitch), device=x.data.device, dtype=torch.bfloat16)
-    _lib.call("v100_convtranspose1d_k5s2_bf16", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
-              ws.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, _stream())
+    assert Wp.shape[1] == 5 * x.C and Wp.dtype == x.data.dtype
+    y = empty_ncw(x.B, C_out, 2 * x.T - 1, x.data.device, x.data.dtype)
+    ws = torch.empty((x.B, 3 * x.C, x.pitch), device=x.data.device, dtype=x.data.dtype)
+    _lib.call("v100_convtranspose1d_k5s2", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
+              ws.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, dt(x.data), _stream())
     return y
 
 
@@ -148,8 +159,9 @@ def embedding_ncw(ids: torch.Tensor, table: torch.Tensor) -> Ncw:
     _cuda(ids, torch.int64)
     B, T = ids.shape
     V, Cc = table.shape
-    y = empty_ncw(B, Cc, T, ids.device)
-    _lib.call("v100_embedding_ncw_bf16", ids.data_ptr(), table.data_ptr(), y.data.data_ptr(), y.pitch, B, T, V, Cc,
+    dt(table)
+    y = empty_ncw(B, Cc, T, ids.device, table.dtype)
+    _lib.call("v100_embedding_ncw16", ids.data_ptr(), table.data_ptr(), y.data.data_ptr(), y.pitch, B, T, V, Cc,
               _stream())
     return y
 

@@ -12,17 +12,18 @@ from torch import nn
 
 from . import kernels as K
 from ._lib import V100Error
-from .blocks import InvertedResidualParams, PreparedCache, require_eval_cuda, run_inverted_residual
+from .blocks import (InvertedResidualParams, PreparedCache, StorageDtypeMixin, require_eval_cuda,
+                     run_inverted_residual)
 from .synth import ALIGN_KERNELS, VOICE_DECODER_POST_KERNELS, VOICE_DECODER_PRE_KERNELS
 
 __all__ = ["TextToAlignTextModel", "AlignTextToAudioModel", "VoiceDecoder", "WORLDNorm", "align_batch"]
 
 
-def _head(conv: nn.Conv1d):
-    return (conv.weight.detach()[:, :, 0].to(torch.bfloat16).contiguous(), conv.bias.detach().float().contiguous())
+def _head(conv: nn.Conv1d, dtype):
+    return (conv.weight.detach()[:, :, 0].to(dtype).contiguous(), conv.bias.detach().float().contiguous())
 
 
-class TextToAlignTextModel(nn.Module):
+class TextToAlignTextModel(StorageDtypeMixin, nn.Module):
     def __init__(self, vocab_size: int, hidden_size: int, learning_rate: float = 1e-3) -> None:
         super().__init__()
         self.hparams = dict(vocab_size=vocab_size, hidden_size=hidden_size, learning_rate=learning_rate)
@@ -31,8 +32,9 @@ class TextToAlignTextModel(nn.Module):
             *[InvertedResidualParams(hidden_size, hidden_size, k) for k in ALIGN_KERNELS],
             nn.Conv1d(hidden_size, 2, 1, bias=True))
         self._prepared = PreparedCache(self, lambda: dict(
-            table=self.embedding.weight.detach().to(torch.bfloat16).contiguous(),
-            blocks=[self.layers[i].prepare() for i in range(4)], head=_head(self.layers[4])))
+            table=self.embedding.weight.detach().to(self.storage_dtype).contiguous(),
+            blocks=[self.layers[i].prepare(self.storage_dtype) for i in range(4)],
+            head=_head(self.layers[4], self.storage_dtype)))
         self.eval()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -105,7 +107,7 @@ def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_va
     return torch.from_numpy(res), torch.tensor([len(o) for o in outs], dtype=torch.int32)
 
 
-class VoiceDecoder(nn.Module):
+class VoiceDecoder(StorageDtypeMixin, nn.Module):
     def __init__(self, hidden_size: int, out_channels: int) -> None:
         super().__init__()
         half = hidden_size // 2
@@ -120,10 +122,11 @@ class VoiceDecoder(nn.Module):
         up = self.layers[4]
         c_in, c_out, _ = up.weight.shape
         # Wp[co][tap*C_in + ci] = weight[ci][co][tap]  (ConvTranspose1d stores [C_in, C_out, k])
-        wp = up.weight.detach().permute(1, 2, 0).reshape(c_out, 5 * c_in).to(torch.bfloat16).contiguous()
-        return dict(pre=[self.layers[i].prepare() for i in range(4)], wp=wp,
+        dtype = self.storage_dtype
+        wp = up.weight.detach().permute(1, 2, 0).reshape(c_out, 5 * c_in).to(dtype).contiguous()
+        return dict(pre=[self.layers[i].prepare(dtype) for i in range(4)], wp=wp,
                     up_bias=up.bias.detach().float().contiguous(),
-                    post=[self.layers[i].prepare() for i in range(5, 8)], head=_head(self.layers[8]))
+                    post=[self.layers[i].prepare(dtype) for i in range(5, 8)], head=_head(self.layers[8], dtype))
 
     def run(self, x: K.Ncw) -> K.Ncw:
         """bf16 Ncw [B, H, T] -> fp32 Ncw [B, out_channels, 2T-1]."""
@@ -137,7 +140,7 @@ class VoiceDecoder(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         require_eval_cuda(self, x)
-        return self.run(K.ncw_from_f32(x.float().contiguous())).valid().contiguous()
+        return self.run(K.ncw_from_f32(x.float().contiguous(), self.storage_dtype)).valid().contiguous()
 
 
 class WORLDNorm(nn.Module):
@@ -157,7 +160,7 @@ class WORLDNorm(nn.Module):
         return mean, std
 
 
-class AlignTextToAudioModel(nn.Module):
+class AlignTextToAudioModel(StorageDtypeMixin, nn.Module):
     def __init__(self, vocab_size: int, hidden_size: int, learning_rate: float = 1e-3, use_mcep: bool = False) -> None:
         super().__init__()
         if use_mcep:
@@ -172,7 +175,7 @@ class AlignTextToAudioModel(nn.Module):
         self.decoder = VoiceDecoder(hidden_size, self.audio_size)
         self.norm = WORLDNorm(self.logspc_size, self.codeap_size)
         self._prepared = PreparedCache(self, lambda: dict(
-            table=self.embedding.weight.detach().to(torch.bfloat16).contiguous(), norm=self.norm.packed()))
+            table=self.embedding.weight.detach().to(self.storage_dtype).contiguous(), norm=self.norm.packed()))
         self.eval()
 
     def _decode(self, aligntext: torch.Tensor) -> K.Ncw:
