@@ -127,3 +127,29 @@ def test_bench_work_model_matches_survey():
     gemm = sum(w["flops"] for w in work if w["kind"] == "gemm") / 1e6
     dw = sum(w["flops"] for w in work if w["kind"] == "dwconv") / 1e6
     assert abs(gemm - 1084.6 - 1.48) / 1086 < 0.03 and abs(dw - 72.0) / 72.0 < 0.03, (gemm, dw)
+
+
+def test_load_checkpoint_roundtrip(tmp_path):
+    """Lightning-style .ckpt (state_dict + hyper_parameters, plus training-only keys) -> drop-in module."""
+    from collections import OrderedDict
+    sd = OrderedDict((k, torch.from_numpy(np.asarray(x))) for k, x in synth.asr_state_dict(64, 128, 44, 128, seed=8).items())
+    sd["criterion.dummy"] = torch.zeros(1)      # training-only sub-module state is ignored
+    path = tmp_path / "asr.ckpt"
+    torch.save({"state_dict": sd, "hyper_parameters": {"audio_size": 64, "embed_size": 128.0, "vocab_size": 44,
+                                                       "hidden_size": 128.0, "learning_rate": 1e-3}}, path)
+    m = v.load_checkpoint(str(path), device="cpu")
+    assert isinstance(m, v.AudioToTextCTC) and not m.training
+    assert m.decoder.layers[1].weight.shape == (44, 128, 1)
+    assert torch.equal(m.state_dict()["encoder.layers.3.conv.1.0.weight"], sd["encoder.layers.3.conv.1.0.weight"])
+    # bare state_dict of the audio model, class inferred from the keys, WORLD statistics from a side file
+    au = {k: torch.from_numpy(np.asarray(x)) for k, x in synth.audio_state_dict(29, 64, seed=8).items()}
+    stat = {k[len("norm."):]: torch.from_numpy(np.asarray(x)) for k, x in
+            synth.audio_state_dict(29, 64, seed=9, randomize_norm=True).items() if k.startswith("norm.")}
+    torch.save(au, tmp_path / "audio.pt")
+    torch.save(stat, tmp_path / "stat.pt")
+    m2 = v.load_checkpoint(str(tmp_path / "audio.pt"), audio_stat=str(tmp_path / "stat.pt"), device="cpu",
+                           storage_dtype=torch.float16)
+    assert isinstance(m2, v.AlignTextToAudioModel) and m2.storage_dtype == torch.float16
+    assert torch.equal(m2.norm.logspc_mean, stat["logspc_mean"])
+    with pytest.raises(v.V100Error):
+        v.load_checkpoint(str(path), model_class="TextToAlignTextModel", device="cpu")

@@ -13,3 +13,4 @@ from .data_modules import MelSpectrogramAudioTransform, BLANK_AUDIO, LOG_OFFSET,
 from .asr import AudioToTextCTC, ConvVoiceEncoder, LinearCharDecoder, AsrPipeline  # noqa: F401
 from .tts import TextToAlignTextModel, AlignTextToAudioModel, VoiceDecoder, WORLDNorm, align_batch  # noqa: F401
 from .text import CharTokenizer  # noqa: F401
+from .checkpoint import load_checkpoint  # noqa: F401
