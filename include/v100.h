@@ -156,6 +156,22 @@ int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* 
                       int B, int T, int blank, void* stream);
 
 /*
+ * Batched CTC forced alignment (Viterbi best path over the blank-expanded label sequence).  Replaces the
+ * per-utterance numpy DP `ctc_best_path` (voice100/models/align.py:18-66, max_move = 3) that the v2 aligner
+ * calls through .cpu().numpy() for every utterance (voice100/models/_asr_v2.py:100-119) -- SURVEY.md 8f #3.
+ *   logprob  fp32 [B][T][V] log-probabilities;  logit_len int32 [B] valid frames;
+ *   text     int64 [B][L] labels (0 = blank never appears inside);  text_len int32 [B];
+ *   workspace uint8 [B][T][2L+1] back-pointers (caller-provided scratch);
+ *   score fp32 [B]; path int32 [B][T] = state index per frame (the reference's best_path);
+ *   path_labels int64 [B][T] = expanded label per frame (best_labels); entries past logit_len are 0.
+ * An utterance whose frames cannot reach the end of its text (2*logit_len < 2*text_len+1, an IndexError in the
+ * reference) gets score = NaN and path = -1.
+ */
+int v100_ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text,
+                       const int32_t* text_len, uint8_t* workspace, float* score, int32_t* path,
+                       int64_t* path_labels, int B, int T, int V, int L, void* stream);
+
+/*
  * WORLD head tail: fp32 NCW [B][260][pitch] -> hasf0[B][T], f0[B][T], logspc[B][T][257],
  * codeap[B][T][1], with std*x+mean and f0 := 0 where hasf0 < 0 when `unnormalize` != 0.
  * Replaces split + WORLDNorm.unnormalize + where (tts.py:181-190,196-200; _layers_v1.py:131-138).

@@ -134,7 +134,30 @@ def gen_tts(seed=31):
           "voiced frac %.2f" % float((hasf0 >= 0).float().mean()))
 
 
+def gen_viterbi(seed=41):
+    """Forced-alignment vectors from the reference's own ctc_best_path (voice100/models/align.py:18-66)."""
+    from voice100.models.align import ctc_best_path as ref_best_path
+    out = {}
+    cases = [(60, 7), (200, 31), (751, 120), (40, 19), (3, 1)]
+    for ci, (T, L) in enumerate(cases):
+        lp, labels = viterbi_case(T, L, seed + ci)
+        score, path, best_labels = ref_best_path(lp, labels)
+        out[f"c{ci}_score"] = np.float32(score)
+        out[f"c{ci}_path"] = path.astype(np.int32)
+        out[f"c{ci}_labels"] = best_labels.astype(np.int64)
+    out["cases"] = np.asarray(cases, np.int64)
+    out["seed"] = np.int64(seed)
+    np.savez_compressed(os.path.join(OUT, "viterbi.npz"), **out)
+    print("viterbi", cases)
+
+
+def viterbi_case(T, L, seed):
+    from voice100_b200.synth import viterbi_inputs
+    return viterbi_inputs(T, L, 29, seed)
+
+
 if __name__ == "__main__":
+    gen_viterbi()
     gen_logmel()
     gen_asr("asr_en_small", hidden=256, embed=256, vocab=29, batch=2, samples=32000)
     gen_asr("asr_ja_phone_ragged", hidden=128, embed=128, vocab=44, batch=3, samples=24000,

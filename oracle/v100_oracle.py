@@ -324,6 +324,55 @@ def audio_predict(aligntext: torch.Tensor, sd: SD):
 
 
 # ----------------------------------------------------------------------------------------------
+# Forced alignment: voice100/models/align.py:18-66 (ctc_best_path, max_move = 3), the per-utterance numpy DP
+# behind AudioToAlignText.ctc_best_path (voice100/models/_asr_v2.py:100-119)
+# ----------------------------------------------------------------------------------------------
+
+def ctc_best_path(logprob: np.ndarray, labels: np.ndarray):
+    """Viterbi best path of `labels` through `logprob[T, V]` over the blank-expanded state sequence
+    (blank, l0, blank, l1, ..., blank).  Restated as a dense recurrence over all S = 2L+1 states with -inf
+    for states outside the active prefix (which starts at 2 states and grows by 2 per frame):
+        cand_j[v] = score[v - j] + logprob[i, lab[v]],  j = 0 (stay), 1 (advance), 2 (skip; not onto a blank)
+    first maximum over j wins (np.argmax), ending in the better of the last two states (ties -> S-2).
+    -> (best_score, best_path[T] state indices, best_labels[T]); fp32 arithmetic like the reference."""
+    logprob = np.asarray(logprob)
+    T = logprob.shape[0]
+    lab = np.zeros(2 * len(labels) + 1, dtype=np.asarray(labels).dtype)
+    lab[1::2] = labels
+    S = lab.shape[0]
+    NEG = np.float32(-np.inf)
+    score = np.full(S, NEG, dtype=logprob.dtype)
+    score[:2] = logprob[0, lab[:2]]
+    active = 2
+    back = np.zeros((T, S), dtype=np.int32)
+    for i in range(1, T):
+        nxt_active = min(active + 2, S)
+        emit = logprob[i, lab]
+        cands = np.full((3, S), NEG, dtype=logprob.dtype)
+        srcs = np.zeros((3, S), dtype=np.int32)
+        for j in range(3):
+            v = np.arange(j, min(active + j, S))
+            cands[j, v] = score[v - j] + emit[v]
+            srcs[j, v] = v - j
+        cands[2, lab == 0] = NEG
+        pick = np.argmax(cands[:, :nxt_active], axis=0)
+        cols = np.arange(nxt_active)
+        score = np.full(S, NEG, dtype=logprob.dtype)
+        score[:nxt_active] = cands[pick, cols]
+        back[i, :nxt_active] = srcs[pick, cols]
+        active = nxt_active
+    if active < S:
+        raise IndexError("too few frames to reach the end of the text (same failure as the reference)")
+    j = S - 1 if score[S - 1] > score[S - 2] else S - 2
+    best = score[j]
+    path = np.zeros(T, dtype=np.int32)
+    for i in range(T - 1, -1, -1):
+        path[i] = j
+        j = back[i, j]
+    return best, path, lab[path]
+
+
+# ----------------------------------------------------------------------------------------------
 # helpers shared by tests / bench
 # ----------------------------------------------------------------------------------------------
 

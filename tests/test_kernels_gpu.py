@@ -246,6 +246,45 @@ def test_ctc_collapse_matches_reference_text_rule():
         assert (ids[b, int(counts[b]):] == 0).all()
 
 
+def test_ctc_best_path_matches_oracle_bit_exact():
+    """Integer/index work: the device Viterbi must reproduce the reference DP exactly (golden + live oracle)."""
+    import voice100_b200 as v
+    from helpers import golden
+    g = golden("viterbi")
+    cases = [(int(T), int(L)) for T, L in g["cases"]]
+    extra = [(300, 60, 900), (751, 200, 901), (97, 48, 902), (20, 30, 903)]      # last: too few frames
+    T_max = max([c[0] for c in cases] + [e[0] for e in extra])
+    L_max = max([c[1] for c in cases] + [e[1] for e in extra])
+    B = len(cases) + len(extra)
+    lp = torch.zeros(B, T_max, 29)
+    text = torch.zeros(B, L_max, dtype=torch.int64)
+    n_frames, n_text, refs = [], [], []
+    for ci, (T, L) in enumerate(cases):
+        a, lab = synth.viterbi_inputs(T, L, 29, int(g["seed"]) + ci)
+        refs.append((g[f"c{ci}_score"], g[f"c{ci}_path"], g[f"c{ci}_labels"]))
+        lp[ci, :T], text[ci, :L] = torch.from_numpy(a), torch.from_numpy(lab)
+        n_frames.append(T); n_text.append(L)
+    for ei, (T, L, seed) in enumerate(extra):
+        a, lab = synth.viterbi_inputs(T, L, 29, seed)
+        try:
+            refs.append(orc.ctc_best_path(a, lab))
+        except IndexError:
+            refs.append(None)
+        lp[len(cases) + ei, :T], text[len(cases) + ei, :L] = torch.from_numpy(a), torch.from_numpy(lab)
+        n_frames.append(T); n_text.append(L)
+    score, hist, path, _ = v.ctc_best_path_batch(lp.to(DEV), torch.tensor(n_frames), text.to(DEV), torch.tensor(n_text))
+    torch.cuda.synchronize()
+    for b, ref in enumerate(refs):
+        T = n_frames[b]
+        if ref is None:
+            assert torch.isnan(score[b]) and (hist[b] == -1).all()
+            continue
+        assert float(score[b]) == float(np.float32(ref[0])), b
+        assert np.array_equal(hist[b, :T].cpu().numpy(), ref[1]) and np.array_equal(path[b, :T].cpu().numpy(), ref[2]), b
+        assert (hist[b, T:] == 0).all()
+    assert refs[-1] is None
+
+
 def test_errors_are_loud():
     from voice100_b200 import V100Error
     x = K.empty_ncw(1, 60, 16, DEV)     # C_in not a multiple of 8

@@ -112,3 +112,15 @@ def test_ctc_collapse_known_answers():
     assert orc.ctc_collapse_text(enc("___")) == ""
     assert orc.ctc_collapse_text(enc("_ _")) == ""
     assert orc.ctc_collapse_text([0, 99, -1, 2, 2, 0, 2]) == "aa"
+
+
+def test_viterbi_matches_reference():
+    """oracle ctc_best_path vs voice100/models/align.py:18-66 run by oracle/gen_golden.py: bit-exact."""
+    g = golden("viterbi")
+    for ci, (T, L) in enumerate(g["cases"]):
+        lp, labels = synth.viterbi_inputs(int(T), int(L), 29, int(g["seed"]) + ci)
+        score, path, best_labels = orc.ctc_best_path(lp, labels)
+        assert np.float32(score) == g[f"c{ci}_score"]
+        assert np.array_equal(path, g[f"c{ci}_path"]) and np.array_equal(best_labels, g[f"c{ci}_labels"])
+        # structural properties of any valid alignment
+        assert path[0] in (0, 1) and path[-1] in (2 * L - 1, 2 * L) and (np.diff(path) >= 0).all() and (np.diff(path) <= 2).all()

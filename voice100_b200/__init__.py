@@ -14,3 +14,4 @@ from .asr import AudioToTextCTC, ConvVoiceEncoder, LinearCharDecoder, AsrPipelin
 from .tts import TextToAlignTextModel, AlignTextToAudioModel, VoiceDecoder, WORLDNorm, align_batch  # noqa: F401
 from .text import CharTokenizer  # noqa: F401
 from .checkpoint import load_checkpoint  # noqa: F401
+from .align import ctc_best_path_batch  # noqa: F401

@@ -27,6 +27,7 @@ SIGNATURES = {
     "v100_embedding_ncw16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
     "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p],
     "v100_ctc_collapse": [_p, _p, _p, _p, _i, _i, _i, _p],
+    "v100_ctc_best_path": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
 }

@@ -149,6 +149,13 @@ int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* 
   return ctc_collapse(tokens, valid_len, out, out_len, B, T, blank, STREAM(stream));
 }
 
+int v100_ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
+                       uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V,
+                       int L, void* stream) {
+  return ctc_best_path(logprob, logit_len, text, text_len, workspace, score, path, path_labels, B, T, V, L,
+                       STREAM(stream));
+}
+
 int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0,
                         float* f0, float* logspc, float* codeap, int B, int T, int unnormalize, void* stream) {
   return world_finalize(y_ncw, y_pitch, mean, std, hasf0, f0, logspc, codeap, B, T, unnormalize, STREAM(stream));

@@ -47,6 +47,9 @@ int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* to
                  cudaStream_t stream);
 int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
                  int blank, cudaStream_t stream);
+int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
+                  uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V, int L,
+                  cudaStream_t stream);
 int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0, float* f0,
                    float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream);
 int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream);

@@ -184,6 +184,110 @@ int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, 
   return 0;
 }
 
+// Batched CTC forced alignment (Viterbi best path), voice100/models/align.py:18-66 (`ctc_best_path`, called per
+// utterance through .cpu().numpy() by the v2 aligner, _asr_v2.py:100-119).  One CTA per utterance; the state
+// vector (expanded labels: blank, l0, blank, l1, ... = S = 2L+1 states) lives in shared memory, every time step
+// is one parallel sweep over the states, back-pointers go to a caller-provided workspace.  Arithmetic is the
+// reference's: fp32 `score[k] + logprob[i][label[v]]`, candidates j = 0,1,2 (stay / advance / skip, the skip
+// never lands on a blank), first maximum wins, the active prefix grows by two states per step.
+__global__ void __launch_bounds__(256)
+ctc_best_path_kernel(const float* __restrict__ logprob, const int32_t* __restrict__ logit_len,
+                     const int64_t* __restrict__ text, const int32_t* __restrict__ text_len,
+                     uint8_t* __restrict__ back, float* __restrict__ score, int32_t* __restrict__ path,
+                     int64_t* __restrict__ path_labels, int T, int V, int L) {
+  extern __shared__ float vit_smem[];
+  const int b = blockIdx.x;
+  const int S_max = 2 * L + 1;
+  float* sc0 = vit_smem;
+  float* sc1 = vit_smem + S_max;
+  int* lab = reinterpret_cast<int*>(vit_smem + 2 * S_max);
+  const int n = min(max(logit_len[b], 0), T);
+  const int l = min(max(text_len[b], 0), L);
+  const int S = 2 * l + 1;
+  const float* lp = logprob + static_cast<long long>(b) * T * V;
+  uint8_t* bk = back + static_cast<long long>(b) * T * S_max;
+  const float NEG_INF = __int_as_float(0xff800000);
+
+  for (int v = threadIdx.x; v < S; v += blockDim.x) {
+    lab[v] = (v & 1) ? static_cast<int>(text[static_cast<long long>(b) * L + (v >> 1)]) : 0;
+    sc0[v] = NEG_INF;
+  }
+  __syncthreads();
+  if (n == 0) {
+    if (threadIdx.x == 0) score[b] = __int_as_float(0x7fc00000);
+    return;
+  }
+  if (threadIdx.x < 2 && threadIdx.x < S) sc0[threadIdx.x] = lp[lab[threadIdx.x]];
+  __syncthreads();
+  int len = min(2, S);
+  float* prev = sc0;
+  float* next = sc1;
+  for (int i = 1; i < n; ++i) {
+    const int len_next = min(len + 2, S);
+    const float* row = lp + static_cast<long long>(i) * V;
+    for (int v = threadIdx.x; v < len_next; v += blockDim.x) {
+      const float e = row[lab[v]];
+      float best = NEG_INF;
+      int best_j = 0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = v - j;
+        float c = NEG_INF;
+        if (k >= 0 && k < len && !(j == 2 && lab[v] == 0)) c = prev[k] + e;
+        if (c > best) { best = c; best_j = j; }       // strict: the first maximum wins, like np.argmax
+      }
+      const int kb = v - best_j;
+      next[v] = best;
+      // back-pointer code: 0..2 = came from v - code; 3 = the reference's uninitialised 0 (no valid predecessor)
+      bk[static_cast<long long>(i) * S_max + v] = (kb >= 0 && kb < len) ? static_cast<uint8_t>(best_j) : static_cast<uint8_t>(3);
+    }
+    __syncthreads();
+    float* t = prev; prev = next; next = t;
+    len = len_next;
+  }
+  if (threadIdx.x == 0) {
+    if (len < S || S < 2) {
+      // the reference indexes scores[labels_len - 1] here and raises IndexError: too few frames for this text
+      score[b] = __int_as_float(0x7fc00000);
+      for (int i = 0; i < T; ++i) { path[static_cast<long long>(b) * T + i] = -1; path_labels[static_cast<long long>(b) * T + i] = 0; }
+    } else {
+      int j = S + ((prev[S - 1] > prev[S - 2]) ? -1 : -2);
+      score[b] = prev[j];
+      for (int i = n - 1; i >= 0; --i) {
+        path[static_cast<long long>(b) * T + i] = j;
+        path_labels[static_cast<long long>(b) * T + i] = lab[j];
+        if (i > 0) {
+          const uint8_t code = bk[static_cast<long long>(i) * S_max + j];
+          j = code == 3 ? 0 : j - code;
+        }
+      }
+      for (int i = n; i < T; ++i) { path[static_cast<long long>(b) * T + i] = 0; path_labels[static_cast<long long>(b) * T + i] = 0; }
+    }
+  }
+}
+
+int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
+                  uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V, int L,
+                  cudaStream_t stream) {
+  if (logprob == nullptr || logit_len == nullptr || text == nullptr || text_len == nullptr || workspace == nullptr ||
+      score == nullptr || path == nullptr || path_labels == nullptr)
+    return fail(V100_E_INVALID, "ctc_best_path: null pointer");
+  if (B <= 0 || T <= 0 || V <= 0 || L <= 0) return fail(V100_E_INVALID, "ctc_best_path: bad sizes");
+  const size_t smem = size_t(3) * (2 * L + 1) * 4;
+  if (smem > 200 * 1024) return fail(V100_E_UNSUPPORTED, "ctc_best_path: text length %d too long for shared memory", L);
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V100_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V100_CUDA(cudaFuncSetAttribute(ctc_best_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dev = dev;
+  }
+  ctc_best_path_kernel<<<B, 256, smem, stream>>>(logprob, logit_len, text, text_len, workspace, score, path,
+                                                 path_labels, T, V, L);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // fp32 NCW [B][C][pitch] -> [B][T][C] through a 32x32 tile.
 __global__ void __launch_bounds__(256)
 ncw_to_ntc_kernel(const float* __restrict__ y, long long pitch, float* __restrict__ out, int C, int T) {

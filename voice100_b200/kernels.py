@@ -186,6 +186,24 @@ def ctc_collapse(tokens: torch.Tensor, valid_len: torch.Tensor = None, blank: in
     return out, out_len
 
 
+def ctc_best_path(logprob: torch.Tensor, logit_len: torch.Tensor, text: torch.Tensor, text_len: torch.Tensor):
+    """logprob fp32 [B, T, V], logit_len [B], text int64 [B, L], text_len [B] ->
+    (score fp32 [B], path int32 [B, T] state indices, path_labels int64 [B, T])."""
+    _cuda(logprob, torch.float32), _cuda(text, torch.int64)
+    B, T, V = logprob.shape
+    L = text.shape[1]
+    dev = logprob.device
+    ll = logit_len.to(device=dev, dtype=torch.int32).contiguous()
+    tl = text_len.to(device=dev, dtype=torch.int32).contiguous()
+    ws = torch.empty((B, T, 2 * L + 1), device=dev, dtype=torch.uint8)
+    score = torch.empty((B,), device=dev, dtype=torch.float32)
+    path = torch.empty((B, T), device=dev, dtype=torch.int32)
+    labels = torch.empty((B, T), device=dev, dtype=torch.int64)
+    _lib.call("v100_ctc_best_path", logprob.data_ptr(), ll.data_ptr(), text.data_ptr(), tl.data_ptr(), ws.data_ptr(),
+              score.data_ptr(), path.data_ptr(), labels.data_ptr(), B, T, V, L, _stream())
+    return score, path, labels
+
+
 def world_finalize(y: Ncw, mean, std, unnormalize: bool):
     B, T, dev = y.B, y.T, y.data.device
     assert y.C == 260

@@ -191,3 +191,16 @@ def synthetic_alignment(batch: int, length: int, seed=1234) -> np.ndarray:
     a[..., 0] = g.random((batch, length))
     a[..., 1] = 4.0 * g.random((batch, length))
     return a
+
+
+def viterbi_inputs(T: int, L: int, vocab_size: int = 29, seed=1234):
+    """Seeded forced-alignment inputs: fp32 log-probabilities [T, V] (log-softmax of N(0, 2)) and a label
+    sequence [L] of non-blank ids with some immediate repeats (the case a naive CTC topology gets wrong)."""
+    g = _rng(seed, f"viterbi{T}x{L}")
+    z = (2.0 * g.standard_normal((T, vocab_size))).astype(np.float32)
+    z = z - z.max(axis=1, keepdims=True)
+    lp = (z - np.log(np.exp(z).sum(axis=1, keepdims=True))).astype(np.float32)
+    labels = g.integers(1, vocab_size, size=L).astype(np.int64)
+    rep = g.random(L) < 0.2
+    labels[1:][rep[1:]] = labels[:-1][rep[1:]]
+    return lp, labels
