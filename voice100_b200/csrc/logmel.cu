@@ -64,7 +64,8 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
     }
   const int s0a = __ldg(fb_start + lane), s0b = __ldg(fb_start + lane + 32);
   const int cnta = __ldg(fb_count + lane), cntb = __ldg(fb_count + lane + 32);
-  const int cnt_max = max(__reduce_max_sync(0xffffffffu, cnta), __reduce_max_sync(0xffffffffu, cntb));
+  // filters 0..31 are short (<= 6 bins), filters 32..63 long (<= 20): separate trip counts
+  const int cnt_max_a = __reduce_max_sync(0xffffffffu, cnta), cnt_max_b = __reduce_max_sync(0xffffffffu, cntb);
 
   const int L = len[b];
   const int n_frames = 1 + L / kHop;
@@ -131,12 +132,9 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
     }
     if (lane == 0) P[256] = rfft512_power(A, 256, cpx{-1.0f, 0.0f});
     __syncwarp();
-    float acca = 0.0f, accb = 0.0f;
-    for (int i = 0; i < cnt_max; ++i) {   // melw is zero past each filter's own length; P stays in range
-      acca = fmaf(melw[i][lane], P[min(s0a + i, 256)], acca);
-      accb = fmaf(melw[i][lane + 32], P[min(s0b + i, 256)], accb);
-    }
-    (void)cnta; (void)cntb;
+    float acca = 0.0f, accb = 0.0f;   // melw is zero past each filter's own length; P stays in range
+    for (int i = 0; i < cnt_max_a; ++i) acca = fmaf(melw[i][lane], P[min(s0a + i, 256)], acca);
+    for (int i = 0; i < cnt_max_b; ++i) accb = fmaf(melw[i][lane + 32], P[min(s0b + i, 256)], accb);
     tile[lane][fl] = out_mode == V100_MEL_POWER_F32_NCW ? acca : logf(acca + log_offset);
     tile[lane + 32][fl] = out_mode == V100_MEL_POWER_F32_NCW ? accb : logf(accb + log_offset);
     __syncwarp();
