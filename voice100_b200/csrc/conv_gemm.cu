@@ -57,10 +57,6 @@ struct GemmParams {
   int dtype;                // DT_BF16 / DT_F16: storage type of x, W, y, res
   float* y32;
   long long y32_pitch;
-  unsigned short* y16;      // direct-store epilogue (no residual): plain 16-byte global stores, no smem/TMA
-  long long y16_pitch;
-  int T_out;
-  int direct_store;
 };
 
 template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG = 1>
@@ -292,10 +288,6 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           // the previous chunk.  With a residual it now holds this chunk's residual sub-tile.
           if (p.has_res) mbar_wait(&rbar[buf], (n >> 1) & 1);
           uint8_t* rowp = my_row + buf * kWarpChunkBytes;
-          const bool direct = p.direct_store && !p.has_res;
-          const long long tcol = static_cast<long long>(t_tile) * Cfg::kOutCols + c * 64;
-          unsigned short* grow = p.y16 + (static_cast<long long>(b) * p.C_out + (m0 + lane)) * p.y16_pitch + tcol;
-          const bool row_ok = (m0 + lane) < p.C_out;
 #pragma unroll
           for (int k16 = 0; k16 < 8; ++k16) {
             uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4));
@@ -351,14 +343,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
                 w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
               }
             }
-            if (direct) {
-              // 16 bytes of this thread's own output row; columns past T but inside the pitch are padding
-              if (row_ok && tcol + k16 * 8 < p.y16_pitch) *reinterpret_cast<uint4*>(grow + k16 * 8) = w;
-            } else {
-              *dst = w;
-            }
+            *dst = w;
           }
-          if (direct) continue;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -537,9 +523,6 @@ int conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, c
   p.k_blocks = (C_in + kBlockK - 1) / kBlockK;
   p.n_taps = 1; p.tap_xrow[0] = 0; p.tap_acc[0] = 0;
   p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr; p.dtype = dtype;
-  p.y16 = static_cast<unsigned short*>(y); p.y16_pitch = y_pitch; p.T_out = T;
-  static const int direct_env = getenv("V100_GEMM_DIRECT") ? atoi(getenv("V100_GEMM_DIRECT")) : 0;  // A/B switch
-  p.direct_store = direct_env;
   p.t_tiles = (T + bn - 1) / bn;
   static const int force_cg = getenv("V100_GEMM_CG") ? atoi(getenv("V100_GEMM_CG")) : 0;  // debugging / A-B runs
   if (bn == 256 && C_out % (2 * kBlockM) == 0 && force_cg != 1) {
