@@ -146,14 +146,7 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
     const uint2* xw = reinterpret_cast<const uint2*>(xs) + lane;
     unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
     int pos = pos0;
-#pragma unroll 1
-    for (int tile = 0; tile < n_tiles; ++tile) {
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint2 bq = xw[4 * q];
-        mma_16816<DT>(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
-      }
+    auto finish_tile = [&](float (&acc)[4], unsigned short* yq, int posq) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
       // acc = out[tau + g + 32tg + {0, 16}], out[tau + g + 8 + 32tg + {0, 16}]; trade with lane g^1 so that even
@@ -170,11 +163,34 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
         o0 = pack2<DT>(lo0, hi0);
         o1 = pack2<DT>(lo1, hi1);
       }
-      if (pos >= 0 && pos < len) *reinterpret_cast<uint32_t*>(yp) = o0;
-      if (pos + 16 >= 0 && pos + 16 < len) *reinterpret_cast<uint32_t*>(yp + 16) = o1;
-      xw += 32;
-      yp += 128;
-      pos += 128;
+      if (posq >= 0 && posq < len) *reinterpret_cast<uint32_t*>(yq) = o0;
+      if (posq + 16 >= 0 && posq + 16 < len) *reinterpret_cast<uint32_t*>(yq + 16) = o1;
+    };
+    int tile = 0;
+#pragma unroll 1
+    for (; tile + 2 <= n_tiles; tile += 2) {   // two tiles per trip: two independent mma chains interleave
+      float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const uint2 b0q = xw[4 * q];
+        const uint2 b1q = xw[32 + 4 * q];
+        mma_16816<DT>(acc0, af[q][0], af[q][1], af[q][2], af[q][3], b0q.x, b0q.y);
+        mma_16816<DT>(acc1, af[q][0], af[q][1], af[q][2], af[q][3], b1q.x, b1q.y);
+      }
+      finish_tile(acc0, yp, pos);
+      finish_tile(acc1, yp + 128, pos + 128);
+      xw += 64;
+      yp += 256;
+      pos += 256;
+    }
+    if (tile < n_tiles) {
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const uint2 bq = xw[4 * q];
+        mma_16816<DT>(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
+      }
+      finish_tile(acc, yp, pos);
     }
     __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
