@@ -291,6 +291,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from voice100_b200.dist import bind_to_gpu_numa
+        bind_to_gpu_numa(local)          # pinned host buffers of each rank live next to its GPU
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
     K = max(1, args.steps)

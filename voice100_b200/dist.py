@@ -45,3 +45,24 @@ def sum_over_ranks(value: float, device="cpu") -> float:
 def job_throughput(units_this_rank: float, seconds_this_rank: float, device="cpu") -> float:
     """Aggregate throughput: all ranks' units / the slowest rank's time."""
     return sum_over_ranks(units_this_rank, device) / max_over_ranks(seconds_this_rank, device)
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index`, so that pinned host buffers
+    allocated afterwards are first-touched on that NUMA node and H2D copies of the ranks do not all cross one
+    socket's memory controllers.  Best effort: returns False when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return False
+        os.sched_setaffinity(0, cpus)
+        return True
+    except Exception:
+        return False
