@@ -151,6 +151,64 @@ def gen_viterbi(seed=41):
     print("viterbi", cases)
 
 
+def gen_asr_v2(name, settings, hidden, vocab, batch, samples, lengths, seed):
+    """AudioToAlignText (voice100/models/_asr_v2.py:18-49), the architecture of the shipped asr_*.yaml configs."""
+    from voice100.models._asr_v2 import AudioToAlignText
+    tr = MelSpectrogramAudioTransform()
+    wav = torch.from_numpy(synth.noise_waveform(batch, samples, seed=seed))
+    with torch.no_grad():
+        feats = [torch.log(tr.melspec(wav[i, :n]).T + tr.log_offset) for i, n in enumerate(lengths)]
+    (audio, audio_len), _ = generate_audio_text_batch([(f, torch.zeros(1, dtype=torch.long)) for f in feats])
+    model = AudioToAlignText(audio_size=64, encoder_settings=[list(r) for r in settings], decoder_num_layers=2,
+                             decoder_hidden_size=hidden, vocab_size=vocab)
+    load(model, synth.asr_v2_state_dict(64, settings, 2, hidden, vocab, seed=seed, randomize_ln=True, gain=2.0))
+    model.eval()
+    with torch.no_grad():
+        logits, logits_len = model(audio, audio_len)
+    np.savez_compressed(
+        os.path.join(OUT, f"{name}.npz"), logits=logits.numpy(), logits_len=logits_len.numpy(),
+        audio_len=audio_len.numpy(), lengths=np.asarray(lengths, np.int32),
+        cfg=np.asarray([64, hidden, vocab, batch, samples, seed], np.int64))
+    print(name, tuple(logits.shape), logits_len.tolist(), "logit std %.4f" % float(logits.std()),
+          "params", sum(p.numel() for p in model.parameters()))
+
+
+def gen_tts_v2(seed=51):
+    """TextToAlignText + AlignTextToAudio (voice100/models/_align_v2.py, _tts_v2.py; config/align_en_base.yaml,
+    config/tts_en_base.yaml)."""
+    from voice100.models._align_v2 import TextToAlignText
+    from voice100.models._tts_v2 import AlignTextToAudio
+    B, L, V = 3, 20, 29
+    text = torch.from_numpy(synth.text_tokens(B, L, V, seed=seed))
+    text_len = torch.tensor([20, 13, 7])
+    amodel = TextToAlignText(vocab_size=V, num_layers=2, hidden_size=256, num_outputs=2, learning_rate=1e-3)
+    load(amodel, synth.align_v2_state_dict(V, 2, 256, 2, seed=seed, gain=2.0))
+    amodel.eval()
+    with torch.no_grad():
+        pred, pred_len = amodel(text, text_len)
+    align = synth.synthetic_alignment(B, L, seed=seed)
+    ats = [amodel.align(text[i, :n], torch.from_numpy(align[i, :n])) for i, n in enumerate(text_len.tolist())]
+    aligntext = torch.nn.utils.rnn.pad_sequence(ats, batch_first=True, padding_value=0)
+    aligntext_len = torch.tensor([len(a) for a in ats])
+    vmodel = AlignTextToAudio(vocab_size=V, logspc_size=257, codeap_size=1, encoder_num_layers=2,
+                              encoder_hidden_size=512, decoder_settings=[list(r) for r in synth.TTS_V2_BASE_DECODER])
+    load(vmodel, synth.audio_v2_state_dict(V, seed=seed, randomize_ln=True, randomize_norm=True, gain=2.0))
+    vmodel.eval()
+    with torch.no_grad():
+        hasf0, f0_hat, logspc_hat, hascodeap, codeap_hat = vmodel(aligntext, aligntext_len)
+        f0, logspc, codeap = vmodel.predict(aligntext, aligntext_len)
+    np.savez_compressed(
+        os.path.join(OUT, "tts_v2_en_base.npz"),
+        align_pred=pred.numpy(), align_pred_len=pred_len.numpy(), text_len=text_len.numpy(),
+        aligntext=aligntext.numpy(), aligntext_len=aligntext_len.numpy(),
+        hasf0_logits=hasf0.numpy(), f0_hat=f0_hat.numpy(), hascodeap_logits=hascodeap.numpy(),
+        f0=f0.numpy(), logspc=logspc.numpy(), codeap=codeap.numpy(),
+        cfg=np.asarray([V, B, L, seed], np.int64))
+    print("tts_v2", tuple(pred.shape), tuple(aligntext.shape), aligntext_len.tolist(), tuple(logspc.shape),
+          "align params", sum(p.numel() for p in amodel.parameters()),
+          "audio params", sum(p.numel() for p in vmodel.parameters() if p.requires_grad))
+
+
 def viterbi_case(T, L, seed):
     from voice100_b200.synth import viterbi_inputs
     return viterbi_inputs(T, L, 29, seed)
@@ -163,3 +221,8 @@ if __name__ == "__main__":
     gen_asr("asr_ja_phone_ragged", hidden=128, embed=128, vocab=44, batch=3, samples=24000,
             lengths=[9000, 17777, 24000], seed=22)
     gen_tts()
+    gen_asr_v2("asr_v2_en_small_ragged", synth.ASR_V2_SMALL_ENCODER, 256, 29, batch=3, samples=24000,
+               lengths=[24000, 9000, 17777], seed=23)
+    gen_asr_v2("asr_v2_en_base", synth.ASR_V2_BASE_ENCODER, 512, 29, batch=2, samples=16000,
+               lengths=[16000, 16000], seed=24)
+    gen_tts_v2()

@@ -324,6 +324,124 @@ def audio_predict(aligntext: torch.Tensor, sd: SD):
 
 
 # ----------------------------------------------------------------------------------------------
+# v2 models: voice100/models/_layers_v2.py:29-103, _asr_v2.py:21-49, _align_v2.py:17-48, _tts_v2.py:13-91
+# ----------------------------------------------------------------------------------------------
+LN_EPS = 1e-5  # torch.nn.LayerNorm default (_layers_v2.py:40,71)
+
+
+def conv_layer_block(x: torch.Tensor, sd: SD, p: str, transpose: bool, stride: int, padding: int) -> torch.Tensor:
+    """ConvLayerBlock / ConvTransposeLayerBlock.forward on [B,C,T] (_layers_v2.py:51-57,82-88):
+    conv -> LayerNorm over channels -> exact (erf) GELU."""
+    w, b = sd[p + ".conv.weight"], sd.get(p + ".conv.bias")
+    x = (F.conv_transpose1d if transpose else F.conv1d)(x, w, b, stride=stride, padding=padding)
+    x = F.layer_norm(x.transpose(1, 2), (x.shape[1],), sd[p + ".layer_norm.weight"], sd[p + ".layer_norm.bias"],
+                     LN_EPS).transpose(1, 2)
+    return F.gelu(x)
+
+
+def conv_layers_v2(x: torch.Tensor, sd: SD, prefix: str, settings) -> torch.Tensor:
+    """get_conv_layers(...) as a function (_layers_v2.py:91-103)."""
+    for i, (_co, transpose, _k, stride, padding, _bias) in enumerate(settings):
+        x = conv_layer_block(x, sd, f"{prefix}.{i}", bool(transpose), stride, padding)
+    return x
+
+
+def lstm_bidirectional(x: torch.Tensor, lengths: Sequence[int], sd: SD, prefix: str, num_layers: int) -> torch.Tensor:
+    """torch.nn.LSTM(bidirectional=True) in eval mode over a packed batch, written out step by step
+    (the reference calls it through pack_padded_sequence/pad_packed_sequence: _asr_v2.py:45-47,
+    _align_v2.py:39-41, _tts_v2.py:56-58).  x [B,T,I] -> [B,T,2H]; every utterance runs over its own
+    length (the backward direction starts at its last valid step with zero state), rows past the
+    length are zero.  Gate order i, f, g, o; c' = f*c + i*g; h' = o*tanh(c')."""
+    B, T, _ = x.shape
+    lens = torch.as_tensor(list(lengths), dtype=torch.long)
+    inp = x
+    for layer in range(num_layers):
+        outs = []
+        for sfx in ("", "_reverse"):
+            w_ih, w_hh = sd[f"{prefix}.weight_ih_l{layer}{sfx}"], sd[f"{prefix}.weight_hh_l{layer}{sfx}"]
+            bias = sd[f"{prefix}.bias_ih_l{layer}{sfx}"] + sd[f"{prefix}.bias_hh_l{layer}{sfx}"]
+            H = w_hh.shape[1]
+            gx = inp @ w_ih.T + bias  # [B,T,4H]
+            h = torch.zeros(B, H, dtype=x.dtype)
+            c = torch.zeros(B, H, dtype=x.dtype)
+            out = torch.zeros(B, T, H, dtype=x.dtype)
+            steps = range(T - 1, -1, -1) if sfx else range(T)
+            for t in steps:
+                a = gx[:, t] + h @ w_hh.T
+                i, f, g, o = a[:, :H], a[:, H:2 * H], a[:, 2 * H:3 * H], a[:, 3 * H:]
+                c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+                h_new = torch.sigmoid(o) * torch.tanh(c_new)
+                live = (t < lens)[:, None]
+                c = torch.where(live, c_new, torch.zeros_like(c))
+                h = torch.where(live, h_new, torch.zeros_like(h))
+                out[:, t] = h
+            outs.append(out)
+        inp = torch.cat(outs, dim=2)
+    return inp
+
+
+def asr_v2_forward(audio: torch.Tensor, audio_len: Sequence[int], sd: SD, encoder_settings, num_layers=2):
+    """AudioToAlignText.forward (_asr_v2.py:39-49): audio [B,T,64] -> (logits [T', B, V] time-major,
+    lengths (audio_len+1)//2), T' = max length.  Padding frames take part in the convolutions exactly as
+    in the reference (no masking before the LSTM)."""
+    x = conv_layers_v2(audio.transpose(1, 2), sd, "encoder", encoder_settings).transpose(1, 2)
+    x_len = [(int(n) + 1) // 2 for n in audio_len]
+    x = lstm_bidirectional(x, x_len, sd, "lstm", num_layers)[:, :max(x_len)]
+    y = x @ sd["dense.weight"].T + sd["dense.bias"]
+    return y.transpose(0, 1).contiguous(), torch.as_tensor(x_len)
+
+
+def align_v2_forward(text: torch.Tensor, text_len: Sequence[int], sd: SD, num_layers=2):
+    """TextToAlignText.forward (_align_v2.py:29-43): text [B,L] -> ([B, max_len, 2], lengths)."""
+    x = F.embedding(text, sd["embedding.weight"])
+    x = lstm_bidirectional(x, text_len, sd, "lstm", num_layers)[:, :max(int(n) for n in text_len)]
+    return x @ sd["dense.weight"].T + sd["dense.bias"], torch.as_tensor([int(n) for n in text_len])
+
+
+def align_text_v2(text: Sequence[int], align: np.ndarray, head=5, tail=5) -> np.ndarray:
+    """TextToAlignText.align (_align_v2.py:54-82): truncating (int()) frame positions, a gap before every token
+    but the first, at least one blank frame between tokens, total head + int(sum(align) - align[0,0]) + tail."""
+    a = torch.as_tensor(np.asarray(align))
+    n = head + int(torch.sum(a) - a[0, 0]) + tail
+    out = np.zeros((n,), dtype=np.int64)
+    t, u = head, 0
+    for i in range(a.shape[0]):
+        if i > 0:
+            t += a[i, 0].item()
+        s = max(int(t), u)
+        u = s + 1
+        t += a[i, 1].item()
+        e = max(int(t), u)
+        u = e
+        out[s:e] = int(text[i])
+    return out
+
+
+def audio_v2_forward(aligntext: torch.Tensor, aligntext_len: Sequence[int], sd: SD, decoder_settings,
+                     num_layers=2, logspc_size=257, codeap_size=1):
+    """AlignTextToAudio.forward (_tts_v2.py:48-78) -> (hasf0_logits[B,T'], f0_hat[B,T'], logspc_hat[B,T',S],
+    hascodeap_logits[B,T',A], codeap_hat[B,T',A])."""
+    x = F.embedding(aligntext, sd["embedding.weight"])
+    x = lstm_bidirectional(x, aligntext_len, sd, "lstm", num_layers)[:, :max(int(n) for n in aligntext_len)]
+    x = conv_layers_v2(x.transpose(1, 2), sd, "decoder", decoder_settings).transpose(1, 2)
+    x = x @ sd["projection.weight"].T + sd["projection.bias"]
+    hasf0, f0, logspc, hascodeap, codeap = torch.split(x, [1, 1, logspc_size, codeap_size, codeap_size], dim=2)
+    return hasf0[:, :, 0], f0[:, :, 0], logspc, hascodeap, codeap
+
+
+def audio_v2_predict(aligntext, aligntext_len, sd: SD, decoder_settings, **kw):
+    """AlignTextToAudio.predict (_tts_v2.py:80-91): unnormalize (_layers_v2.py:199-206), f0 := 0 where
+    hasf0 < 0, codeap := 0 where hascodeap < 0."""
+    hasf0, f0, logspc, hascodeap, codeap = audio_v2_forward(aligntext, aligntext_len, sd, decoder_settings, **kw)
+    f0 = sd["norm.f0_std"] * f0 + sd["norm.f0_mean"]
+    logspc = sd["norm.logspc_std"] * logspc + sd["norm.logspc_mean"]
+    codeap = sd["norm.codeap_std"] * codeap + sd["norm.codeap_mean"]
+    f0 = torch.where(hasf0 < 0, torch.zeros((1,), dtype=f0.dtype), f0)
+    codeap = torch.where(hascodeap < 0, torch.zeros((1, 1), dtype=codeap.dtype), codeap)
+    return f0, logspc, codeap
+
+
+# ----------------------------------------------------------------------------------------------
 # Forced alignment: voice100/models/align.py:18-66 (ctc_best_path, max_move = 3), the per-utterance numpy DP
 # behind AudioToAlignText.ctc_best_path (voice100/models/_asr_v2.py:100-119)
 # ----------------------------------------------------------------------------------------------

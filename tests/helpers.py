@@ -41,3 +41,25 @@ def tts_case():
     text = torch.from_numpy(synth.text_tokens(B, L, V, seed=seed))
     align = synth.synthetic_alignment(B, L, seed=seed)
     return sd_a, sd_v, text, align, g
+
+
+def asr_v2_case(name):
+    """-> (state_dict, waveform, lengths, encoder settings, golden npz) for an AudioToAlignText fixture"""
+    g = golden(name)
+    audio_size, hidden, vocab, batch, samples, seed = [int(x) for x in g["cfg"]]
+    settings = synth.ASR_V2_BASE_ENCODER if hidden == 512 else synth.ASR_V2_SMALL_ENCODER
+    sd = {k: torch.from_numpy(v) for k, v in synth.asr_v2_state_dict(
+        audio_size, settings, 2, hidden, vocab, seed=seed, randomize_ln=True, gain=2.0).items()}
+    wav = torch.from_numpy(synth.noise_waveform(batch, samples, seed=seed))
+    return sd, wav, [int(x) for x in g["lengths"]], settings, g
+
+
+def tts_v2_case():
+    g = golden("tts_v2_en_base")
+    V, B, L, seed = [int(x) for x in g["cfg"]]
+    sd_a = {k: torch.from_numpy(v) for k, v in synth.align_v2_state_dict(V, 2, 256, 2, seed=seed, gain=2.0).items()}
+    sd_v = {k: torch.from_numpy(v) for k, v in synth.audio_v2_state_dict(
+        V, seed=seed, randomize_ln=True, randomize_norm=True, gain=2.0).items()}
+    text = torch.from_numpy(synth.text_tokens(B, L, V, seed=seed))
+    align = synth.synthetic_alignment(B, L, seed=seed)
+    return sd_a, sd_v, text, align, g

@@ -124,3 +124,66 @@ def test_viterbi_matches_reference():
         assert np.array_equal(path, g[f"c{ci}_path"]) and np.array_equal(best_labels, g[f"c{ci}_labels"])
         # structural properties of any valid alignment
         assert path[0] in (0, 1) and path[-1] in (2 * L - 1, 2 * L) and (np.diff(path) >= 0).all() and (np.diff(path) <= 2).all()
+
+
+# ---- v2 models (LayerNorm/GELU conv blocks + bidirectional LSTM) ----
+
+def _asr_v2(name):
+    from helpers import asr_v2_case
+    sd, wav, lengths, settings, g = asr_v2_case(name)
+    audio, audio_len = orc.logmel_batch(wav, lengths)
+    assert [int(x) for x in audio_len] == [int(x) for x in g["audio_len"]]
+    logits, out_len = orc.asr_v2_forward(audio, audio_len, sd, settings)
+    assert logits.shape == g["logits"].shape                      # [T', B, V], time-major (_asr_v2.py:47-49)
+    assert [int(x) for x in out_len] == [int(x) for x in g["logits_len"]]
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=5e-5)
+    return logits, out_len, g
+
+
+def test_asr_v2_small_ragged_matches_reference():
+    logits, out_len, g = _asr_v2("asr_v2_en_small_ragged")
+    # rows past an utterance's length are the LSTM's zero padding through the dense layer: the bias alone
+    from helpers import asr_v2_case
+    sd = asr_v2_case("asr_v2_en_small_ragged")[0]
+    np.testing.assert_allclose(logits[int(out_len[1]):, 1].numpy(),
+                               np.broadcast_to(sd["dense.bias"].numpy(), logits[int(out_len[1]):, 1].shape), atol=1e-6)
+
+
+def test_asr_v2_base_matches_reference():
+    _asr_v2("asr_v2_en_base")
+
+
+def test_v2_param_counts():
+    n = lambda sd: sum(v.size for k, v in sd.items() if not k.startswith("norm."))
+    assert n(synth.asr_v2_state_dict()) == 12_008_477              # printed by the reference modules (gen_golden.py)
+    assert n(synth.asr_v2_state_dict(64, synth.ASR_V2_SMALL_ENCODER, 2, 256, 29)) == 2_891_293
+    assert n(synth.align_v2_state_dict()) == 2_638_082
+    assert n(synth.audio_v2_state_dict()) == 15_896_837
+
+
+def test_tts_v2_matches_reference():
+    from helpers import tts_v2_case
+    sd_a, sd_v, text, align, g = tts_v2_case()
+    text_len = [int(x) for x in g["text_len"]]
+    pred, pred_len = orc.align_v2_forward(text, text_len, sd_a)
+    assert [int(x) for x in pred_len] == [int(x) for x in g["align_pred_len"]]
+    np.testing.assert_allclose(pred.numpy(), g["align_pred"], rtol=0, atol=5e-5)
+    ats = [orc.align_text_v2(text[i, :n].numpy(), align[i, :n]) for i, n in enumerate(text_len)]
+    assert [len(a) for a in ats] == [int(x) for x in g["aligntext_len"]]
+    for i, a in enumerate(ats):
+        np.testing.assert_array_equal(a, g["aligntext"][i, :len(a)])
+    aligntext = torch.from_numpy(g["aligntext"])
+    lens = [int(x) for x in g["aligntext_len"]]
+    hasf0, f0_hat, _logspc_hat, hascodeap, _codeap_hat = orc.audio_v2_forward(
+        aligntext, lens, sd_v, synth.TTS_V2_BASE_DECODER)
+    assert hasf0.shape == g["hasf0_logits"].shape == (3, 2 * max(lens) - 1)
+    np.testing.assert_allclose(hasf0.numpy(), g["hasf0_logits"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(f0_hat.numpy(), g["f0_hat"], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(hascodeap.numpy(), g["hascodeap_logits"], rtol=0, atol=1e-4)
+    f0, logspc, codeap = orc.audio_v2_predict(aligntext, lens, sd_v, synth.TTS_V2_BASE_DECODER)
+    # the sign of a near-zero voicing logit may flip between two fp32 summation orders: compare where it is decisive
+    sure = np.abs(g["hasf0_logits"]) > 1e-3
+    np.testing.assert_allclose(f0.numpy()[sure], g["f0"][sure], rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(logspc.numpy(), g["logspc"], rtol=0, atol=1e-3)
+    sure_c = np.abs(g["hascodeap_logits"]) > 1e-3
+    np.testing.assert_allclose(codeap.numpy()[sure_c], g["codeap"][sure_c], rtol=0, atol=1e-3)

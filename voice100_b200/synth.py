@@ -14,6 +14,9 @@ The `state_dict` key layout is the reference's own (probed by importing
   audio voice100/models/tts.py:13-29,152-170  embedding.weight, decoder.layers.{0-3,5-7}.conv.*,
                                          decoder.layers.4.* (ConvTranspose1d [C_in,C_out,5]),
                                          decoder.layers.8.*, norm.{f0,logspc,codeap}_{mean,std}
+  v2    voice100/models/_layers_v2.py:29-103, _asr_v2.py:31-37, _align_v2.py:18-27, _tts_v2.py:35-43
+                                         {encoder,decoder}.{i}.{conv,layer_norm}.*, lstm.{weight,bias}_{ih,hh}_l{n}[_reverse],
+                                         dense.* / projection.*, embedding.weight, norm.*
 """
 from __future__ import annotations
 
@@ -137,6 +140,99 @@ def audio_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=Fal
         sd["norm.logspc_mean"] = np.zeros((257,), np.float32)
         sd["norm.codeap_std"] = np.ones((1,), np.float32)
         sd["norm.codeap_mean"] = np.zeros((1,), np.float32)
+    return sd
+
+
+# ----------------------------------------------------------------------------
+# v2 models (LayerNorm + GELU conv blocks, bidirectional LSTM)
+# ----------------------------------------------------------------------------
+
+# config/asr_en_base.yaml:16-18, config/asr_en_small.yaml:16-18, config/tts_en_base.yaml:20-23
+# rows: (out_channels, transpose, kernel_size, stride, padding, bias)
+ASR_V2_BASE_ENCODER = ((512, False, 5, 2, 2, False), (512, False, 5, 1, 2, False))
+ASR_V2_SMALL_ENCODER = ((256, False, 3, 2, 1, False), (256, False, 3, 1, 1, False))
+TTS_V2_BASE_DECODER = ((512, False, 5, 1, 2, False), (512, True, 5, 2, 2, False), (512, False, 5, 1, 2, False))
+
+
+def _conv_layers_v2(sd, seed, prefix, in_channels, settings, randomize_ln, gain):
+    c = in_channels
+    for i, (co, transpose, k, _stride, _pad, bias) in enumerate(settings):
+        p = f"{prefix}.{i}"
+        if randomize_ln:
+            sd[p + ".layer_norm.weight"] = _uniform(seed, p + ".layer_norm.weight", (co,), 0.5, 1.5)
+            sd[p + ".layer_norm.bias"] = _uniform(seed, p + ".layer_norm.bias", (co,), -0.5, 0.5)
+        else:
+            sd[p + ".layer_norm.weight"] = np.ones((co,), np.float32)
+            sd[p + ".layer_norm.bias"] = np.zeros((co,), np.float32)
+        # Conv1d weight [C_out, C_in, k] (fan_in C_in*k); ConvTranspose1d weight [C_in, C_out, k] (fan_in C_out*k)
+        shape, fan_in = ((c, co, k), co * k) if transpose else ((co, c, k), c * k)
+        _conv(sd, seed, p + ".conv.weight", shape, fan_in, gain)
+        if bias:
+            _conv(sd, seed, p + ".conv.bias", (co,), fan_in, gain)
+        c = co
+    return c
+
+
+def _lstm(sd, seed, prefix, input_size, hidden_size, num_layers, gain):
+    # torch.nn.LSTM.reset_parameters: every tensor U(+-1/sqrt(hidden_size)); gate row order i, f, g, o
+    for layer in range(num_layers):
+        isz = input_size if layer == 0 else 2 * hidden_size
+        for sfx in ("", "_reverse"):
+            _conv(sd, seed, f"{prefix}.weight_ih_l{layer}{sfx}", (4 * hidden_size, isz), hidden_size, gain)
+            _conv(sd, seed, f"{prefix}.weight_hh_l{layer}{sfx}", (4 * hidden_size, hidden_size), hidden_size, gain)
+            _conv(sd, seed, f"{prefix}.bias_ih_l{layer}{sfx}", (4 * hidden_size,), hidden_size, gain)
+            _conv(sd, seed, f"{prefix}.bias_hh_l{layer}{sfx}", (4 * hidden_size,), hidden_size, gain)
+
+
+def asr_v2_state_dict(audio_size=64, encoder_settings=ASR_V2_BASE_ENCODER, decoder_num_layers=2,
+                      decoder_hidden_size=512, vocab_size=29, seed=1234, randomize_ln=False, gain=1.0):
+    """Weights for AudioToAlignText (voice100/models/_asr_v2.py:21-37)."""
+    sd: Dict[str, np.ndarray] = {}
+    c = _conv_layers_v2(sd, seed, "encoder", audio_size, encoder_settings, randomize_ln, gain)
+    assert c == decoder_hidden_size
+    _lstm(sd, seed, "lstm", decoder_hidden_size, decoder_hidden_size, decoder_num_layers, gain)
+    _conv(sd, seed, "dense.weight", (vocab_size, 2 * decoder_hidden_size), 2 * decoder_hidden_size, gain)
+    _conv(sd, seed, "dense.bias", (vocab_size,), 2 * decoder_hidden_size, gain)
+    return sd
+
+
+def align_v2_state_dict(vocab_size=29, num_layers=2, hidden_size=256, num_outputs=2, seed=1234, gain=1.0):
+    """Weights for TextToAlignText (voice100/models/_align_v2.py:17-27)."""
+    sd: Dict[str, np.ndarray] = {}
+    sd["embedding.weight"] = _rng(seed, "embedding.weight").standard_normal(
+        (vocab_size, hidden_size)).astype(np.float32)
+    _lstm(sd, seed, "lstm", hidden_size, hidden_size, num_layers, gain)
+    _conv(sd, seed, "dense.weight", (num_outputs, 2 * hidden_size), 2 * hidden_size, gain)
+    _conv(sd, seed, "dense.bias", (num_outputs,), 2 * hidden_size, gain)
+    return sd
+
+
+def audio_v2_state_dict(vocab_size=29, logspc_size=257, codeap_size=1, encoder_num_layers=2,
+                        encoder_hidden_size=512, decoder_settings=TTS_V2_BASE_DECODER, seed=1234,
+                        randomize_ln=False, randomize_norm=False, gain=1.0):
+    """Weights for AlignTextToAudio (voice100/models/_tts_v2.py:13-46)."""
+    sd: Dict[str, np.ndarray] = {}
+    sd["embedding.weight"] = _rng(seed, "embedding.weight").standard_normal(
+        (vocab_size, encoder_hidden_size)).astype(np.float32)
+    _lstm(sd, seed, "lstm", encoder_hidden_size, encoder_hidden_size, encoder_num_layers, gain)
+    c = _conv_layers_v2(sd, seed, "decoder", 2 * encoder_hidden_size, decoder_settings, randomize_ln, gain)
+    audio_size = 2 + logspc_size + 2 * codeap_size
+    _conv(sd, seed, "projection.weight", (audio_size, c), c, gain)
+    _conv(sd, seed, "projection.bias", (audio_size,), c, gain)
+    if randomize_norm:
+        sd["norm.f0_std"] = _uniform(seed, "norm.f0_std", (1,), 20.0, 60.0)
+        sd["norm.f0_mean"] = _uniform(seed, "norm.f0_mean", (1,), 100.0, 200.0)
+        sd["norm.logspc_std"] = _uniform(seed, "norm.logspc_std", (logspc_size,), 0.5, 2.0)
+        sd["norm.logspc_mean"] = _uniform(seed, "norm.logspc_mean", (logspc_size,), -8.0, -2.0)
+        sd["norm.codeap_std"] = _uniform(seed, "norm.codeap_std", (codeap_size,), 0.5, 2.0)
+        sd["norm.codeap_mean"] = _uniform(seed, "norm.codeap_mean", (codeap_size,), -3.0, 0.0)
+    else:
+        sd["norm.f0_std"] = np.ones((1,), np.float32)
+        sd["norm.f0_mean"] = np.zeros((1,), np.float32)
+        sd["norm.logspc_std"] = np.ones((logspc_size,), np.float32)
+        sd["norm.logspc_mean"] = np.zeros((logspc_size,), np.float32)
+        sd["norm.codeap_std"] = np.ones((codeap_size,), np.float32)
+        sd["norm.codeap_mean"] = np.zeros((codeap_size,), np.float32)
     return sd
 
 
