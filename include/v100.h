@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 2
+#define V100_ABI_VERSION 3
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
@@ -183,6 +183,56 @@ int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, 
 
 /* fp32 NCW [B][C][pitch] -> fp32 [B][T][C] (align head output [B][L][2]). */
 int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * v2 models: ConvLayerBlock / ConvTransposeLayerBlock (voice100/models/_layers_v2.py:29-88) and the
+ * bidirectional LSTM stacks of AudioToAlignText (_asr_v2.py:31-49), TextToAlignText (_align_v2.py:22-43)
+ * and AlignTextToAudio (_tts_v2.py:35-60).
+ *
+ * Time-major layout ("TM") used around the recurrent layers: x[c][t * Bp + b], 16-bit, Bp = batch rounded up
+ * to a multiple of 8.  A TM tensor is also a valid NCW tensor with B = 1, T = pitch = T * Bp, so the LSTM input
+ * projection (weight_ih, bias_ih + bias_hh) and the dense heads are plain v100_conv1x1 / v100_conv1x1_f32out
+ * calls on it.
+ * ------------------------------------------------------------------------------------------------ */
+
+/*
+ * nn.Conv1d(C_in, C_out, k, stride, padding) of ConvLayerBlock (_layers_v2.py:41-48,52), dense (groups = 1):
+ * y[b][co][to] = bias[co] + sum_{ci,j} Wp[co][j*C_in + ci] * x[b][ci][to*stride + j - pad], zero padded,
+ * T_out = (T_in + 2*pad - k)/stride + 1.  Wp is the weight re-packed tap-major ([C_out][k*C_in]); bias fp32 [C_out]
+ * (zeros when the layer has none).  k in {3,5}, stride in {1,2}, (k*C_in) % 8 == 0.
+ * workspace: 16-bit [B][k*C_in][y_pitch] (the k shifted/strided views stacked along channels; TMA needs
+ * 16-byte aligned box offsets, so tap shifts are materialised once and the conv becomes one GEMM).
+ */
+int v100_conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
+                void* y, int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad,
+                int dtype, void* stream);
+
+/*
+ * transpose -> nn.LayerNorm(C) -> transpose -> gelu of ConvLayerBlock.forward (_layers_v2.py:53-57,84-88):
+ * per (b, t) column, y = gelu((x - mean_c) * rsqrt(var_c + eps) * gamma[c] + beta[c]), biased variance,
+ * exact (erf) GELU.  NCW in, NCW out (x and y may alias), statistics in fp32.
+ */
+int v100_layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const float* beta, float eps,
+                        void* y, int64_t y_pitch, int B, int C, int T, int dtype, void* stream);
+
+/* NCW 16-bit [B][C][pitch] -> TM [C][T*Bp] (columns b in [B,Bp) zero) and back.
+ * Replace the transposes + pack_padded_sequence / pad_packed_sequence around nn.LSTM (_asr_v2.py:44-47). */
+int v100_ncw_to_tm(const void* x, int64_t x_pitch, void* y, int B, int C, int T, int Bp, void* stream);
+int v100_tm_to_ncw(const void* x, void* y, int64_t y_pitch, int B, int C, int T, int Bp, void* stream);
+
+/*
+ * One bidirectional nn.LSTM layer in eval mode over a packed batch (_asr_v2.py:33-35,46; gate order i,f,g,o).
+ * gx:  TM 16-bit [8H][T*Bp] = W_ih x + b_ih + b_hh for every step; rows [0,4H) forward, [4H,8H) reverse
+ * w_hh: 16-bit [2][4H][H] (weight_hh_l{n}, weight_hh_l{n}_reverse)
+ * lengths: int32 [B]; utterance b runs over steps [0, lengths[b]) (reverse direction starts at its last step
+ *          with zero state), outputs past the length are zero (pad_packed_sequence)
+ * y:   TM 16-bit [2H][T*Bp], rows [0,H) forward, [H,2H) reverse (= the concatenated nn.LSTM output)
+ * workspace: v100_lstm_workspace_bytes(B, H) bytes, 1024-byte aligned (h exchange buffers + step counters)
+ * H a multiple of 64, <= 512.  Cell state fp32, h rounded to the storage type each step.
+ */
+int64_t v100_lstm_workspace_bytes(int B, int H);
+int v100_lstm_layer(const void* gx, const void* w_hh, const int32_t* lengths, void* y, void* workspace,
+                    int B, int Bp, int T, int H, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

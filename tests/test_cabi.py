@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     src = open(os.path.join(ROOT, "include", "v100.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    decls = re.findall(r"\b(?:int|const char\*)\s+(v100_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
+    decls = re.findall(r"\b(?:int|int64_t|const char\*)\s+(v100_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S)
     return {name: [a.strip() for a in args.split(",")] if args.strip() != "void" else [] for name, args in decls}
 
 
@@ -35,7 +35,7 @@ def test_library_loads_and_exports_header_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (v100_\w+)", out))
     assert exported == set(funcs), exported ^ set(funcs)
-    assert _lib.lib().v100_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().v100_abi_version() == _lib.ABI_VERSION == 3
 
 
 def test_ctypes_table_matches_header():
@@ -52,7 +52,7 @@ def test_ctypes_table_matches_header():
                 assert ct is ctypes.c_float, (name, decl)
             else:
                 assert ct is ctypes.c_int, (name, decl)
-    assert set(funcs) - set(_lib.SIGNATURES) == {"v100_last_error"}
+    assert set(funcs) - set(_lib.SIGNATURES) == {"v100_last_error", "v100_lstm_workspace_bytes"}
 
 
 def test_product_never_imports_oracle():
@@ -71,6 +71,11 @@ def test_no_cpu_fallback():
         v.MelSpectrogramAudioTransform().melspec(torch.zeros(1000))
     with pytest.raises(v.V100Error):
         v.TextToAlignTextModel(29, 64)(torch.zeros(1, 5, dtype=torch.long))
+    with pytest.raises(v.V100Error):
+        v.AudioToAlignText(64, [list(r) for r in synth.ASR_V2_SMALL_ENCODER], 2, 256, 29)(
+            torch.zeros(1, 50, 64), torch.tensor([50]))
+    with pytest.raises(v.V100Error):
+        v.TextToAlignText(29, 2, 64, 2)(torch.zeros(1, 5, dtype=torch.long), torch.tensor([5]))
     m.train()
     with pytest.raises(v.V100Error):
         m(torch.zeros(1, 50, 64))
@@ -84,6 +89,27 @@ def test_state_dict_layout_matches_reference_keys():
         for k, t in model.state_dict().items():
             assert tuple(t.shape) == tuple(sd[k].shape), k
         model.load_state_dict({k: torch.from_numpy(np.asarray(x)) for k, x in sd.items()})
+
+
+def test_v2_state_dict_layout_matches_reference_keys():
+    small = [list(r) for r in synth.ASR_V2_SMALL_ENCODER]
+    dec = [list(r) for r in synth.TTS_V2_BASE_DECODER]
+    for model, sd in ((v.AudioToAlignText(64, small, 2, 256, 29), synth.asr_v2_state_dict(64, small, 2, 256, 29)),
+                      (v.TextToAlignText(29, 2, 64, 2), synth.align_v2_state_dict(29, 2, 64, 2)),
+                      (v.AlignTextToAudio(29, 257, 1, 2, 64, dec), synth.audio_v2_state_dict(29, 257, 1, 2, 64, dec))):
+        assert set(model.state_dict().keys()) == set(sd.keys())
+        for k, t in model.state_dict().items():
+            assert tuple(t.shape) == tuple(sd[k].shape), k
+        model.load_state_dict({k: torch.from_numpy(np.asarray(x)) for k, x in sd.items()})
+
+
+def test_align_v2_host_function_matches_oracle():
+    import v100_oracle as orc
+    text = torch.from_numpy(synth.text_tokens(3, 17, seed=5))
+    align = synth.synthetic_alignment(3, 17, seed=5)
+    for i in range(3):
+        got = v.TextToAlignText.align(text[i], torch.from_numpy(align[i]))
+        assert got.tolist() == orc.align_text_v2(text[i].tolist(), align[i]).tolist()
 
 
 def test_align_host_function_matches_oracle():

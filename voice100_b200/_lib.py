@@ -30,9 +30,14 @@ SIGNATURES = {
     "v100_ctc_best_path": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
+    "v100_conv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "v100_layernorm_gelu": [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _i, _p],
+    "v100_ncw_to_tm": [_p, _l, _p, _i, _i, _i, _i, _p],
+    "v100_tm_to_ncw": [_p, _p, _l, _i, _i, _i, _i, _p],
+    "v100_lstm_layer": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 
@@ -52,6 +57,8 @@ def lib():
             fn = getattr(handle, name)
             fn.argtypes = argtypes
             fn.restype = _i
+        handle.v100_lstm_workspace_bytes.argtypes = [_i, _i]
+        handle.v100_lstm_workspace_bytes.restype = _l
         handle.v100_last_error.argtypes = []
         handle.v100_last_error.restype = C.c_char_p
         if handle.v100_abi_version() != ABI_VERSION:
@@ -64,6 +71,7 @@ def lib():
 # builds its shifted channel stack)
 KERNELS_PER_CALL = {name: 1 for name in SIGNATURES}
 KERNELS_PER_CALL["v100_convtranspose1d_k5s2"] = 2
+KERNELS_PER_CALL["v100_conv1d"] = 2   # tap stacking + GEMM
 KERNELS_PER_CALL["v100_abi_version"] = 0
 
 stats = {"launches": 0}

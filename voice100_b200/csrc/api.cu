@@ -47,12 +47,13 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* m, CUtensorMapDataType type, const void* base, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box) {
+                  const cuuint64_t* strides, const cuuint32_t* box,
+                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t ones[3] = {1, 1, 1};
   CUresult r = fn(m, type, rank, const_cast<void*>(base), dims, strides, box, ones,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu strides %llu)",
@@ -66,6 +67,13 @@ int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int
   const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
   const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
   return encode(m, type, base, 2, dims, strides, box);
+}
+
+int make_tmap_2d_plain(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1) {
+  const cuuint64_t dims[2] = {cuuint64_t(d0), cuuint64_t(d1)};
+  const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
+  const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
+  return encode(m, type, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
@@ -163,6 +171,33 @@ int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, 
 
 int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream) {
   return ncw_f32_to_ntc(y_ncw, y_pitch, out, B, C, T, STREAM(stream));
+}
+
+int v100_conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
+                int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad, int dtype,
+                void* stream) {
+  return conv1d(x, x_pitch, Wp, bias, workspace, y, y_pitch, B, C_in, C_out, T_in, k, stride, pad, dtype,
+                STREAM(stream));
+}
+
+int v100_layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const float* beta, float eps, void* y,
+                        int64_t y_pitch, int B, int C, int T, int dtype, void* stream) {
+  return layernorm_gelu(x, x_pitch, gamma, beta, eps, y, y_pitch, B, C, T, dtype, STREAM(stream));
+}
+
+int v100_ncw_to_tm(const void* x, int64_t x_pitch, void* y, int B, int C, int T, int Bp, void* stream) {
+  return ncw_to_tm(x, x_pitch, y, B, C, T, Bp, STREAM(stream));
+}
+
+int v100_tm_to_ncw(const void* x, void* y, int64_t y_pitch, int B, int C, int T, int Bp, void* stream) {
+  return tm_to_ncw(x, y, y_pitch, B, C, T, Bp, STREAM(stream));
+}
+
+int64_t v100_lstm_workspace_bytes(int B, int H) { return static_cast<int64_t>(lstm_workspace_bytes(B, H)); }
+
+int v100_lstm_layer(const void* gx, const void* w_hh, const int32_t* lengths, void* y, void* workspace, int B,
+                    int Bp, int T, int H, int dtype, void* stream) {
+  return lstm_layer(gx, w_hh, lengths, y, workspace, B, Bp, T, H, dtype, STREAM(stream));
 }
 
 }  // extern "C"

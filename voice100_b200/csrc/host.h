@@ -23,6 +23,8 @@ int num_sms();
 
 // 16-bit tensor maps, 128-byte swizzle, zero fill out of bounds.  Dimensions innermost first.
 int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
+// same, without swizzle (rows land in shared memory as plain row-major lines)
+int make_tmap_2d_plain(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
                  int64_t stride2_bytes, int box0, int box1);
 
@@ -53,5 +55,17 @@ int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t*
 int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0, float* f0,
                    float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream);
 int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream);
+
+// v2 models (seq.cu)
+int conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
+           int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad, int dtype,
+           cudaStream_t stream);
+int layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const float* beta, float eps, void* y,
+                   int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream);
+int ncw_to_tm(const void* x, int64_t x_pitch, void* y, int B, int C, int T, int Bp, cudaStream_t stream);
+int tm_to_ncw(const void* x, void* y, int64_t y_pitch, int B, int C, int T, int Bp, cudaStream_t stream);
+size_t lstm_workspace_bytes(int B, int H);
+int lstm_layer(const void* gx, const void* w_hh, const int32_t* lengths, void* y, void* workspace, int B, int Bp,
+               int T, int H, int dtype, cudaStream_t stream);
 
 }  // namespace v100

@@ -220,3 +220,75 @@ def ncw_f32_to_ntc(y: Ncw) -> torch.Tensor:
     out = torch.empty((y.B, y.T, y.C), device=y.data.device, dtype=torch.float32)
     _lib.call("v100_ncw_f32_to_ntc", y.data.data_ptr(), y.pitch, out.data_ptr(), y.B, y.C, y.T, _stream())
     return out
+
+
+# ---- v2 models: dense conv + LayerNorm/GELU, time-major layout, LSTM (include/v100.h, "v2 models") ----
+
+def conv1d(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor, k: int, stride: int, pad: int) -> Ncw:
+    """Dense Conv1d; Wp is the tap-major packed weight [C_out, k*C_in]."""
+    C_out = Wp.shape[0]
+    assert Wp.shape[1] == k * x.C and Wp.dtype == x.data.dtype
+    T_out = (x.T + 2 * pad - k) // stride + 1
+    y = empty_ncw(x.B, C_out, T_out, x.data.device, x.data.dtype)
+    ws = torch.empty((x.B, k * x.C, y.pitch), device=x.data.device, dtype=x.data.dtype)
+    _lib.call("v100_conv1d", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(), ws.data_ptr(),
+              y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, k, stride, pad, dt(x.data), _stream())
+    return y
+
+
+def layernorm_gelu(x: Ncw, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> Ncw:
+    """LayerNorm over channels + GELU(erf), in place."""
+    _lib.call("v100_layernorm_gelu", x.data.data_ptr(), x.pitch, gamma.data_ptr(), beta.data_ptr(), float(eps),
+              x.data.data_ptr(), x.pitch, x.B, x.C, x.T, dt(x.data), _stream())
+    return x
+
+
+@dataclass
+class Tm:
+    """Time-major activations: data [C, T*Bp] with column t*Bp + b; also a 1-utterance Ncw of T*Bp columns."""
+    data: torch.Tensor
+    B: int
+    T: int
+    Bp: int
+
+    @property
+    def C(self):
+        return self.data.shape[0]
+
+    def as_ncw(self) -> Ncw:
+        return Ncw(self.data.view(1, self.data.shape[0], self.data.shape[1]), self.T * self.Bp)
+
+
+def ncw_to_tm(x: Ncw) -> Tm:
+    Bp = pitch_of(x.B)
+    y = torch.empty((x.C, x.T * Bp), device=x.data.device, dtype=x.data.dtype)
+    _lib.call("v100_ncw_to_tm", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, Bp, _stream())
+    return Tm(y, x.B, x.T, Bp)
+
+
+def tm_to_ncw(x: Tm) -> Ncw:
+    y = empty_ncw(x.B, x.C, x.T, x.data.device, x.data.dtype)
+    _lib.call("v100_tm_to_ncw", x.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, x.Bp, _stream())
+    return y
+
+
+def lstm_workspace(B: int, H: int, device) -> torch.Tensor:
+    n = int(_lib.lib().v100_lstm_workspace_bytes(B, H))
+    ws = torch.empty((n + 1024,), device=device, dtype=torch.uint8)
+    off = (-ws.data_ptr()) % 1024
+    return ws[off:off + n]
+
+
+def lstm_layer(x: Tm, w_ih: torch.Tensor, bias: torch.Tensor, w_hh: torch.Tensor, lengths: torch.Tensor,
+               workspace: torch.Tensor = None) -> Tm:
+    """One bidirectional layer: w_ih [8H, I] (forward rows first), bias fp32 [8H] = b_ih + b_hh, w_hh [2, 4H, H],
+    lengths int32 [B] on the device."""
+    H = w_hh.shape[2]
+    assert w_ih.shape == (8 * H, x.C) and w_hh.shape == (2, 4 * H, H) and w_ih.dtype == w_hh.dtype == x.data.dtype
+    _cuda(lengths, torch.int32)
+    gx = conv1x1(x.as_ncw(), w_ih, None, bias, ACT_NONE)           # [1, 8H, T*Bp]: every step's input projection
+    y = torch.empty((2 * H, x.T * x.Bp), device=x.data.device, dtype=x.data.dtype)
+    ws = workspace if workspace is not None else lstm_workspace(x.B, H, x.data.device)
+    _lib.call("v100_lstm_layer", gx.data.data_ptr(), w_hh.data_ptr(), lengths.data_ptr(), y.data_ptr(),
+              ws.data_ptr(), x.B, x.Bp, x.T, H, dt(x.data), _stream())
+    return Tm(y, x.B, x.T, x.Bp)
