@@ -256,6 +256,89 @@ def run_tts(args):
         "gpu_launches": launches * K, "gpu_launches_per_step": launches}))
 
 
+def run_asr_v2(args):
+    """Secondary workload: the architecture of the reference's shipped asr_en_base.yaml (AudioToAlignText: two
+    LayerNorm/GELU conv blocks -> 2-layer biLSTM(512) -> Linear) on the headline input shape, B x 15 s clips.
+    Same metric as the headline (audio-seconds per second); not the number BASELINE.json quotes."""
+    import numpy as np
+    import torch
+    import voice100_b200 as v
+    from voice100_b200 import _lib, synth
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, L = args.batch, SAMPLE_RATE * CLIP_SECONDS
+    dtype = torch.float16 if args.dtype == "f16" else torch.bfloat16
+    settings = [list(r) for r in synth.ASR_V2_BASE_ENCODER]
+    model = v.AudioToAlignText(64, settings, 2, 512, args.vocab)
+    model.load_state_dict({k: torch.from_numpy(np.asarray(t)) for k, t in
+                           synth.asr_v2_state_dict(64, synth.ASR_V2_BASE_ENCODER, 2, 512, args.vocab, seed=1234).items()})
+    model = model.to(dev).eval().set_storage_dtype(dtype)
+    tr = v.MelSpectrogramAudioTransform().to(dev)
+    pipe = v.AsrV2Pipeline(tr, model)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    wavs = [0.1 * torch.randn((B, L), device=dev, generator=g) for _ in range(2)]   # 2 x 15 MB > nothing; see config
+    if args.ragged:
+        lengths = torch.from_numpy(synth.ragged_lengths(B, 2 * SAMPLE_RATE, L, seed=1234)).to(dev)
+    else:
+        lengths = torch.full((B,), L, dtype=torch.int32, device=dev)
+    audio_seconds = float(lengths.double().sum()) / SAMPLE_RATE
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for i in range(W):
+        pipe(wavs[i & 1], lengths)
+    torch.cuda.synchronize()
+    n0 = _lib.stats["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        tokens, out_len = pipe(wavs[i & 1], lengths)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = (_lib.stats["launches"] - n0) // K
+
+    class Tracer:
+        def __init__(self):
+            self.ev = []
+
+        def before(self, name):
+            self._s = torch.cuda.Event(enable_timing=True)
+            self._s.record()
+
+        def after(self, name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.ev.append((name, self._s, e))
+
+    _lib.tracer = Tracer()
+    pipe(wavs[0], lengths)
+    torch.cuda.synchronize()
+    ev, _lib.tracer = _lib.tracer.ev, None
+    launch_ms = [[name.replace("v100_", ""), round(s.elapsed_time(e), 4)] for name, s, e in ev]
+    # end to end: pinned host waveforms in, host tokens out
+    wav_h = wavs[0].cpu().pin_memory()
+    len_h = lengths.cpu().pin_memory()
+    Ke = max(2, min(K, 5))
+    tok_h = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        tk, _ = pipe(wav_h.to(dev, non_blocking=True), len_h.to(dev, non_blocking=True))
+        tok_h.copy_(tk, non_blocking=True)
+        torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / Ke
+    print(json.dumps({
+        "metric": "asr_audio_seconds_per_second", "value": round(audio_seconds / (ms * 1e-3), 1), "unit": "audio-s/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"asr_en_base v2 (config/asr_en_base.yaml): log-mel + AudioToAlignText(conv k5 x2, "
+                               f"biLSTM 2x512, V={args.vocab}) + argmax, {B} x {CLIP_SECONDS} s clips"
+                               + (", ragged U[2 s,15 s]" if args.ragged else ""),
+                   "l2": "two input batches alternate; every step streams > 1 GB of activations (> L2)"},
+        "e2e": {"value": round(audio_seconds / dt, 1), "unit": "audio-s/s",
+                "h2d_bytes_per_step": int(wav_h.numel() * 4 + len_h.numel() * 4),
+                "d2h_bytes_per_step": int(tok_h.numel() * 8)},
+        "gpu_launches": launches * K, "gpu_launches_per_step": launches, "launch_ms": launch_ms}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -270,12 +353,14 @@ def main():
                     help="BASELINE.json configs[4]: clip lengths U[2 s, 15 s] padded to the batch maximum (audio-seconds "
                          "then count valid samples only); the default is the metric's fixed 15 s clips")
     ap.add_argument("--vocab", type=int, default=MODEL["vocab_size"], help="44 = asr_ja_phone_base")
-    ap.add_argument("--workload", default="asr", choices=["asr", "tts"], help="asr = the headline metric")
+    ap.add_argument("--workload", default="asr", choices=["asr", "tts", "asr_v2"], help="asr = the headline metric")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "tts":
         return run_tts(args)
+    if args.workload == "asr_v2":
+        return run_asr_v2(args)
 
     import numpy as np
     import torch

@@ -89,8 +89,8 @@ def _lstm_case(B, T, I, H, lengths, seed, dtype=torch.bfloat16):
 # STATED TOLERANCE for one LSTM layer (|h| <= 1): the input projection and every h_t are rounded to the
 # storage type (bf16: 2^-9 relative) and the gates use tanh.approx (2^-11); the recurrence damps old errors
 # through the forget gate, so the error stays a small multiple of one rounding step.
-LSTM_MAX_ABS = {torch.bfloat16: 0.03, torch.float16: 0.006}
-LSTM_RMS = {torch.bfloat16: 0.004, torch.float16: 0.001}
+LSTM_MAX_ABS = {torch.bfloat16: 0.01, torch.float16: 0.002}
+LSTM_RMS = {torch.bfloat16: 0.0015, torch.float16: 0.0003}
 
 
 @pytest.mark.parametrize("B,T,I,H,ragged", [(3, 20, 64, 64, True), (5, 37, 128, 256, True), (130, 12, 64, 128, True),
@@ -136,8 +136,8 @@ def test_v2_argument_errors():
 # ---------------------------------------------------------------- models vs the reference's golden vectors
 
 # STATED TOLERANCES (bf16 storage vs the fp32 reference), as fractions of the output's standard deviation.
-V2_LOGIT_MAX_REL_STD = 0.25
-V2_LOGIT_RMS_REL_STD = 0.05
+V2_LOGIT_MAX_REL_STD = 0.10
+V2_LOGIT_RMS_REL_STD = 0.025
 
 
 def _load(model, sd):

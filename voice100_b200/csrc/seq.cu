@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <cstdlib>
+
 namespace v100 {
 
 // ------------------------------------------------------------------------------------------------
@@ -95,6 +97,7 @@ layernorm_gelu_kernel(const uint32_t* __restrict__ x, long long x_pitch, const f
   const bool live = t0 + 2 * lane < x_pitch;
   const uint32_t* xb = x + static_cast<long long>(b) * C * (x_pitch >> 1);
   float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll 8
   for (int c = w; c < C; c += 8) {
     const uint32_t v = live ? __ldg(xb + c * (x_pitch >> 1) + xcol) : 0u;
     ln_tile[c * 32 + lane] = v;
@@ -133,6 +136,7 @@ layernorm_gelu_kernel(const uint32_t* __restrict__ x, long long x_pitch, const f
   const float r0 = stat[1][2 * lane], r1 = stat[1][2 * lane + 1];
   if (t0 + 2 * lane >= y_pitch) return;
   uint32_t* yb = y + static_cast<long long>(b) * C * (y_pitch >> 1) + xcol;
+#pragma unroll 4
   for (int c = w; c < C; c += 8) {
     const uint32_t v = ln_tile[c * 32 + lane];
     const float g = __ldg(gamma + c), be = __ldg(beta + c);
@@ -243,6 +247,7 @@ struct LstmParams {
   unsigned short* hx;     // exchange buffer [2 dirs][groups_total][2][128][H]
   unsigned int* counters; // [2 dirs][groups_total]
   int dtype;
+  int cluster;            // CTAs per cluster (consecutive slices of one (direction, group)); 1 = no multicast
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -263,6 +268,31 @@ __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned in
 // generic-proxy global writes <-> async-proxy (TMA) global reads
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+// TMA load delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of
+// every CTA in `mask` of this cluster
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+
+#ifdef V100_LSTM_PROF
+// profiling build only (tools/lstm_prof.py): globaltimer stamps of block 0 for a few steps
+__device__ unsigned long long g_lstm_prof[64 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define LSTM_STAMP(step, slot) \
+  do { if (blockIdx.x == 0 && (step) >= 100 && (step) < 164) g_lstm_prof[((step) - 100) * 8 + (slot)] = gtime(); } while (0)
+#else
+#define LSTM_STAMP(step, slot) do {} while (0)
+#endif
+
 template <int DT>
 __global__ void __launch_bounds__(kLstmThreads, 1)
 lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_constant__ CUtensorMap tm_w,
@@ -274,11 +304,11 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
   uint8_t* sW = sA + KB * 16384;                        // W slice: KB x [64 rows x 64 k] (8 KB each)
   unsigned short* sG = reinterpret_cast<unsigned short*>(sW + KB * 8192);  // 2 x [64 gate rows][128 utterances]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sG) + 2 * kLstmN * kLstmRows * 2);
-  uint64_t* h_full = bars;        // [1]
-  uint64_t* acc_full = bars + 1;  // [1]
-  uint64_t* gx_full = bars + 2;   // [2]
-  uint64_t* w_full = bars + 4;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* h_full = bars;         // [8] one per 64-wide k block of the h tile
+  uint64_t* acc_full = bars + 8;   // [1]
+  uint64_t* gx_full = bars + 9;    // [2]
+  uint64_t* w_full = bars + 11;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x % p.slices;
@@ -304,7 +334,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
     tma_prefetch_desc(&tm_gx);
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_h);
-    mbar_init(h_full, 1);
+    for (int kb = 0; kb < 8; ++kb) mbar_init(&h_full[kb], 1);
     mbar_init(acc_full, 1);
     mbar_init(&gx_full[0], 1);
     mbar_init(&gx_full[1], 1);
@@ -316,9 +346,12 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  // peers multicast into this CTA's shared memory and signal its barriers: they must be initialised first
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = p.cluster > 1 ? int(cluster_ctarank()) : 0;
+  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   if (warp == 4) {
     if (lane == 0) {
@@ -341,6 +374,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
       for (int k = 1; k < p.T; ++k) {
         // every slice of this (direction, group) has published h of step k-1
         const unsigned int need = unsigned(k) * per_step;
+        LSTM_STAMP(k, 0);
         if (ld_acquire_u32(counter) < need) {
           const long long t_start = clock64();
           while (ld_acquire_u32(counter) < need) {
@@ -351,15 +385,21 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
             }
           }
         }
+        LSTM_STAMP(k, 1);
         fence_proxy_async_global();
         // the gate warps of this CTA are past step k-1 as well: their Gx buffer (k+1)&1 is free again
         if (k + 1 < p.T) load_gx(k + 1);
-        mbar_expect_tx(h_full, uint32_t(kLstmRows) * p.H * 2);
+        // h_{k-1} of the group: the CTAs of a cluster are slices of the same (direction, group) and all passed
+        // the same counter, so each loads 1/cluster of the tile and multicasts it to every peer
         const int hrow = hx_row0 + ((k - 1) & 1) * kLstmRows;
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * 16384, &tm_h, h_full, kb * 64, hrow);
-        mbar_wait(h_full, (k - 1) & 1);
-        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) mbar_expect_tx(&h_full[kb], 16384);
+        for (int kb = crank; kb < KB; kb += p.cluster) {
+          if (p.cluster > 1) tma_load_2d_mc(sA + kb * 16384, &tm_h, &h_full[kb], kb * 64, hrow, cmask);
+          else tma_load_2d(sA + kb * 16384, &tm_h, &h_full[kb], kb * 64, hrow);
+        }
         for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&h_full[kb], (k - 1) & 1);
+          tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = umma_desc(a_addr + kb * 16384 + kk * 32, 16, 1024);
@@ -368,6 +408,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
           }
         }
         umma_commit(acc_full);
+        LSTM_STAMP(k, 2);
       }
     }
   } else {
@@ -389,6 +430,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
         tmem_ld32(lane_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(acc + 32));
         tmem_ld_wait();
         tc_fence_before();
+        if (threadIdx.x == 0) LSTM_STAMP(k, 3);
       } else {
 #pragma unroll
         for (int i = 0; i < kLstmN; ++i) acc[i] = 0u;
@@ -415,10 +457,15 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
       uint4* hdst = reinterpret_cast<uint4*>(p.hx + (static_cast<long long>(hx_row0 + (k & 1) * kLstmRows + row)) * p.H + u0);
       hdst[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       hdst[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+      // publish: every thread orders its stores against the async proxy (the consumers read them with TMA),
+      // the barrier collects the four warps, one release-add makes the whole tile visible (cumulativity)
+      if (threadIdx.x == 0) LSTM_STAMP(k, 4);
       fence_proxy_async_global();
-      __threadfence();
+      if (threadIdx.x == 0) LSTM_STAMP(k, 5);
       named_bar_sync(1, 128);
+      if (threadIdx.x == 0) LSTM_STAMP(k, 6);
       if (threadIdx.x == 0) red_release_add_u32(counter, 1u);
+      if (threadIdx.x == 0) LSTM_STAMP(k, 7);
       // layer output (off the critical path): y[dir*H + u0 + u][t*Bp + b]
       if (b < p.Bp) {
         unsigned short* yp = p.y + (static_cast<long long>(dir) * p.H + u0) * p.n_cols + static_cast<long long>(t) * p.Bp + b;
@@ -430,12 +477,19 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its shared memory
+  if (p.cluster > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kLstmN);
   }
 }
+
+#ifdef V100_LSTM_PROF
+extern "C" int v100_debug_lstm_prof(unsigned long long* out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(out, g_lstm_prof, sizeof(g_lstm_prof)));
+}
+#endif
 
 size_t lstm_workspace_bytes(int B, int H) {
   const size_t groups = (size_t(B) + kLstmRows - 1) / kLstmRows;
@@ -469,17 +523,43 @@ int lstm_layer(const void* gx, const void* w_hh, const int32_t* lengths, void* y
   if (int e = make_tmap_2d(&tm_w, tt, w_hh, H, int64_t(8) * H, int64_t(H) * 2, 64, kLstmUnits)) return e;
   if (int e = make_tmap_2d(&tm_h, tt, workspace, H, int64_t(2) * p.groups_total * 2 * kLstmRows, int64_t(H) * 2, 64, kLstmRows)) return e;
   const int KB = H / 64;
-  const size_t smem = 1024 + size_t(KB) * (16384 + 8192) + 2 * kLstmN * kLstmRows * 2 + 64;
+  const size_t smem = 1024 + size_t(KB) * (16384 + 8192) + 2 * kLstmN * kLstmRows * 2 + 128;
   auto kern = dtype == DT_F16 ? lstm_layer_kernel<DT_F16> : lstm_layer_kernel<DT_BF16>;
   V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   // all CTAs of a launch must be co-resident: at most floor(SMs / (2 * slices)) groups per launch
   const int max_groups = num_sms() / (2 * p.slices);
   if (max_groups < 1) return fail(V100_E_UNSUPPORTED, "lstm_layer: device too small for H=%d", H);
+  static const int force_cluster = getenv("V100_LSTM_CLUSTER") ? atoi(getenv("V100_LSTM_CLUSTER")) : 0;  // A/B runs
   for (int g0 = 0; g0 < p.groups_total; g0 += max_groups) {
     p.group0 = g0;
     p.groups = p.groups_total - g0 < max_groups ? p.groups_total - g0 : max_groups;
-    kern<<<2 * p.groups * p.slices, kLstmThreads, smem, stream>>>(tm_gx, tm_w, tm_h, p);
-    V100_CUDA(cudaGetLastError());
+    const int grid = 2 * p.groups * p.slices;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kLstmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // V100_LSTM_CLUSTER=n: the n CTAs of a cluster each load 1/n of the h tile and multicast it to their peers
+    // (largest n <= k blocks, <= 8, whose clusters are all co-resident).  Measured on B200 (256 x 751 steps,
+    // H = 512): 3.99 ms per layer without clusters, 4.03 / 4.11 / 4.12 ms with n = 2 / 4 / 8 -- the step is bound
+    // by each SM's own ingest of the 128 KB tile, not by L2 read traffic, so the default is no cluster.
+    int cs = 1;
+    if (force_cluster > 1) cs = force_cluster < KB ? force_cluster : KB;
+    if (cs > 8) cs = 8;
+    while (cs & (cs - 1)) --cs;
+    for (; cs > 1; cs >>= 1) {
+      attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      int active = 0;
+      if (cudaOccupancyMaxActiveClusters(&active, kern, &cfg) == cudaSuccess && active * cs >= grid) break;
+      (void)cudaGetLastError();
+    }
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    p.cluster = cs;
+    V100_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_gx, tm_w, tm_h, p));
   }
   return 0;
 }
