@@ -179,3 +179,37 @@ def test_load_checkpoint_roundtrip(tmp_path):
     assert torch.equal(m2.norm.logspc_mean, stat["logspc_mean"])
     with pytest.raises(v.V100Error):
         v.load_checkpoint(str(path), model_class="TextToAlignTextModel", device="cpu")
+
+
+def test_load_checkpoint_v2(tmp_path):
+    """v2 checkpoints (what the reference's shipped configs produce): class from the keys, conv settings from the
+    Lightning hyper_parameters (or `hparams=` for a bare state_dict), everything else from the tensors."""
+    small = [list(r) for r in synth.ASR_V2_SMALL_ENCODER]
+    sd = {k: torch.from_numpy(np.asarray(x)) for k, x in synth.asr_v2_state_dict(64, small, 2, 256, 44, seed=3).items()}
+    sd["criterion.dummy"] = torch.zeros(1)
+    torch.save({"state_dict": sd, "hyper_parameters": {"audio_size": 64, "encoder_settings": small,
+                                                       "decoder_num_layers": 2, "decoder_hidden_size": 256,
+                                                       "vocab_size": 44}}, tmp_path / "asr_v2.ckpt")
+    m = v.load_checkpoint(str(tmp_path / "asr_v2.ckpt"), device="cpu")
+    assert isinstance(m, v.AudioToAlignText) and m.dense.weight.shape == (44, 512) and m.lstm.num_layers == 2
+    assert m.encoder[0].conv.stride == (2,) and torch.equal(m.lstm.weight_hh_l1_reverse, sd["lstm.weight_hh_l1_reverse"])
+    bare = {k: t for k, t in sd.items() if not k.startswith("criterion")}
+    torch.save(bare, tmp_path / "asr_v2_bare.pt")
+    with pytest.raises(v.V100Error, match="hparams"):
+        v.load_checkpoint(str(tmp_path / "asr_v2_bare.pt"), device="cpu")
+    assert isinstance(v.load_checkpoint(str(tmp_path / "asr_v2_bare.pt"), device="cpu",
+                                        hparams={"encoder_settings": small}), v.AudioToAlignText)
+    wrong = [[256, False, 5, 2, 2, False], [256, False, 3, 1, 1, False]]
+    with pytest.raises(v.V100Error, match="disagrees"):
+        v.load_checkpoint(str(tmp_path / "asr_v2_bare.pt"), device="cpu", hparams={"encoder_settings": wrong})
+    al = {k: torch.from_numpy(np.asarray(x)) for k, x in synth.align_v2_state_dict(29, 2, 64, 2, seed=3).items()}
+    torch.save(al, tmp_path / "align_v2.pt")
+    m2 = v.load_checkpoint(str(tmp_path / "align_v2.pt"), device="cpu")
+    assert isinstance(m2, v.TextToAlignText) and m2.embedding.weight.shape == (29, 64)
+    dec = [list(r) for r in synth.TTS_V2_BASE_DECODER]
+    au = {k: torch.from_numpy(np.asarray(x)) for k, x in
+          synth.audio_v2_state_dict(29, 257, 1, 2, 64, dec, seed=3, randomize_norm=True).items()}
+    torch.save({"state_dict": au, "hyper_parameters": {"decoder_settings": dec}}, tmp_path / "tts_v2.ckpt")
+    m3 = v.load_checkpoint(str(tmp_path / "tts_v2.ckpt"), device="cpu")
+    assert isinstance(m3, v.AlignTextToAudio) and m3.logspc_size == 257 and m3.codeap_size == 1
+    assert torch.equal(m3.norm.logspc_mean, au["norm.logspc_mean"])
