@@ -256,6 +256,63 @@ def run_tts(args):
         "gpu_launches": launches * K, "gpu_launches_per_step": launches}))
 
 
+def run_tts_v2(args):
+    """Secondary workload: the reference's shipped TTS configs (config/align_en_base.yaml + config/tts_en_base.yaml):
+    text [B,100] -> TextToAlignText(2 x biLSTM-256) -> host align_batch_v2 (seeded synthetic alignment) ->
+    AlignTextToAudio(2 x biLSTM-512, conv / transposed-conv blocks).predict -> WORLD parameters."""
+    import numpy as np
+    import torch
+    import voice100_b200 as v
+    from voice100_b200 import _lib, synth
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, Ltxt, V = args.batch, 100, 29
+    load = lambda m, sd: (m.load_state_dict({k: torch.from_numpy(np.asarray(t)) for k, t in sd.items()}), m.to(dev).eval())[1]
+    amodel = load(v.TextToAlignText(V, 2, 256, 2), synth.align_v2_state_dict(V, 2, 256, 2, seed=1234))
+    dec = [list(r) for r in synth.TTS_V2_BASE_DECODER]
+    vmodel = load(v.AlignTextToAudio(V, 257, 1, 2, 512, dec), synth.audio_v2_state_dict(V, seed=1234))
+    text = torch.from_numpy(synth.text_tokens(B, Ltxt, V, seed=1234))
+    text_len = torch.full((B,), Ltxt, dtype=torch.int64)
+    align = torch.from_numpy(synth.synthetic_alignment(B, Ltxt, seed=1234))
+    aligntext, at_len = v.align_batch_v2(text, align, text_len)
+    text_d, at_d = text.to(dev), aligntext.to(dev)
+    out_frames = float((2 * at_len.double() - 1).sum())
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W):
+        amodel(text_d, text_len); vmodel.predict(at_d, at_len)
+    torch.cuda.synchronize()
+    n0 = _lib.stats["launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        pred, _ = amodel(text_d, text_len)
+        f0, logspc, codeap = vmodel.predict(at_d, at_len)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = (_lib.stats["launches"] - n0) // K
+    Ke = max(2, min(K, 5))
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        pred, _ = amodel(text.pin_memory().to(dev, non_blocking=True), text_len)
+        pred_h = pred.cpu()
+        at_h, at_len_h = v.align_batch_v2(text, align, text_len)      # (the benchmark alignment, not exp(pred)-1)
+        f0, logspc, codeap = vmodel.predict(at_h.pin_memory().to(dev, non_blocking=True), at_len_h)
+        out_h = (f0.cpu(), logspc.cpu(), codeap.cpu())
+    dt = (time.perf_counter() - t0) / Ke
+    print(json.dumps({
+        "metric": "tts_output_audio_seconds_per_second", "value": round(out_frames * 0.01 / (ms * 1e-3), 1),
+        "unit": "audio-s/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"tts v2 (config/align_en_base.yaml + config/tts_en_base.yaml): TextToAlignText + "
+                               f"AlignTextToAudio, {B} x 100 tokens, aligned text [{B},{aligntext.shape[1]}] -> "
+                               f"WORLD [{B},{2 * int(at_len.max()) - 1},259]"},
+        "e2e": {"value": round(out_frames * 0.01 / dt, 1), "unit": "audio-s/s",
+                "note": "includes the host alignment, H2D of text and D2H of fp32 WORLD parameters",
+                "d2h_bytes_per_step": int(sum(t.numel() for t in out_h) * 4 + pred_h.numel() * 4)},
+        "gpu_launches": launches * K, "gpu_launches_per_step": launches}))
+
+
 def run_asr_v2(args):
     """Secondary workload: the architecture of the reference's shipped asr_en_base.yaml (AudioToAlignText: two
     LayerNorm/GELU conv blocks -> 2-layer biLSTM(512) -> Linear) on the headline input shape, B x 15 s clips.
@@ -353,7 +410,7 @@ def main():
                     help="BASELINE.json configs[4]: clip lengths U[2 s, 15 s] padded to the batch maximum (audio-seconds "
                          "then count valid samples only); the default is the metric's fixed 15 s clips")
     ap.add_argument("--vocab", type=int, default=MODEL["vocab_size"], help="44 = asr_ja_phone_base")
-    ap.add_argument("--workload", default="asr", choices=["asr", "tts", "asr_v2"], help="asr = the headline metric")
+    ap.add_argument("--workload", default="asr", choices=["asr", "tts", "asr_v2", "tts_v2"], help="asr = the headline metric")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -361,6 +418,8 @@ def main():
         return run_tts(args)
     if args.workload == "asr_v2":
         return run_asr_v2(args)
+    if args.workload == "tts_v2":
+        return run_tts_v2(args)
 
     import numpy as np
     import torch

@@ -112,6 +112,20 @@ def test_align_v2_host_function_matches_oracle():
         assert got.tolist() == orc.align_text_v2(text[i].tolist(), align[i]).tolist()
 
 
+def test_align_batch_v2_matches_reference_loop():
+    import v100_oracle as orc
+    text = torch.from_numpy(synth.text_tokens(9, 40, seed=6))
+    align = torch.from_numpy(synth.synthetic_alignment(9, 40, seed=6))
+    align[3, 5:9, 1] = 0.0                                  # zero durations: the one-frame minimum kicks in
+    lens = torch.tensor([40, 1, 17, 40, 33, 2, 40, 25, 9])
+    at, at_len = v.align_batch_v2(text, align, lens)
+    for b in range(9):
+        n = int(lens[b])
+        ref = orc.align_text_v2(text[b, :n].tolist(), align[b, :n].numpy())
+        assert int(at_len[b]) == len(ref) and at[b, :len(ref)].tolist() == ref.tolist()
+        assert (at[b, len(ref):] == 0).all()
+
+
 def test_align_host_function_matches_oracle():
     import v100_oracle as orc
     text = torch.from_numpy(synth.text_tokens(3, 17, seed=5))

@@ -16,4 +16,4 @@ from .text import CharTokenizer  # noqa: F401
 from .checkpoint import load_checkpoint  # noqa: F401
 from .align import ctc_best_path_batch  # noqa: F401
 from .v2 import (AudioToAlignText, TextToAlignText, AlignTextToAudio, AsrV2Pipeline,  # noqa: F401
-                 ConvLayerBlock, ConvTransposeLayerBlock, get_conv_layers)
+                 ConvLayerBlock, ConvTransposeLayerBlock, get_conv_layers, align_batch_v2)

@@ -25,7 +25,7 @@ from .blocks import PreparedCache, StorageDtypeMixin, require_eval_cuda
 from .tts import WORLDNorm
 
 __all__ = ["ConvLayerBlock", "ConvTransposeLayerBlock", "get_conv_layers", "AudioToAlignText", "TextToAlignText",
-           "AlignTextToAudio", "AsrV2Pipeline"]
+           "AlignTextToAudio", "AsrV2Pipeline", "align_batch_v2"]
 
 
 class ConvLayerBlock(nn.Module):
@@ -254,6 +254,46 @@ class TextToAlignText(StorageDtypeMixin, nn.Module):
             u = e
             out[s:e] = toks[i]
         return out
+
+
+def align_batch_v2(text, align, text_len=None, head: int = 5, tail: int = 5, pad_value: int = 0):
+    """`TextToAlignText.align` (_align_v2.py:54-82) over a padded batch on the host: text int64 [B, L], align float
+    [B, L, 2], optional text_len [B] -> (aligntext int64 [B, T_max], aligntext_len int32 [B]).  Same arithmetic as the
+    reference loop: float64 running sum of the float32 entries with the first gap skipped, int() truncation,
+    s_i = max(int(t), e_{i-1}), e_i = max(int(t + dur_i), s_i + 1)."""
+    import numpy as np
+    text_np = text.detach().cpu().numpy()
+    al32 = align.detach().cpu()
+    al = al32.numpy().astype(np.float64)
+    B, L = text_np.shape
+    lens = np.full((B,), L, np.int64) if text_len is None else np.asarray(text_len.detach().cpu()).astype(np.int64)
+    flat = al.reshape(B, 2 * L).copy()
+    flat[:, 0] = 0.0                                          # the first token's gap is not applied
+    t = head + np.cumsum(flat, axis=1)
+    a, b = t[:, 0::2].astype(np.int64), t[:, 1::2].astype(np.int64)
+    s, e = np.empty_like(a), np.empty_like(b)
+    prev = np.zeros((B,), np.int64)
+    for i in range(L):                                        # running max: sequential in i, vector over the batch
+        s[:, i] = np.maximum(a[:, i], prev)
+        e[:, i] = np.maximum(b[:, i], s[:, i] + 1)
+        prev = e[:, i]
+    outs = []
+    for u in range(B):
+        n = int(lens[u])
+        total = head + int(torch.sum(al32[u, :n]) - al32[u, 0, 0]) + tail if n else head + tail
+        if n and e[u, n - 1] > total:
+            raise IndexError("alignment runs past the aligned text (same failure as the reference)")
+        out = np.zeros((total,), np.int64)
+        if n:
+            seg = e[u, :n] - s[u, :n]
+            pos = np.repeat(s[u, :n] - (np.cumsum(seg) - seg), seg) + np.arange(int(seg.sum()))
+            out[pos] = np.repeat(text_np[u, :n], seg)
+        outs.append(out)
+    T = max(len(o) for o in outs)
+    res = np.full((B, T), pad_value, np.int64)
+    for u, o in enumerate(outs):
+        res[u, :len(o)] = o
+    return torch.from_numpy(res), torch.tensor([len(o) for o in outs], dtype=torch.int32)
 
 
 class AlignTextToAudio(StorageDtypeMixin, nn.Module):
