@@ -292,13 +292,17 @@ def run_tts_v2(args):
     ms = e0.elapsed_time(e1) / K
     launches = (_lib.stats["launches"] - n0) // K
     Ke = max(2, min(K, 5))
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    pred_h, out_h, text_p = pin(pred), (pin(f0), pin(logspc), pin(codeap)), text.pin_memory()
     t0 = time.perf_counter()
     for _ in range(Ke):
-        pred, _ = amodel(text.pin_memory().to(dev, non_blocking=True), text_len)
-        pred_h = pred.cpu()
+        pred, _ = amodel(text_p.to(dev, non_blocking=True), text_len)
+        pred_h.copy_(pred, non_blocking=True)
         at_h, at_len_h = v.align_batch_v2(text, align, text_len)      # (the benchmark alignment, not exp(pred)-1)
-        f0, logspc, codeap = vmodel.predict(at_h.pin_memory().to(dev, non_blocking=True), at_len_h)
-        out_h = (f0.cpu(), logspc.cpu(), codeap.cpu())
+        outs = vmodel.predict(at_h.pin_memory().to(dev, non_blocking=True), at_len_h)
+        for h, d in zip(out_h, outs):
+            h.copy_(d, non_blocking=True)
+        torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / Ke
     print(json.dumps({
         "metric": "tts_output_audio_seconds_per_second", "value": round(out_frames * 0.01 / (ms * 1e-3), 1),
