@@ -34,11 +34,11 @@ lens = torch.full((B,), T, dtype=torch.int32, device=dev)
 for _ in range(3):
     K.lstm_layer(x, w_ih, bias, w_hh, lens)
 torch.cuda.synchronize()
-buf = (ctypes.c_ulonglong * 512)()
+buf = (ctypes.c_ulonglong * 768)()
 fn = _lib.lib().v100_debug_lstm_prof
 fn.argtypes = [ctypes.c_void_p]
 assert fn(buf) == 0
-st = np.array(buf, dtype=np.int64).reshape(64, 8)[2:62]
+st = np.array(buf, dtype=np.int64).reshape(64, 12)[2:62]
 names = ["ctl: wait counter", "ctl: TMA h + MMA issue + commit", "gate: commit -> acc in registers",
          "gate: Gx wait + gate math + h store", "gate: proxy fence", "gate: bar.sync", "gate: red.release",
          "next step: publish -> control thread starts waiting"]
@@ -49,3 +49,7 @@ print(f"B={B} H={H}: median step {step:.0f} ns")
 for n, v in zip(names, d):
     print(f"  {n:50s} median {np.median(v):7.0f} ns   p90 {np.percentile(v, 90):7.0f}")
 print(f"  {'red.release done -> own counter wait satisfied':50s} median {np.median(st[1:, 1] - st[:-1, 7]):7.0f} ns")
+print(f"  {'  counter seen -> all TMA loads issued':50s} median {np.median(st[:, 8] - st[:, 1]):7.0f} ns")
+print(f"  {'  loads issued -> first 16 KB box landed':50s} median {np.median(st[:, 9] - st[:, 8]):7.0f} ns")
+print(f"  {'  first box -> last box landed':50s} median {np.median(st[:, 10] - st[:, 9]):7.0f} ns")
+print(f"  {'  last box -> MMAs issued + commit':50s} median {np.median(st[:, 2] - st[:, 10]):7.0f} ns")

@@ -244,7 +244,7 @@ struct LstmParams {
   long long n_cols;  // T * Bp
   const int32_t* lengths;
   unsigned short* y;      // [2H][n_cols]
-  unsigned short* hx;     // exchange buffer [2 dirs][groups_total][2][128][H]
+  unsigned short* hx;     // exchange buffer [2 dirs][groups_total][2][H/64][128][64]
   unsigned int* counters; // [2 dirs][groups_total]
   int dtype;
   int cluster;            // CTAs per cluster (consecutive slices of one (direction, group)); 1 = no multicast
@@ -281,14 +281,14 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, 
 
 #ifdef V100_LSTM_PROF
 // profiling build only (tools/lstm_prof.py): globaltimer stamps of block 0 for a few steps
-__device__ unsigned long long g_lstm_prof[64 * 8];
+__device__ unsigned long long g_lstm_prof[64 * 12];
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 #define LSTM_STAMP(step, slot) \
-  do { if (blockIdx.x == 0 && (step) >= 100 && (step) < 164) g_lstm_prof[((step) - 100) * 8 + (slot)] = gtime(); } while (0)
+  do { if (blockIdx.x == 0 && (step) >= 100 && (step) < 164) g_lstm_prof[((step) - 100) * 12 + (slot)] = gtime(); } while (0)
 #else
 #define LSTM_STAMP(step, slot) do {} while (0)
 #endif
@@ -317,7 +317,6 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
   const int grp = p.group0 + gl;
   const int dg = dir * p.groups_total + grp;
   unsigned int* counter = p.counters + dg;
-  const int hx_row0 = dg * 2 * kLstmRows;  // row of parity 0 in the exchange buffer (rows of H elements)
   const int u0 = slice * kLstmUnits;
 
   auto load_gx = [&](int k) {  // control thread: the four gate blocks of step k -> buffer k & 1
@@ -354,8 +353,11 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   if (warp == 4) {
+    // ===================== control warp: TMA + MMA issue =====================
+    // lane 0 polls the step counter, waits for the tile and issues the MMAs; lanes 0..KB-1 each issue one
+    // 16 KB box of the h tile (one warp instruction instead of a serial loop -- the serial issue of 13 TMA
+    // operations by one thread was 0.74 us of every 5.4 us step); lane 8 prefetches the next step's Gx.
     if (lane == 0) {
-      // ===================== control: TMA + MMA issue =====================
       mbar_expect_tx(w_full, uint32_t(kLstmN) * p.H * 2);
       for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -365,13 +367,18 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
       load_gx(0);
       if (p.T > 1) load_gx(1);
       mbar_wait(w_full, 0);
-      const uint32_t fmt = DT == DT_F16 ? 0u : 1u;
-      // kind::f16, D = f32, A and B K-major, M = 128, N = 64
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(kLstmN >> 3) << 17) |
-                             (uint32_t(kLstmRows >> 4) << 24);
-      const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
-      const unsigned int per_step = p.slices;
-      for (int k = 1; k < p.T; ++k) {
+    }
+    const uint32_t fmt = DT == DT_F16 ? 0u : 1u;
+    // kind::f16, D = f32, A and B K-major, M = 128, N = 64
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(kLstmN >> 3) << 17) |
+                           (uint32_t(kLstmRows >> 4) << 24);
+    const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    const unsigned int per_step = p.slices;
+    const bool loads_box = lane < KB && (lane % p.cluster) == crank;
+    for (int k = 1; k < p.T; ++k) {
+      if (lane == 0) {
+        // arm the tile barriers before the wait: the bytes can only arrive after it anyway
+        for (int kb = 0; kb < KB; ++kb) mbar_expect_tx(&h_full[kb], 16384);
         // every slice of this (direction, group) has published h of step k-1
         const unsigned int need = unsigned(k) * per_step;
         LSTM_STAMP(k, 0);
@@ -386,19 +393,25 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
           }
         }
         LSTM_STAMP(k, 1);
+      }
+      __syncwarp();
+      // h_{k-1} of the group.  (With clusters the CTAs are slices of the same (direction, group) and all passed
+      // the same counter, so each loads 1/cluster of the tile and multicasts it to every peer.)
+      if (loads_box) {
         fence_proxy_async_global();
-        // the gate warps of this CTA are past step k-1 as well: their Gx buffer (k+1)&1 is free again
-        if (k + 1 < p.T) load_gx(k + 1);
-        // h_{k-1} of the group: the CTAs of a cluster are slices of the same (direction, group) and all passed
-        // the same counter, so each loads 1/cluster of the tile and multicasts it to every peer
-        const int hrow = hx_row0 + ((k - 1) & 1) * kLstmRows;
-        for (int kb = 0; kb < KB; ++kb) mbar_expect_tx(&h_full[kb], 16384);
-        for (int kb = crank; kb < KB; kb += p.cluster) {
-          if (p.cluster > 1) tma_load_2d_mc(sA + kb * 16384, &tm_h, &h_full[kb], kb * 64, hrow, cmask);
-          else tma_load_2d(sA + kb * 16384, &tm_h, &h_full[kb], kb * 64, hrow);
-        }
+        // exchange buffer = [dir][group][parity][k block][128 rows][64]: one box is 16 KB contiguous in global memory
+        const int hrow = ((dg * 2 + ((k - 1) & 1)) * KB + lane) * kLstmRows;
+        if (p.cluster > 1) tma_load_2d_mc(sA + lane * 16384, &tm_h, &h_full[lane], 0, hrow, cmask);
+        else tma_load_2d(sA + lane * 16384, &tm_h, &h_full[lane], 0, hrow);
+      }
+      // the gate warps of this CTA are past step k-1 as well: their Gx buffer (k+1)&1 is free again
+      if (lane == 8 && k + 1 < p.T) load_gx(k + 1);
+      if (lane == 0) {
+        LSTM_STAMP(k, 8);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&h_full[kb], (k - 1) & 1);
+          if (kb == 0) LSTM_STAMP(k, 9);
+          if (kb == KB - 1) LSTM_STAMP(k, 10);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -410,6 +423,7 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
         umma_commit(acc_full);
         LSTM_STAMP(k, 2);
       }
+      __syncwarp();
     }
   } else {
     // ===================== gates: one thread = one utterance, 16 hidden units =====================
@@ -454,7 +468,8 @@ lstm_layer_kernel(const __grid_constant__ CUtensorMap tm_gx, const __grid_consta
         else hprev = h;
       }
       // h_t for the next step's MMA: exchange buffer parity k&1, row = utterance, 16 units = 32 bytes
-      uint4* hdst = reinterpret_cast<uint4*>(p.hx + (static_cast<long long>(hx_row0 + (k & 1) * kLstmRows + row)) * p.H + u0);
+      uint4* hdst = reinterpret_cast<uint4*>(
+          p.hx + (static_cast<long long>((dg * 2 + (k & 1)) * KB + (u0 >> 6)) * kLstmRows + row) * 64 + (u0 & 63));
       hdst[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
       hdst[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
       // publish: every thread orders its stores against the async proxy (the consumers read them with TMA),
@@ -521,7 +536,7 @@ int lstm_layer(const void* gx, const void* w_hh, const int32_t* lengths, void* y
   CUtensorMap tm_gx, tm_w, tm_h;
   if (int e = make_tmap_2d_plain(&tm_gx, tt, gx, p.n_cols, int64_t(8) * H, p.n_cols * 2, kLstmRows, kLstmUnits)) return e;
   if (int e = make_tmap_2d(&tm_w, tt, w_hh, H, int64_t(8) * H, int64_t(H) * 2, 64, kLstmUnits)) return e;
-  if (int e = make_tmap_2d(&tm_h, tt, workspace, H, int64_t(2) * p.groups_total * 2 * kLstmRows, int64_t(H) * 2, 64, kLstmRows)) return e;
+  if (int e = make_tmap_2d(&tm_h, tt, workspace, 64, int64_t(2) * p.groups_total * 2 * (H / 64) * kLstmRows, 128, 64, kLstmRows)) return e;
   const int KB = H / 64;
   const size_t smem = 1024 + size_t(KB) * (16384 + 8192) + 2 * kLstmN * kLstmRows * 2 + 128;
   auto kern = dtype == DT_F16 ? lstm_layer_kernel<DT_F16> : lstm_layer_kernel<DT_BF16>;
