@@ -190,6 +190,16 @@ def test_asr_full_size_properties():
     # host path (pinned buffers, chunked H2D, async D2H) returns the same tokens
     tok_h, len_h = pipe.transcribe_host(wav.cpu().pin_memory(), lengths.pin_memory(), device=DEV)
     assert torch.equal(tok_h, tokens.cpu()) and len_h.tolist() == out_len.cpu().tolist()
+    # streaming form: whole-batch graphs, two batches in flight on alternating buffer sets
+    wav_h, len_p = wav.cpu().pin_memory(), lengths.pin_memory()
+    wav_r = wav.flip(0).cpu().pin_memory()
+    len_r = lengths.flip(0).contiguous().pin_memory()
+    t1 = pipe.submit_host(wav_h, len_p, device=DEV, chunks=1)
+    t2 = pipe.submit_host(wav_r, len_r, device=DEV, chunks=1)
+    t3 = pipe.submit_host(wav_h, len_p, device=DEV, chunks=1)
+    assert torch.equal(t2.result()[0], tokens.flip(0).cpu())
+    assert torch.equal(t3.result()[0], tokens.cpu()) and t3.result()[1].tolist() == out_len.cpu().tolist()
+    del t1
     # oracle on a sample of utterances (features padded to the batch's frame count with BLANK_AUDIO)
     for i in (0, 131, 255):
         n = int(lengths[i])

@@ -154,7 +154,10 @@ class AsrPipeline:
         static device buffers.  H2D copies run on a side stream straight into those buffers, so chunk i+1
         uploads while chunk i computes, and each chunk's tokens come back with an async D2H.  Returns a
         ticket; `ticket.result()` waits for THIS batch only, so the next batch can be submitted (and start
-        uploading) before the previous one has finished computing.  Two tickets may be in flight."""
+        uploading) before the previous one has finished computing.  Two tickets may be in flight: consecutive
+        calls alternate between two sets of graphs / device buffers, so batch i+1 uploads into its own buffers
+        while batch i still computes.  `chunks=1` gives the best throughput (whole-batch kernels, uploads hidden
+        behind the previous batch), more chunks give a shorter latency for a single batch."""
         dev = torch.device(device)
         B, L = waveform.shape
         n = max(1, min(chunks, B))
@@ -163,8 +166,9 @@ class AsrPipeline:
             self._copy_stream = torch.cuda.Stream(dev)
             self._host_out, self._slot, self._chunk_graphs = {}, 0, {}
         T_out = (self.transform.num_frames(L) + 1) // 2
-        key = (B, T_out, self._slot)
-        self._slot ^= 1                      # double-buffered pinned outputs: two tickets in flight
+        slot = self._slot
+        key = (B, T_out, slot)
+        self._slot ^= 1                      # double-buffered device inputs and pinned outputs: two tickets in flight
         if key not in self._host_out:
             self._host_out[key] = (torch.empty((B, T_out), dtype=torch.int64).pin_memory(),
                                    torch.empty((B,), dtype=torch.int32).pin_memory())
@@ -172,7 +176,7 @@ class AsrPipeline:
         staged = []
         for i in range(n):
             a, b = B * i // n, B * (i + 1) // n
-            gkey = (i, b - a, L)
+            gkey = (i, b - a, L, slot)
             if gkey not in self._chunk_graphs:
                 self._chunk_graphs[gkey] = list(self._capture(b - a, L, dev)) + [None]
             cg = self._chunk_graphs[gkey]
