@@ -14,7 +14,7 @@ from voice100_b200.data_modules import MelSpectrogramAudioTransform
 DEV = "cuda"
 B = int(os.environ.get("PROF_B", "256"))
 T = 751
-which = set((os.environ.get("PROF_WHICH") or "dw,gemm,logmel").split(","))
+which = set((os.environ.get("PROF_WHICH") or "dw,gemm,logmel").split(","))   # also: v2
 
 
 def ncw(C, T):
@@ -47,5 +47,22 @@ if "logmel" in which:
     ln = torch.full((B,), 240000, dtype=torch.int32, device=DEV)
     for _ in range(2):
         tr.logmel_batch(wav, ln, ncw_bf16=True)
+if "v2" in which:
+    # the v2 kernels at the asr_v2 benchmark shapes; the LSTM over PROF_LSTM_T steps (ncu replays the kernel)
+    x = ncw(512, T)
+    g, be = torch.ones(512, device=DEV), torch.zeros(512, device=DEV)
+    wp = (torch.randn(512, 5 * 512, device=DEV) / 50).to(torch.bfloat16)
+    for _ in range(2):
+        y = K.conv1d(x, wp, be, 5, 1, 2)
+        K.layernorm_gelu(y, g, be, 1e-5)
+        tm = K.ncw_to_tm(y)
+    Tl = int(os.environ.get("PROF_LSTM_T", "96"))
+    H = 512
+    xt = K.Tm(torch.randn(H, Tl * K.pitch_of(B), device=DEV).to(torch.bfloat16), B, Tl, K.pitch_of(B))
+    w_ih = (torch.randn(8 * H, H, device=DEV) / H ** 0.5).to(torch.bfloat16)
+    w_hh = (torch.randn(2, 4 * H, H, device=DEV) / H ** 0.5).to(torch.bfloat16)
+    lens = torch.full((B,), Tl, dtype=torch.int32, device=DEV)
+    for _ in range(2):
+        K.lstm_layer(xt, w_ih, torch.zeros(8 * H, device=DEV), w_hh, lens)
 torch.cuda.synchronize()
 print("profile_kernels done")
