@@ -83,6 +83,22 @@ int conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, vo
 // LayerNorm over channels + GELU(erf), NCW -> NCW.  One CTA = one utterance x 64 time columns; the [C x 64]
 // tile is staged in shared memory once, statistics are two-pass (mean, then centred sum of squares) in fp32.
 // ------------------------------------------------------------------------------------------------
+// gelu(x) = x * Phi(x), Phi(x) = 0.5 * erfc(-x / sqrt(2)).  erfc by Abramowitz & Stegun 7.1.26 (|abs err| < 1.5e-7),
+// evaluated on the side without cancellation: Phi(x) = 0.5 * q for x < 0 and 1 - 0.5 * q for x >= 0 with
+// q = poly(t) * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt(2)).  A third of the instructions of erff(); the result is
+// rounded to a 16-bit type right after.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float q = poly * t * __expf(-z * z);
+  const float phi = x < 0.0f ? 0.5f * q : 1.0f - 0.5f * q;
+  return x * phi;
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256)
 layernorm_gelu_kernel(const uint32_t* __restrict__ x, long long x_pitch, const float* __restrict__ gamma,
@@ -142,8 +158,8 @@ layernorm_gelu_kernel(const uint32_t* __restrict__ x, long long x_pitch, const f
     const float g = __ldg(gamma + c), be = __ldg(beta + c);
     float a0 = fmaf((unpack_lo<DT>(v) - m0) * r0, g, be);
     float a1 = fmaf((unpack_hi<DT>(v) - m1) * r1, g, be);
-    a0 = 0.5f * a0 * (1.0f + erff(a0 * 0.70710678118654752f));
-    a1 = 0.5f * a1 * (1.0f + erff(a1 * 0.70710678118654752f));
+    a0 = gelu_erf(a0);
+    a1 = gelu_erf(a1);
     // columns past T hold whatever the producer left in the row padding: keep them finite
     if (t0 + 2 * lane >= T) a0 = 0.0f;
     if (t0 + 2 * lane + 1 >= T) a1 = 0.0f;
@@ -169,39 +185,58 @@ int layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// NCW [B][C][pitch]  <->  time-major [C][T*Bp]   (16-bit elements, 32 x 32 tiles through shared memory)
+// NCW [B][C][pitch]  <->  time-major [C][T*Bp]   (16-bit elements, 64 x 64 tiles through shared memory)
 // ------------------------------------------------------------------------------------------------
+// tile = 64 time steps x 64 utterances of one channel; both the reads (64 steps of an utterance row) and the
+// writes (64 utterances of a step) are 128-byte segments
 __global__ void __launch_bounds__(256)
 ncw_to_tm_kernel(const unsigned short* __restrict__ x, long long pitch, unsigned short* __restrict__ y, int B, int C,
                  int T, int Bp) {
-  __shared__ unsigned short tile[32][34];
-  const int c = blockIdx.z, t0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  __shared__ uint32_t tile[64][33];  // [utterance][pair of time steps]
+  const int c = blockIdx.z, t0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int b = b0 + r, t = t0 + tx;
-    tile[r][tx] = (b < B && t < T) ? x[(static_cast<long long>(b) * C + c) * pitch + t] : (unsigned short)0;
+  for (int r = ty; r < 64; r += 8) {
+    const int b = b0 + r, t = t0 + 2 * tx;
+    uint32_t v = 0;
+    if (b < B && t < pitch) {  // pitch is even; columns in [T, pitch) are masked below
+      v = *reinterpret_cast<const uint32_t*>(x + (static_cast<long long>(b) * C + c) * pitch + t);
+      if (t >= T) v = 0;
+      else if (t + 1 >= T) v &= 0xFFFFu;
+    }
+    tile[r][tx] = v;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, b = b0 + tx;
-    if (t < T && b < Bp) y[static_cast<long long>(c) * T * Bp + static_cast<long long>(t) * Bp + b] = tile[tx][r];
+  for (int r = ty; r < 64; r += 8) {  // r = time step within the tile, tx = pair of utterances
+    const int t = t0 + r, b = b0 + 2 * tx;
+    if (t < T && b < Bp) {
+      const uint32_t lo = tile[2 * tx][r >> 1], hi = tile[2 * tx + 1][r >> 1];
+      const uint32_t v = (r & 1) ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+      *reinterpret_cast<uint32_t*>(y + static_cast<long long>(c) * T * Bp + static_cast<long long>(t) * Bp + b) = v;
+    }
   }
 }
 
 __global__ void __launch_bounds__(256)
 tm_to_ncw_kernel(const unsigned short* __restrict__ x, unsigned short* __restrict__ y, long long pitch, int B, int C,
                  int T, int Bp) {
-  __shared__ unsigned short tile[32][34];
-  const int c = blockIdx.z, t0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  __shared__ uint32_t tile[64][33];  // [time step][pair of utterances]
+  const int c = blockIdx.z, t0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int t = t0 + r, b = b0 + tx;
-    tile[r][tx] = (t < T && b < B) ? x[static_cast<long long>(c) * T * Bp + static_cast<long long>(t) * Bp + b] : (unsigned short)0;
+  for (int r = ty; r < 64; r += 8) {
+    const int t = t0 + r, b = b0 + 2 * tx;
+    uint32_t v = 0;
+    if (t < T && b < Bp)  // Bp is even; utterances in [B, Bp) are zero in a TM tensor
+      v = *reinterpret_cast<const uint32_t*>(x + static_cast<long long>(c) * T * Bp + static_cast<long long>(t) * Bp + b);
+    tile[r][tx] = v;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int b = b0 + r, t = t0 + tx;
-    if (b < B && t < pitch) y[(static_cast<long long>(b) * C + c) * pitch + t] = tile[tx][r];
+  for (int r = ty; r < 64; r += 8) {  // r = utterance within the tile, tx = pair of time steps
+    const int b = b0 + r, t = t0 + 2 * tx;
+    if (b < B && t < pitch) {
+      const uint32_t lo = tile[2 * tx][r >> 1], hi = tile[2 * tx + 1][r >> 1];
+      const uint32_t v = (r & 1) ? ((lo >> 16) | (hi & 0xFFFF0000u)) : ((lo & 0xFFFFu) | (hi << 16));
+      *reinterpret_cast<uint32_t*>(y + (static_cast<long long>(b) * C + c) * pitch + t) = v;
+    }
   }
 }
 
@@ -209,7 +244,8 @@ int ncw_to_tm(const void* x, int64_t x_pitch, void* y, int B, int C, int T, int 
   if (x == nullptr || y == nullptr) return fail(V100_E_INVALID, "ncw_to_tm: null pointer");
   if (B <= 0 || C <= 0 || T <= 0 || Bp < B || (Bp & 7) != 0 || x_pitch < T || C > 65535)
     return fail(V100_E_INVALID, "ncw_to_tm: bad sizes (Bp must be a multiple of 8, >= B)");
-  dim3 grid((T + 31) / 32, (Bp + 31) / 32, C);
+  if ((x_pitch & 1) != 0) return fail(V100_E_INVALID, "ncw_to_tm: pitch must be even");
+  dim3 grid((T + 63) / 64, (Bp + 63) / 64, C);
   ncw_to_tm_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(x), x_pitch,
                                              static_cast<unsigned short*>(y), B, C, T, Bp);
   V100_CUDA(cudaGetLastError());
@@ -220,7 +256,8 @@ int tm_to_ncw(const void* x, void* y, int64_t y_pitch, int B, int C, int T, int 
   if (x == nullptr || y == nullptr) return fail(V100_E_INVALID, "tm_to_ncw: null pointer");
   if (B <= 0 || C <= 0 || T <= 0 || Bp < B || (Bp & 7) != 0 || y_pitch < T || C > 65535)
     return fail(V100_E_INVALID, "tm_to_ncw: bad sizes (Bp must be a multiple of 8, >= B)");
-  dim3 grid((unsigned)((y_pitch + 31) / 32), (B + 31) / 32, C);
+  if ((y_pitch & 1) != 0) return fail(V100_E_INVALID, "tm_to_ncw: pitch must be even");
+  dim3 grid((unsigned)((y_pitch + 63) / 64), (B + 63) / 64, C);
   tm_to_ncw_kernel<<<grid, 256, 0, stream>>>(static_cast<const unsigned short*>(x), static_cast<unsigned short*>(y),
                                              y_pitch, B, C, T, Bp);
   V100_CUDA(cudaGetLastError());
