@@ -209,6 +209,32 @@ def gen_tts_v2(seed=51):
           "audio params", sum(p.numel() for p in vmodel.parameters() if p.requires_grad))
 
 
+def gen_mcep(seed=61):
+    """mel-cepstrum TTS head: create_mc2sp_matrix (voice100/vocoder.py:115-123) and the export wrapper
+    AlignTextToAudioPredict (voice100/export_onnx.py:81-97) over a logspc_size=25 model, as config/tts_en_base.yaml
+    trains it.  voice100.vocoder imports pyworld at module level; oracle/_shim/pyworld.py stands in for it."""
+    from voice100.vocoder import create_mc2sp_matrix
+    from voice100.export_onnx import AlignTextToAudioPredict
+    from voice100.models._tts_v2 import AlignTextToAudio
+    V, B = 29, 2
+    aligntext = torch.from_numpy(synth.text_tokens(B, 40, V, seed=seed))
+    aligntext_len = torch.tensor([40, 23])
+    aligntext[1, 23:] = 0
+    model = AlignTextToAudio(vocab_size=V, logspc_size=25, codeap_size=1, encoder_num_layers=2,
+                             encoder_hidden_size=512, decoder_settings=[list(r) for r in synth.TTS_V2_BASE_DECODER])
+    load(model, synth.audio_v2_state_dict(V, 25, 1, 2, 512, synth.TTS_V2_BASE_DECODER, seed=seed, randomize_ln=True,
+                                          randomize_norm=True, gain=2.0))
+    model.eval()
+    with torch.no_grad():
+        f0, logspc, codeap = AlignTextToAudioPredict(model)(aligntext, aligntext_len)
+        _, mcep, _ = model.predict(aligntext, aligntext_len)
+    np.savez_compressed(
+        os.path.join(OUT, "tts_v2_mcep.npz"), mc2sp_matrix=create_mc2sp_matrix(512, 24, 0.410).astype(np.float32),
+        aligntext=aligntext.numpy(), aligntext_len=aligntext_len.numpy(), f0=f0.numpy(), logspc=logspc.numpy(),
+        mcep=mcep.numpy(), codeap=codeap.numpy(), cfg=np.asarray([V, B, seed], np.int64))
+    print("mcep", tuple(mcep.shape), "->", tuple(logspc.shape), "logspc std %.3f" % float(logspc.std()))
+
+
 def viterbi_case(T, L, seed):
     from voice100_b200.synth import viterbi_inputs
     return viterbi_inputs(T, L, 29, seed)
@@ -226,3 +252,4 @@ if __name__ == "__main__":
     gen_asr_v2("asr_v2_en_base", synth.ASR_V2_BASE_ENCODER, 512, 29, batch=2, samples=16000,
                lengths=[16000, 16000], seed=24)
     gen_tts_v2()
+    gen_mcep()

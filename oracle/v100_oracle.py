@@ -442,6 +442,42 @@ def audio_v2_predict(aligntext, aligntext_len, sd: SD, decoder_settings, **kw):
 
 
 # ----------------------------------------------------------------------------------------------
+# mel-cepstrum -> log spectrum: voice100/vocoder.py:115-145 (create_mc2sp_matrix, freqt; PySPTK conventions),
+# applied after predict() by the export wrapper (voice100/export_onnx.py:81-97) and the data module
+# (voice100/data_modules.py:229-231) when the model was trained on 25 mel-cepstral coefficients.
+# ----------------------------------------------------------------------------------------------
+
+def freqt_vector(c: np.ndarray, out_order: int, alpha: float) -> np.ndarray:
+    """SPTK `freqt` on one cepstrum vector: all-pass frequency warping by `alpha` (Oppenheim recursion,
+    float64).  Input taken last coefficient first; g' = alpha*g shifted by the recurrence
+    g'[0] = c_i + a g[0];  g'[1] = (1 - a^2) g[0] + a g[1];  g'[j] = g[j-1] + a (g[j] - g'[j-1])."""
+    g = np.zeros(out_order + 1)
+    for ci in np.asarray(c, np.float64)[::-1]:
+        prev = g
+        g = np.empty_like(prev)
+        g[0] = ci + alpha * prev[0]
+        if out_order >= 1:
+            g[1] = (1.0 - alpha * alpha) * prev[0] + alpha * prev[1]
+        for j in range(2, out_order + 1):
+            g[j] = prev[j - 1] + alpha * (prev[j] - g[j - 1])
+    return g
+
+
+def mc2sp_matrix(fftlen=512, order=24, alpha=0.410) -> np.ndarray:
+    """[order+1, fftlen/2+1] matrix M with logspc = mcep @ M (vocoder.py:115-123): un-warp each unit cepstrum to
+    fftlen/2 + 1 coefficients, double c0, extend to the even sequence [c0..cN, cN..c1] and take the real DFT."""
+    n = fftlen // 2
+    rows = []
+    for k in range(order + 1):
+        e = np.zeros(order + 1)
+        e[k] = 1.0
+        c = freqt_vector(e, n, -alpha)
+        c[0] *= 2.0
+        rows.append(np.fft.rfft(np.concatenate([c, c[:0:-1]])).real)
+    return np.stack(rows)
+
+
+# ----------------------------------------------------------------------------------------------
 # Forced alignment: voice100/models/align.py:18-66 (ctc_best_path, max_move = 3), the per-utterance numpy DP
 # behind AudioToAlignText.ctc_best_path (voice100/models/_asr_v2.py:100-119)
 # ----------------------------------------------------------------------------------------------

@@ -187,3 +187,23 @@ def test_tts_v2_matches_reference():
     np.testing.assert_allclose(logspc.numpy(), g["logspc"], rtol=0, atol=1e-3)
     sure_c = np.abs(g["hascodeap_logits"]) > 1e-3
     np.testing.assert_allclose(codeap.numpy()[sure_c], g["codeap"][sure_c], rtol=0, atol=1e-3)
+
+
+def test_mc2sp_matches_reference():
+    """mel-cepstrum -> log-spectrum matrix and the export wrapper's output (vocoder.py:115-123, export_onnx.py:81-97)."""
+    from voice100_b200.vocoder import create_mc2sp_matrix
+    g = golden("tts_v2_mcep")
+    ref = g["mc2sp_matrix"]
+    assert ref.shape == (25, 257)
+    np.testing.assert_allclose(orc.mc2sp_matrix(512, 24, 0.410), ref, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(create_mc2sp_matrix(512, 24, 0.410), ref, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ref[0], 2.0, atol=1e-6)                  # c0 alone is a flat spectrum of 2 c0
+    V, B, seed = [int(x) for x in g["cfg"]]
+    sd = {k: torch.from_numpy(v) for k, v in synth.audio_v2_state_dict(
+        V, 25, 1, 2, 512, synth.TTS_V2_BASE_DECODER, seed=seed, randomize_ln=True, randomize_norm=True, gain=2.0).items()}
+    lens = [int(x) for x in g["aligntext_len"]]
+    f0, mcep, codeap = orc.audio_v2_predict(torch.from_numpy(g["aligntext"]), lens, sd, synth.TTS_V2_BASE_DECODER,
+                                            logspc_size=25)
+    np.testing.assert_allclose(mcep.numpy(), g["mcep"], rtol=0, atol=2e-4)
+    logspc = mcep.double().numpy() @ orc.mc2sp_matrix(512, 24, 0.410)
+    np.testing.assert_allclose(logspc, g["logspc"], rtol=0, atol=5e-3)  # |logspc| ~ 1e2: fp32 matmul round-off

@@ -209,3 +209,30 @@ def test_tts_v2_matches_golden():
     sure = np.abs(g["hasf0_logits"]) > 2.5 * 0.25 * float(np.std(g["hasf0_logits"]))
     np.testing.assert_allclose(f0.cpu().numpy()[sure], g["f0"][sure], rtol=0, atol=0.25 * float(np.std(g["f0"])))
     assert codeap.shape == g["codeap"].shape
+
+
+def test_tts_v2_mcep_head_matches_golden():
+    """AlignTextToAudioPredict: predict + mel-cepstrum -> log-spectrum folded into the projection GEMM."""
+    from helpers import golden
+    from voice100_b200.vocoder import AlignTextToAudioPredict
+    g = golden("tts_v2_mcep")
+    V, B, seed = [int(x) for x in g["cfg"]]
+    sd = {k: torch.from_numpy(val) for k, val in synth.audio_v2_state_dict(
+        V, 25, 1, 2, 512, synth.TTS_V2_BASE_DECODER, seed=seed, randomize_ln=True, randomize_norm=True, gain=2.0).items()}
+    model = _load(v2.AlignTextToAudio(V, 25, 1, 2, 512, [list(r) for r in synth.TTS_V2_BASE_DECODER]), sd)
+    wrap = AlignTextToAudioPredict(model).to(DEV)
+    aligntext, lens = torch.from_numpy(g["aligntext"]).to(DEV), torch.from_numpy(g["aligntext_len"])
+    f0, logspc, codeap = wrap(aligntext, lens)
+    ref = torch.from_numpy(g["logspc"])
+    assert logspc.shape == ref.shape == (B, 79, 257) and f0.shape == (B, 79) and codeap.shape == (B, 79, 1)
+    # the spectrum carries a large per-bin offset (the un-normalised c0): compare the variation around the bin means
+    centred = lambda t: t - ref.mean(dim=(0, 1), keepdim=True)
+    rep = orc.parity_report(centred(ref), centred(logspc.cpu()))
+    print("tts v2 mcep->logspc", rep)
+    assert rep["max_abs_rel_std"] < V2_LOGIT_MAX_REL_STD and rep["rms_rel_std"] < V2_LOGIT_RMS_REL_STD, rep
+    # and the un-fused route agrees with the fused head: predict() -> 25 mel-cepstra -> matrix on the host
+    _, mcep, _ = model.predict(aligntext, lens)
+    unfused = mcep.double().cpu() @ torch.from_numpy(orc.mc2sp_matrix(512, 24, 0.410))
+    rep2 = orc.parity_report(centred(ref), centred(unfused.float()))
+    print("  un-fused route", rep2)
+    assert rep2["rms_rel_std"] < V2_LOGIT_RMS_REL_STD

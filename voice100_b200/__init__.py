@@ -17,3 +17,4 @@ from .checkpoint import load_checkpoint  # noqa: F401
 from .align import ctc_best_path_batch  # noqa: F401
 from .v2 import (AudioToAlignText, TextToAlignText, AlignTextToAudio, AsrV2Pipeline,  # noqa: F401
                  ConvLayerBlock, ConvTransposeLayerBlock, get_conv_layers, align_batch_v2)
+from .vocoder import AlignTextToAudioPredict, create_mc2sp_matrix  # noqa: F401
