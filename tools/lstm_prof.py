@@ -39,17 +39,13 @@ fn = _lib.lib().v100_debug_lstm_prof
 fn.argtypes = [ctypes.c_void_p]
 assert fn(buf) == 0
 st = np.array(buf, dtype=np.int64).reshape(64, 12)[2:62]
-names = ["ctl: wait counter", "ctl: TMA h + MMA issue + commit", "gate: commit -> acc in registers",
-         "gate: Gx wait + gate math + h store", "gate: proxy fence", "gate: bar.sync", "gate: red.release",
-         "next step: publish -> control thread starts waiting"]
-d = [st[:, 1] - st[:, 0], st[:, 2] - st[:, 1], st[:, 3] - st[:, 2], st[:, 4] - st[:, 3], st[:, 5] - st[:, 4],
-     st[:, 6] - st[:, 5], st[:, 7] - st[:, 6]]
-step = np.median(st[1:, 0] - st[:-1, 0])
-print(f"B={B} H={H}: median step {step:.0f} ns")
-for n, v in zip(names, d):
-    print(f"  {n:50s} median {np.median(v):7.0f} ns   p90 {np.percentile(v, 90):7.0f}")
-print(f"  {'red.release done -> own counter wait satisfied':50s} median {np.median(st[1:, 1] - st[:-1, 7]):7.0f} ns")
-print(f"  {'  counter seen -> all TMA loads issued':50s} median {np.median(st[:, 8] - st[:, 1]):7.0f} ns")
-print(f"  {'  loads issued -> first 16 KB box landed':50s} median {np.median(st[:, 9] - st[:, 8]):7.0f} ns")
-print(f"  {'  first box -> last box landed':50s} median {np.median(st[:, 10] - st[:, 9]):7.0f} ns")
-print(f"  {'  last box -> MMAs issued + commit':50s} median {np.median(st[:, 2] - st[:, 10]):7.0f} ns")
+# slots: 0 poll start, 1 counter seen, 8 TMA issued, 10 tile landed, 2 MMAs committed, 3 accumulator in registers,
+# 9 activations written, 11 exchange barrier passed, 4 cell update + h stores done, 5 fence, 6 barrier, 7 released
+seq = [("counter seen -> TMA issued", (1, 8)), ("TMA issued -> both halves landed", (8, 10)),
+       ("MMAs issued + commit", (10, 2)), ("commit -> accumulator in registers", (2, 3)),
+       ("+ Gx, activation -> exchange buffer", (3, 9)), ("exchange barrier", (9, 11)),
+       ("cell update + h stores", (11, 4)), ("proxy fence", (4, 5)), ("barrier", (5, 6)), ("red.release", (6, 7))]
+print(f"B={B} H={H}: median step {np.median(st[1:, 0] - st[:-1, 0]):.0f} ns")
+print(f"  {'release done -> counter seen (next step)':45s} {np.median(st[1:, 1] - st[:-1, 7]):7.0f} ns")
+for name, ab in seq:
+    print(f"  {name:45s} {np.median(st[:, ab[1]] - st[:, ab[0]]):7.0f} ns")

@@ -47,13 +47,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* m, CUtensorMapDataType type, const void* base, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box,
-                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                  const cuuint64_t* strides, const cuuint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t ones[3] = {1, 1, 1};
   CUresult r = fn(m, type, rank, const_cast<void*>(base), dims, strides, box, ones,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu strides %llu)",
@@ -67,13 +66,6 @@ int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int
   const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
   const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
   return encode(m, type, base, 2, dims, strides, box);
-}
-
-int make_tmap_2d_plain(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1) {
-  const cuuint64_t dims[2] = {cuuint64_t(d0), cuuint64_t(d1)};
-  const cuuint64_t strides[1] = {cuuint64_t(stride1_bytes)};
-  const cuuint32_t box[2] = {cuuint32_t(box0), cuuint32_t(box1)};
-  return encode(m, type, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,

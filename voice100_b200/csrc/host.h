@@ -23,8 +23,6 @@ int num_sms();
 
 // 16-bit tensor maps, 128-byte swizzle, zero fill out of bounds.  Dimensions innermost first.
 int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
-// same, without swizzle (rows land in shared memory as plain row-major lines)
-int make_tmap_2d_plain(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
                  int64_t stride2_bytes, int box0, int box1);
 
