@@ -5,5 +5,5 @@ set -e
 REV=$1; OUT=$(realpath -m $2); TMP=$(mktemp -d)
 git archive $REV voice100_b200/csrc include | tar -x -C $TMP
 cd $TMP/voice100_b200/csrc
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --compiler-options -fPIC -shared -o $OUT api.cu conv_gemm.cu dwconv.cu logmel.cu misc.cu
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --compiler-options -fPIC -shared -o $OUT $(ls *.cu)
 rm -rf $TMP; echo built $OUT from $REV
