@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   uint64_t* res_bar = bars + 2 * STAGES + 4;    // [8 epilogue warps][2 buffers]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * kEpiWarps);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -249,7 +249,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
       const bool relu6 = p.act == V100_ACT_RELU6;
       const bool f16 = p.dtype == DT_F16;
 
-      if (p.has_res && lane == 0 && tile0 < p.num_tiles) {
+      // one elected lane of the (converged) warp issues every TMA operation of this warp; bulk async-groups are
+      // per thread, so the same lane also commits and waits
+      const bool issuer = elect_one();
+      if (p.has_res && issuer && tile0 < p.num_tiles) {
         const int r = tile0 / p.m_tiles;
         mbar_expect_tx(&rbar[0], kWarpChunkBytes);
         tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + h * 64,
@@ -363,7 +366,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           }
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) {
+          if (issuer) {
             tma_store_3d(&tm_y, stg + buf * kWarpChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
             tma_store_commit();
             tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
@@ -384,7 +387,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
         sc = sc_next;
         sh = sh_next;
       }
-      if (lane == 0) tma_store_wait_all<0>();
+      if (issuer) tma_store_wait_all<0>();
     } else {
       // fp32 NCW direct store, bias only; group g owns columns [g*BLOCK_N/2, (g+1)*BLOCK_N/2)
       int iter = 0;
