@@ -9,7 +9,26 @@ import voice100_b200 as v
 from voice100_b200 import kernels as K, synth
 dev = "cuda"
 torch.manual_seed(0)
-MODE = os.environ.get("SAN_MODE", "all")   # all | nogemm (everything that does not use TMA/mbarrier/tcgen05)
+MODE = os.environ.get("SAN_MODE", "all")   # all | nogemm (everything that does not use TMA/mbarrier/tcgen05) | v2
+if MODE == "v2":
+    # the v2 kernels: tap stack + GEMM, LayerNorm/GELU, layout changes, the LSTM pair kernel (ragged, 2 groups)
+    m = v.AudioToAlignText(64, [[128, False, 3, 2, 1, False], [128, False, 5, 1, 2, True]], 2, 128, 29).to(dev).eval()
+    B = 70
+    audio = torch.randn(B, 37, 64, device=dev)
+    audio_len = torch.randint(1, 38, (B,), device=dev)
+    audio_len[0] = 37
+    for dtype in (torch.bfloat16, torch.float16):
+        m.set_storage_dtype(dtype)
+        logits, lens = m(audio, audio_len)
+        tok, _ = m.greedy(audio, audio_len)
+    al = v.TextToAlignText(29, 2, 64, 2).to(dev).eval()
+    al(torch.randint(1, 29, (3, 11), device=dev), torch.tensor([11, 4, 7]))
+    tts = v.AlignTextToAudio(29, 25, 1, 2, 64, [[64, False, 5, 1, 2, False], [64, True, 5, 2, 2, False], [64, False, 5, 1, 2, False]]).to(dev).eval()
+    tts.predict(torch.randint(1, 29, (3, 21), device=dev), torch.tensor([21, 9, 14]))
+    v.AlignTextToAudioPredict(tts).to(dev)(torch.randint(1, 29, (3, 21), device=dev), torch.tensor([21, 9, 14]))
+    torch.cuda.synchronize()
+    print("sanitize_small (v2) done")
+    sys.exit(0)
 if MODE == "nogemm":
     tr = v.MelSpectrogramAudioTransform().to(dev)
     wav = 0.1 * torch.randn(3, 16000 * 2 + 123, device=dev)
