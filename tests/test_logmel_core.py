@@ -15,18 +15,27 @@ HARNESS = r"""
 #include "logmel_core.h"
 #include <cmath>
 using namespace v100;
+extern "C" void fft16_host(float* v) { fft16(reinterpret_cast<cpx*>(v)); }
+// the 16-thread register decomposition of logmel.cu, thread by thread, with its shared-memory indexing
 extern "C" void rfft512_power_host(const float* frame, float* power) {
   static cpx tw[512];
   for (int k = 0; k < 512; ++k) { tw[k].x = (float)cos(-2.0*M_PI*k/512.0); tw[k].y = (float)sin(-2.0*M_PI*k/512.0); }
-  cpx A[256], B[256];
-  for (int n = 0; n < 256; ++n) { A[fswz(n)].x = frame[2*n]; A[fswz(n)].y = frame[2*n+1]; }
-  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 256, 1, i, fft256_twiddles(1, i, tw));
-  for (int i = 0; i < 64; ++i) fft256_butterfly(B, A, 64, 4, i, fft256_twiddles(4, i, tw));
-  for (int i = 0; i < 64; ++i) fft256_butterfly(A, B, 16, 16, i, fft256_twiddles(16, i, tw));
-  for (int i = 0; i < 64; ++i) fft256_butterfly_last(B, A, i);
-  for (int k = 0; k <= 256; ++k) power[k] = rfft512_power(A, k, tw[k]);
+  cpx E[16 * 17], Z[256];
+  for (int q = 0; q < 16; ++q) {            // thread q: FFT over r, twiddle, write column q of the exchange
+    cpx v[16];
+    for (int r = 0; r < 16; ++r) { const int n = q + 16 * r; v[r] = cpx{frame[2 * n], frame[2 * n + 1]}; }
+    fft16(v);
+    for (int k1 = 0; k1 < 16; ++k1) E[k1 * 17 + q] = cmul(v[k1], tw[(2 * q * k1) & 511]);
+  }
+  for (int k1 = 0; k1 < 16; ++k1) {         // thread k1: FFT over q -> Z[k1 + 16 k2]
+    cpx v[16];
+    for (int q = 0; q < 16; ++q) v[q] = E[k1 * 17 + q];
+    fft16(v);
+    for (int k2 = 0; k2 < 16; ++k2) Z[k1 + 16 * k2] = v[k2];
+  }
+  for (int k = 0; k < 256; ++k) power[k] = rfft512_power_pair(Z[k], Z[(256 - k) & 255], tw[k]);
+  power[256] = rfft512_power_pair(Z[0], Z[0], tw[256]);
 }
-extern "C" int fswz_host(int i) { return fswz(i); }
 """
 
 
@@ -63,31 +72,32 @@ def test_rfft512_power_matches_numpy(host_fft):
     assert p.argmax() == 37 and abs(p[37] - 256.0 ** 2) < 1e-2 * 256.0 ** 2       # one bin, N/2 amplitude
 
 
-def test_swizzle_is_a_conflict_free_bijection(host_fft):
+def test_fft16_matches_numpy(host_fft):
     import glob
     so = glob.glob(os.path.join(tempfile.gettempdir(), "*", "h.so"))
     lib = ctypes.CDLL(sorted(so, key=os.path.getmtime)[-1])
-    f = [lib.fswz_host(i) for i in range(256)]
-    assert sorted(f) == list(range(256))
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        v = (rng.standard_normal(16) + 1j * rng.standard_normal(16)).astype(np.complex64)
+        buf = v.view(np.float32).copy()
+        lib.fft16_host(buf.ctypes.data_as(ctypes.c_void_p))
+        np.testing.assert_allclose(buf.view(np.complex64), np.fft.fft(v.astype(np.complex128)), atol=2e-6 * 16)
 
-    def wavefronts(addrs):           # 64-bit accesses: two half-warps, 16 bank pairs
-        tot = 0
-        for half in (addrs[:16], addrs[16:]):
-            banks = {}
-            for a in set(half):
-                banks.setdefault(a % 16, set()).add(a)
-            tot += max(len(v) for v in banks.values())
-        return tot
-    n, s = 256, 1
-    while n > 1:
-        m = n // 4
-        for base in (0, 32):
-            idx = [base + l for l in range(32)]
-            for j in range(4):
-                assert wavefronts([f[i % s + s * (i // s + j * m)] for i in idx]) == 2       # reads
-                assert wavefronts([f[i % s + s * (4 * (i // s) + j)] for i in idx]) == 2     # writes
-        n //= 4
-        s *= 4
+
+def test_shared_memory_accesses_are_conflict_free():
+    """The kernel's 64-bit shared-memory accesses of one half-warp (16 lanes x 8 bytes = one 128-byte wavefront when
+    the 16 lanes hit 16 different bank pairs): exchange writes E[k1*17 + q], exchange reads E[q*17 + qq], spectrum
+    writes Z[q + 16 k2] and partner reads Z[(256 - q - 16 k2) & 255]."""
+    def bank_pairs(idx):
+        return len({i % 16 for i in idx})
+    for k1 in range(16):
+        assert bank_pairs([k1 * 17 + q for q in range(16)]) == 16
+    for qq in range(16):
+        assert bank_pairs([q * 17 + qq for q in range(16)]) == 16      # what the padding to 17 buys
+        assert bank_pairs([q * 16 + qq for q in range(16)]) == 1       # ... and what 16 would cost
+    for k2 in range(16):
+        assert bank_pairs([q + 16 * k2 for q in range(16)]) == 16
+        assert bank_pairs([(256 - q - 16 * k2) & 255 for q in range(16)]) == 16
 
 
 def test_frame_pipeline_matches_oracle(host_fft):

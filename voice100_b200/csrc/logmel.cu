@@ -3,10 +3,10 @@
 //
 // Replaces reflect-pad + unfold + window + cuFFT R2C + abs/pow + sgemm + add/log + transpose
 // (>= 6 library launches, and a 257-bin complex spectrum written to and read back from HBM).
-// One warp transforms one frame (radix-4 Stockham FFT in shared memory, see logmel_core.h); a CTA of
-// 8 warps produces a [64 mel x 64 frame] tile so that the NCW output rows are written as full
-// 128-byte lines.  The kernel is bound by FFT arithmetic and shared-memory traffic, not by HBM
-// (64 KB in + 12.8 KB out per audio-second); see DESIGN.md for its roofline discussion.
+// Sixteen threads transform one frame: 256 = 16 x 16, two 16-point FFTs in registers with one transpose
+// through shared memory in between (logmel_core.h); a CTA of 8 warps produces a [64 mel x 64 frame] tile so
+// that the NCW output rows are written as full 128-byte lines.  The kernel is bound by FFT arithmetic and
+// shared-memory traffic, not by HBM (64 KB in + 12.8 KB out per audio-second); see DESIGN.md.
 #include "common.cuh"
 #include "host.h"
 #include "logmel_core.h"
@@ -18,126 +18,144 @@ constexpr int kMelFrames = 64;  // frames per CTA
 constexpr int kNMels = 64;
 constexpr int kNFft = 512, kWin = 400, kHop = 160, kWinLeft = (kNFft - kWin) / 2;  // data_modules.py:266-269
 constexpr int kMelMaxTaps = 24;   // longest mel filter (bins); the HTK bank at 512/16 kHz/64 needs 20
-constexpr int kMelSmemBytes = 512 * 8 + 2 * kMelWarps * 256 * 8 + kNMels * (kMelFrames + 1) * 4 + kWin * 4 +
-                              kMelMaxTaps * kNMels * 4;
+// shared memory: twiddles, window pairs, mel weights, output tile, and per half-warp an exchange buffer (16 x 17
+// complex, reused for the 257 power bins) and the packed spectrum Z (256 complex)
+constexpr int kMelExch = 16 * 17;
+constexpr int kMelSmemBytes = 512 * 8 + 256 * 8 + kMelMaxTaps * kNMels * 4 + kNMels * (kMelFrames + 1) * 4 +
+                              2 * kMelWarps * (kMelExch + 256) * 8;
 
-__global__ void __launch_bounds__(kMelWarps * 32, 3)
+__global__ void __launch_bounds__(kMelWarps * 32, 2)
 logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, long long wav_pitch,
               const int32_t* __restrict__ fb_start, const int32_t* __restrict__ fb_count,
               const int32_t* __restrict__ fb_off, const float* __restrict__ fb_w, float log_offset, void* out, int T,
               long long out_pitch, int out_mode) {
   extern __shared__ __align__(16) uint8_t mel_smem[];
-  cpx* tw = reinterpret_cast<cpx*>(mel_smem);                                  // [512]
-  cpx (*bufA)[256] = reinterpret_cast<cpx (*)[256]>(tw + 512);                  // [kMelWarps][256]
-  cpx (*bufB)[256] = bufA + kMelWarps;                                          // [kMelWarps][256]
-  float (*tile)[kMelFrames + 1] = reinterpret_cast<float (*)[kMelFrames + 1]>(bufB + kMelWarps);  // [64][65]
-  float* win = reinterpret_cast<float*>(tile + kNMels);                        // [kWin]
-  float (*melw)[kNMels] = reinterpret_cast<float (*)[kNMels]>(win + kWin);      // [kMelMaxTaps][64] tap-major
+  cpx* tw = reinterpret_cast<cpx*>(mel_smem);                                  // [512] exp(-2 pi i k / 512)
+  float2* win2 = reinterpret_cast<float2*>(tw + 512);                          // [256] window of samples 2n, 2n+1
+  float (*melw)[kNMels] = reinterpret_cast<float (*)[kNMels]>(win2 + 256);      // [kMelMaxTaps][64] tap-major
+  float (*tile)[kMelFrames + 1] = reinterpret_cast<float (*)[kMelFrames + 1]>(melw + kMelMaxTaps);  // [64][65]
+  cpx* exch = reinterpret_cast<cpx*>(tile + kNMels);                           // [16 half-warps][16 x 17]
+  cpx* zbuf = exch + 2 * kMelWarps * kMelExch;                                 // [16 half-warps][256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * kMelFrames;
 
   for (int k = threadIdx.x; k < 512; k += blockDim.x) {
-    float s, c;
-    sincospif(-float(k) / 256.0f, &s, &c);  // exp(-2*pi*i*k/512)
-    tw[k] = cpx{c, s};
+    float sn, cs;
+    sincospif(-float(k) / 256.0f, &sn, &cs);  // exp(-2*pi*i*k/512)
+    tw[k] = cpx{cs, sn};
   }
-  for (int i = threadIdx.x; i < kWin; i += blockDim.x) win[i] = 0.5f - 0.5f * cospif(float(2 * i) / float(kWin));
+  for (int n = threadIdx.x; n < 256; n += blockDim.x) {   // periodic Hann(400) centred in the 512 frame
+    float w2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = 2 * n + h - kWinLeft;
+      w2[h] = (m >= 0 && m < kWin) ? 0.5f - 0.5f * cospif(float(2 * m) / float(kWin)) : 0.0f;
+    }
+    win2[n] = make_float2(w2[0], w2[1]);
+  }
   for (int i = threadIdx.x; i < kMelMaxTaps * kNMels; i += blockDim.x) {   // melw[tap][filter], zero padded
     const int tap = i / kNMels, m = i - tap * kNMels;
     melw[tap][m] = tap < __ldg(fb_count + m) ? __ldg(fb_w + __ldg(fb_off + m) + tap) : 0.0f;
   }
   __syncthreads();
 
-  // ---- per-lane constants, reused for the 8 frames this warp transforms ----
-  const tw3 t1a = fft256_twiddles(1, lane, tw), t1b = fft256_twiddles(1, lane + 32, tw);
-  const tw3 t2a = fft256_twiddles(4, lane, tw), t2b = fft256_twiddles(4, lane + 32, tw);
-  const cpx wlane = tw[lane];                  // exp(-2*pi*i*(lane + 32 i)/512) = wlane * tw[32 i]
-  float wv[16];                                // window taps of the samples this lane loads (0 outside 56..455)
+  // ---- sixteen threads per frame (logmel_core.h, "register-resident variant"); a warp works on two frames ----
+  const int q = lane & 15, hw = warp * 2 + (lane >> 4);
+  cpx* E = exch + hw * kMelExch;
+  cpx* Z = zbuf + hw * 256;
+  float* P = reinterpret_cast<float*>(E);  // the power spectrum reuses the exchange buffer (257 <= 544 floats)
+  cpx twq[16];                             // W256^(q k1), constant per thread
 #pragma unroll
-  for (int u = 0; u < 8; ++u)
+  for (int k1 = 0; k1 < 16; ++k1) twq[k1] = tw[(2 * q * k1) & 511];
+  const cpx wq = tw[q];                    // exp(-2 pi i (q + 16 k2) / 512) = wq * exp(-2 pi i k2 / 32)
+  int s0[4], cmax[4];                      // this thread's mel filters q + 16 i
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int m = 2 * (lane + 32 * u) + h;
-      wv[2 * u + h] = (m >= kWinLeft && m < kWinLeft + kWin) ? win[m - kWinLeft] : 0.0f;
-    }
-  const int s0a = __ldg(fb_start + lane), s0b = __ldg(fb_start + lane + 32);
-  const int cnta = __ldg(fb_count + lane), cntb = __ldg(fb_count + lane + 32);
-  // filters 0..31 are short (<= 6 bins), filters 32..63 long (<= 20): separate trip counts
-  const int cnt_max_a = __reduce_max_sync(0xffffffffu, cnta), cnt_max_b = __reduce_max_sync(0xffffffffu, cntb);
+  for (int i = 0; i < 4; ++i) {
+    s0[i] = __ldg(fb_start + q + 16 * i);
+    int c = __ldg(fb_count + q + 16 * i);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    cmax[i] = c;                           // trip count of the 16 filters handled together
+  }
 
   const int L = len[b];
   const int n_frames = 1 + L / kHop;
   const float* x = wav + static_cast<long long>(b) * wav_pitch;
   const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
   const float blank = out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(log_offset);
-  cpx* A = bufA[warp];
-  cpx* Bf = bufB[warp];
-  float* P = reinterpret_cast<float*>(Bf);  // power spectrum reuses the ping-pong buffer (257 <= 512 floats)
 
-  for (int fi = 0; fi < kMelFrames / kMelWarps; ++fi) {
-    const int fl = warp * (kMelFrames / kMelWarps) + fi;
+  for (int fi = 0; fi < kMelFrames / (2 * kMelWarps); ++fi) {
+    const int fl = hw * (kMelFrames / (2 * kMelWarps)) + fi;
     const int t = f0 + fl;
-    if (t >= n_frames) {
-      tile[lane][fl] = blank;
-      tile[lane + 32][fl] = blank;
+    const bool valid = t < n_frames;
+    if (!__any_sync(0xffffffffu, valid)) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tile[q + 16 * i][fl] = blank;
       continue;
     }
-    // frame t covers reflect-padded samples [160 t, 160 t + 512) = clip samples 160 t - 256 + m
+    // frame t covers reflect-padded samples [160 t, 160 t + 512) = clip samples 160 t - 256 + m;
+    // this thread takes the complex points n = q + 16 r (samples 2n, 2n+1); the window is zero for n < 28, n >= 228
+    cpx v[16];
     const int base = kHop * t - kNFft / 2;
-    if (vec_ok && base + kWinLeft >= 0 && base + kWinLeft + kWin <= L) {
-      // interior frame: the 400 windowed samples are in range, 8-byte aligned pairs
+    v[0] = cpx{0.0f, 0.0f};
+    v[15] = cpx{0.0f, 0.0f};
+    if (valid && vec_ok && base + kWinLeft >= 0 && base + kWinLeft + kWin <= L) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int n = lane + 32 * u;
-        float2 v = make_float2(0.0f, 0.0f);
-        if (2 * n >= kWinLeft && 2 * n < kWinLeft + kWin) v = __ldg(reinterpret_cast<const float2*>(x + base + 2 * n));
-        A[fswz(n)] = cpx{v.x * wv[2 * u], v.y * wv[2 * u + 1]};
+      for (int r = 1; r < 15; ++r) {
+        const int n = q + 16 * r;
+        float2 sv = make_float2(0.0f, 0.0f);
+        if (n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) sv = __ldg(reinterpret_cast<const float2*>(x + base + 2 * n));
+        const float2 w2 = win2[n];
+        v[r] = cpx{sv.x * w2.x, sv.y * w2.y};
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int n = lane + 32 * u;
-        float v[2];
+      for (int r = 1; r < 15; ++r) {
+        const int n = q + 16 * r;
+        const float2 w2 = win2[n];
+        float sv[2] = {0.0f, 0.0f};
+        if (valid && n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int m = 2 * n + h;
-          float sv = 0.0f;
-          if (m >= kWinLeft && m < kWinLeft + kWin) {
-            int i = base + m;
+          for (int h = 0; h < 2; ++h) {
+            int i = base + 2 * n + h;
             i = i < 0 ? -i : i;
             i = i >= L ? 2 * (L - 1) - i : i;
-            sv = __ldg(x + i) * wv[2 * u + h];
+            sv[h] = __ldg(x + i);
           }
-          v[h] = sv;
         }
-        A[fswz(n)] = cpx{v[0], v[1]};
+        v[r] = cpx{sv[0] * w2.x, sv[1] * w2.y};
       }
     }
-    __syncwarp();
-    fft256_butterfly(A, Bf, 256, 1, lane, t1a);   fft256_butterfly(A, Bf, 256, 1, lane + 32, t1b);   __syncwarp();
-    fft256_butterfly(Bf, A, 64, 4, lane, t2a);    fft256_butterfly(Bf, A, 64, 4, lane + 32, t2b);    __syncwarp();
-    // pass 3 has only 4 distinct twiddle sets per warp: broadcast shared loads instead of 12 more registers
-    fft256_butterfly(A, Bf, 16, 16, lane, fft256_twiddles(16, lane, tw));
-    fft256_butterfly(A, Bf, 16, 16, lane + 32, fft256_twiddles(16, lane + 32, tw));
-    __syncwarp();
-    fft256_butterfly_last(Bf, A, lane);           fft256_butterfly_last(Bf, A, lane + 32);           __syncwarp();
+    fft16(v);                                              // over r:  Y[q][k1]
+    E[q] = v[0];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      // exp(-2*pi*i*(32 i)/512) = exp(-i*pi*i/8): compile-time constants
-      float ci, si;
-      sincospif(-float(i) / 8.0f, &si, &ci);
-      P[lane + 32 * i] = rfft512_power(A, lane + 32 * i, cmul(wlane, cpx{ci, si}));
+    for (int k1 = 1; k1 < 16; ++k1) E[k1 * 17 + q] = cmul(v[k1], twq[k1]);
+    __syncwarp();
+#pragma unroll
+    for (int qq = 0; qq < 16; ++qq) v[qq] = E[q * 17 + qq]; // this thread is now k1 = q
+    fft16(v);                                              // over q:  v[k2] = Z[q + 16 k2]
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) Z[q + 16 * k2] = v[k2];
+    __syncwarp();                                          // (every lane is past its reads of E: P may overwrite it)
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+      float ck, sk;
+      sincospif(-float(k2) / 16.0f, &sk, &ck);             // exp(-2 pi i 16 k2 / 512): compile-time constants
+      const int k = q + 16 * k2;
+      P[k] = rfft512_power_pair(v[k2], Z[(256 - k) & 255], cmul(wq, cpx{ck, sk}));
     }
-    if (lane == 0) P[256] = rfft512_power(A, 256, cpx{-1.0f, 0.0f});
+    if (q == 0) P[256] = rfft512_power_pair(v[0], v[0], cpx{-1.0f, 0.0f});
     __syncwarp();
-    float acca = 0.0f, accb = 0.0f;   // melw is zero past each filter's own length; P stays in range
-    for (int i = 0; i < cnt_max_a; ++i) acca = fmaf(melw[i][lane], P[min(s0a + i, 256)], acca);
-    for (int i = 0; i < cnt_max_b; ++i) accb = fmaf(melw[i][lane + 32], P[min(s0b + i, 256)], accb);
-    tile[lane][fl] = out_mode == V100_MEL_POWER_F32_NCW ? acca : logf(acca + log_offset);
-    tile[lane + 32][fl] = out_mode == V100_MEL_POWER_F32_NCW ? accb : logf(accb + log_offset);
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = q + 16 * i;
+      float acc = 0.0f;                                    // melw is zero past each filter's own length; P stays in range
+      for (int tap = 0; tap < cmax[i]; ++tap) acc = fmaf(melw[tap][m], P[min(s0[i] + tap, 256)], acc);
+      tile[m][fl] = !valid ? blank : (out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + log_offset));
+    }
+    __syncwarp();                                          // P (= E) is free for the next frame
   }
   __syncthreads();
 
