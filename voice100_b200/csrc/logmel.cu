@@ -20,7 +20,8 @@ constexpr int kNFft = 512, kWin = 400, kHop = 160, kWinLeft = (kNFft - kWin) / 2
 constexpr int kMelMaxTaps = 24;   // longest mel filter (bins); the HTK bank at 512/16 kHz/64 needs 20
 // shared memory: twiddles, window pairs, mel weights, output tile, and per half-warp an exchange buffer (16 x 17
 // complex, reused for the 257 power bins) and the packed spectrum Z (256 complex)
-constexpr int kMelExch = 16 * 17;
+constexpr int kMelExch = 16 * 17 + 8;  // + 8: consecutive half-warps' buffers start 16 banks apart, so the 32-bit
+                                       // power-spectrum accesses of the two frames of a warp do not collide
 constexpr int kMelSmemBytes = 512 * 8 + 256 * 8 + kMelMaxTaps * kNMels * 4 + kNMels * (kMelFrames + 1) * 4 +
                               2 * kMelWarps * (kMelExch + 256) * 8;
 
@@ -87,7 +88,8 @@ logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, lo
   const float blank = out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(log_offset);
 
   for (int fi = 0; fi < kMelFrames / (2 * kMelWarps); ++fi) {
-    const int fl = hw * (kMelFrames / (2 * kMelWarps)) + fi;
+    // the two half-warps of a warp take frames 16 apart: their tile[mel][frame] stores land 16 banks apart
+    const int fl = 16 * (2 * (fi >> 1) + (hw & 1)) + 2 * (hw >> 1) + (fi & 1);
     const int t = f0 + fl;
     const bool valid = t < n_frames;
     if (!__any_sync(0xffffffffu, valid)) {
