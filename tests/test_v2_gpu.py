@@ -94,7 +94,9 @@ LSTM_RMS = {torch.bfloat16: 0.0015, torch.float16: 0.0003}
 
 
 @pytest.mark.parametrize("B,T,I,H,ragged", [(3, 20, 64, 64, True), (5, 37, 128, 256, True), (130, 12, 64, 128, True),
-                                           (2, 60, 512, 512, False), (260, 9, 64, 512, True), (1, 1, 64, 64, False)])
+                                           (2, 60, 512, 512, False), (260, 9, 64, 512, True), (1, 1, 64, 64, False),
+                                           (65, 2, 64, 192, True), (7, 33, 192, 320, True), (70, 5, 64, 448, True),
+                                           (600, 3, 64, 128, True)])
 def test_lstm_layer_matches_oracle(B, T, I, H, ragged):
     g = np.random.Generator(np.random.PCG64(B * 1000 + T))
     lengths = [int(n) for n in g.integers(1, T + 1, size=B)] if ragged else [T] * B
