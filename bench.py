@@ -375,17 +375,23 @@ def run_asr_v2(args):
     torch.cuda.synchronize()
     ev, _lib.tracer = _lib.tracer.ev, None
     launch_ms = [[name.replace("v100_", ""), round(s.elapsed_time(e), 4)] for name, s, e in ev]
-    # end to end: pinned host waveforms in, host tokens out
-    wav_h = wavs[0].cpu().pin_memory()
+    # end to end: pinned host waveforms in, host tokens out; batch i+1 uploads while batch i computes
+    host_wav = [w.cpu().pin_memory() for w in wavs]
     len_h = lengths.cpu().pin_memory()
-    Ke = max(2, min(K, 5))
-    tok_h = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+    for i in range(4):
+        pipe.transcribe_host(host_wav[i & 1], len_h, device=dev, chunks=1)
+    Ke = max(3, K)
     t0 = time.perf_counter()
-    for _ in range(Ke):
-        tk, _ = pipe(wav_h.to(dev, non_blocking=True), len_h.to(dev, non_blocking=True))
-        tok_h.copy_(tk, non_blocking=True)
-        torch.cuda.synchronize()
+    prev = None
+    for i in range(Ke):
+        ticket = pipe.submit_host(host_wav[i & 1], len_h, device=dev, chunks=1)
+        if prev is not None:
+            tok_h, _ = prev.result()
+        prev = ticket
+    tok_h, _ = prev.result()
+    torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / Ke
+    wav_h = host_wav[0]
     print(json.dumps({
         "metric": "asr_audio_seconds_per_second", "value": round(audio_seconds / (ms * 1e-3), 1), "unit": "audio-s/s",
         "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms, 4), "higher_is_better": True,

@@ -165,9 +165,13 @@ def test_asr_v2_matches_golden(name, dtype):
     scale = 1.0 if dtype == torch.bfloat16 else 0.25
     assert rep["max_abs_rel_std"] < V2_LOGIT_MAX_REL_STD * scale and rep["rms_rel_std"] < V2_LOGIT_RMS_REL_STD * scale, rep
     # greedy tokens through the fused pipeline (log-mel on the device, argmax without materialising logits)
-    tokens, out_len = v2.AsrV2Pipeline(tr, model)(wav.to(DEV), lens)
+    pipe = v2.AsrV2Pipeline(tr, model)
+    tokens, out_len = pipe(wav.to(DEV), lens)                      # [B, T'] like AsrPipeline
     assert out_len.cpu().tolist() == g["logits_len"].tolist()
-    tok = tokens[: ref.shape[0]].cpu()
+    tok = tokens.t()[: ref.shape[0]].cpu()
+    # pinned-host streaming form (CUDA graphs on alternating buffer sets) returns the same tokens
+    tok_h, len_h = pipe.transcribe_host(wav.pin_memory(), lens.cpu().pin_memory(), device=DEV, chunks=1)
+    assert torch.equal(tok_h, tokens.cpu()) and len_h.tolist() == g["logits_len"].tolist()
     margin = 2.5 * rep["max_abs"]
     top2 = ref.topk(2, dim=-1).values
     sure = (top2[..., 0] - top2[..., 1]) > margin

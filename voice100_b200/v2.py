@@ -21,6 +21,7 @@ from torch import nn
 
 from . import kernels as K
 from ._lib import V100Error
+from .asr import AsrPipeline
 from .blocks import PreparedCache, StorageDtypeMixin, require_eval_cuda
 from .tts import WORLDNorm
 
@@ -191,15 +192,20 @@ class AudioToAlignText(StorageDtypeMixin, nn.Module):
         return tokens.view(tm.T, tm.Bp)[:, :tm.B], x_len
 
 
-class AsrV2Pipeline:
-    """waveform -> tokens for AudioToAlignText: log-mel, conv blocks, LSTM stack, head and argmax on libv100."""
+class AsrV2Pipeline(AsrPipeline):
+    """waveform -> tokens for AudioToAlignText: log-mel, conv blocks, LSTM stack, head and argmax on libv100.
+    Same interface as AsrPipeline -- `pipe(waveform, lengths) -> (tokens int64 [B, T'], lengths [B])`, `.graphed()`,
+    `.submit_host()/.transcribe_host()` (pinned-host streaming on two alternating buffer sets), `.transcribe_ids()`;
+    `model.greedy` keeps the reference's time-major [T', B] form."""
 
     def __init__(self, transform, model: AudioToAlignText):
         self.transform, self.model = transform, model
 
+    @torch.no_grad()
     def __call__(self, waveform: torch.Tensor, lengths: torch.Tensor):
         feats, audio_len = self.transform.logmel_batch(waveform, lengths, ncw_dtype=self.model.storage_dtype)
-        return self.model.greedy(feats, audio_len)
+        tokens, x_len = self.model.greedy(feats, audio_len)
+        return tokens.t().contiguous(), x_len
 
 
 class TextToAlignText(StorageDtypeMixin, nn.Module):
