@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 3
+#define V100_ABI_VERSION 4
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
@@ -206,6 +206,15 @@ int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, 
 int v100_conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace,
                 void* y, int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad,
                 int dtype, void* stream);
+
+/*
+ * The same nn.Conv1d for stride 1 and padding (k-1)/2 on TIME-MAJOR tensors (x [C_in][T*Bp] -> y [C_out][T*Bp]):
+ * a tap is a shift by (j - pad)*Bp columns, which is a 16-byte aligned TMA box offset, so the k taps accumulate in
+ * one GEMM tile with no workspace and no data movement.  k odd, <= 5; C_in a multiple of 64; Wp and bias as above.
+ * Columns b in [B, Bp) carry conv(0) = bias.
+ */
+int v100_conv1d_tm(const void* x, const void* Wp, const float* bias, void* y, int C_in, int C_out, int T, int Bp,
+                   int k, int dtype, void* stream);
 
 /*
  * transpose -> nn.LayerNorm(C) -> transpose -> gelu of ConvLayerBlock.forward (_layers_v2.py:53-57,84-88):

@@ -42,6 +42,27 @@ def test_conv1d_matches_torch(k, stride, pad, B, C_in, C_out, T):
     assert float((err - ref.abs() * 2.0 ** -8).max()) < 2e-3, float(err.max())
 
 
+@pytest.mark.parametrize("k", [1, 3, 5])
+@pytest.mark.parametrize("B,C_in,C_out,T", [(3, 64, 256, 77), (20, 512, 512, 41), (1, 128, 24, 9)])
+def test_conv1d_time_major_matches_torch(k, B, C_in, C_out, T):
+    """Dense conv evaluated on the time-major tensor: taps are column offsets of (j - pad) * Bp."""
+    x = _q(_rng_t(11, B, C_in, T))
+    w = _q(_rng_t(12, C_out, C_in, k, scale=1.0 / np.sqrt(C_in * k)))
+    bias = _rng_t(13, C_out, scale=0.1)
+    ref = F.conv1d(x, w, bias, stride=1, padding=(k - 1) // 2)
+    tm = K.ncw_to_tm(K.ncw_from_f32(x.to(DEV), torch.bfloat16))
+    wp = w.permute(0, 2, 1).reshape(C_out, k * C_in).to(DEV, torch.bfloat16).contiguous()
+    y = K.conv1d_tm(tm, wp, bias.to(DEV), k)
+    got = K.ncw_to_f32(K.tm_to_ncw(y)).cpu()
+    assert got.shape == ref.shape
+    err = (got - ref).abs()
+    assert float((err - ref.abs() * 2.0 ** -8).max()) < 2e-3, float(err.max())
+    # the padding utterances [B, Bp) see zero input: conv(0) = bias
+    if tm.Bp > B:
+        pad = y.data.float().view(C_out, T, tm.Bp)[:, :, B:].cpu()
+        np.testing.assert_allclose(pad, bias.to(torch.bfloat16).float()[:, None, None].expand_as(pad), atol=1e-6)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,C,T", [(3, 512, 131), (2, 256, 64), (1, 24, 7)])
 def test_layernorm_gelu_matches_torch(dtype, B, C, T):

@@ -31,13 +31,14 @@ SIGNATURES = {
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
     "v100_conv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
+    "v100_conv1d_tm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "v100_layernorm_gelu": [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _i, _p],
     "v100_ncw_to_tm": [_p, _l, _p, _i, _i, _i, _i, _p],
     "v100_tm_to_ncw": [_p, _p, _l, _i, _i, _i, _i, _p],
     "v100_lstm_layer": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 

@@ -172,6 +172,11 @@ int v100_conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bia
                 STREAM(stream));
 }
 
+int v100_conv1d_tm(const void* x, const void* Wp, const float* bias, void* y, int C_in, int C_out, int T, int Bp,
+                   int k, int dtype, void* stream) {
+  return conv1d_tm(x, Wp, bias, y, C_in, C_out, T, Bp, k, dtype, STREAM(stream));
+}
+
 int v100_layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const float* beta, float eps, void* y,
                         int64_t y_pitch, int B, int C, int T, int dtype, void* stream) {
   return layernorm_gelu(x, x_pitch, gamma, beta, eps, y, y_pitch, B, C, T, dtype, STREAM(stream));

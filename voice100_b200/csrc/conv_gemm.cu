@@ -49,6 +49,7 @@ struct GemmParams {
   int m_tiles, t_tiles, num_tiles, k_blocks;
   int n_taps;
   int tap_xrow[kMaxTaps];   // first X channel row of the tap
+  int tap_col[kMaxTaps];    // column (time) offset of the tap; must keep the box 16-byte aligned
   int tap_acc[kMaxTaps];
   const float* scale;
   const float* shift;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
         const int b = r / p.t_tiles;
         const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM;
         for (int tap = 0; tap < p.n_taps; ++tap) {
-          const int t_in0 = t_tile * BLOCK_N + int(cta_rank) * Cfg::kBCols;
+          const int t_in0 = t_tile * BLOCK_N + int(cta_rank) * Cfg::kBCols + p.tap_col[tap];
           const int xrow0 = p.tap_xrow[tap];
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -579,6 +580,44 @@ int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* b
   p.y32 = y; p.y32_pitch = y_pitch;
   if (bn == 256) return launch_gemm<256, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
   return launch_gemm<128, 1, OUT_F32, 4>(tw, tx, tx, tx, p, stream);
+}
+
+// Dense Conv1d, stride 1, "same" padding, on the TIME-MAJOR layout x[c][t*Bp + b] (seq.cu): a tap is a shift by a
+// whole number of Bp-column groups, i.e. a 16-byte aligned column offset of the TMA box, and what falls off either
+// end of the tensor is exactly the conv's zero padding -- k taps accumulate into one tile with no data movement.
+int conv1d_tm(const void* x, const void* Wp, const float* bias, void* y, int C_in, int C_out, int T, int Bp, int k,
+              int dtype, cudaStream_t stream) {
+  if (int e = check_dtype(dtype, "conv1d_tm")) return e;
+  if (C_in <= 0 || C_out <= 0 || T <= 0 || Bp <= 0) return fail(V100_E_INVALID, "conv1d_tm: non-positive size");
+  if (k < 1 || k > kMaxTaps || (k & 1) == 0) return fail(V100_E_UNSUPPORTED, "conv1d_tm: kernel size %d (odd, <= %d)", k, kMaxTaps);
+  if (C_in % 64 != 0) return fail(V100_E_UNSUPPORTED, "conv1d_tm: C_in=%d must be a multiple of 64", C_in);
+  if ((Bp & 7) != 0) return fail(V100_E_INVALID, "conv1d_tm: Bp must be a multiple of 8");
+  if (bias == nullptr || Wp == nullptr) return fail(V100_E_INVALID, "conv1d_tm: null W/bias");
+  const long long N = static_cast<long long>(T) * Bp;
+  if (N > 2147483647LL - 512) return fail(V100_E_UNSUPPORTED, "conv1d_tm: T*Bp too large");
+  if (int e = check_ncw(x, N, int(N), "conv1d_tm x")) return e;
+  if (int e = check_ncw(y, N, int(N), "conv1d_tm y")) return e;
+  const int bn = pick_block_n(int(N));
+  CUtensorMap tw, tx, ty;
+  if (int e = make_tmap_2d(&tw, tmap_type(dtype), Wp, int64_t(C_in) * k, C_out, int64_t(C_in) * k * 2, 64, 128)) return e;
+  if (int e = make_tmap_3d(&tx, tmap_type(dtype), x, N, C_in, 1, N * 2, int64_t(C_in) * N * 2, 64, 64)) return e;
+  if (int e = make_tmap_3d(&ty, tmap_type(dtype), y, N, C_out, 1, N * 2, int64_t(C_out) * N * 2, 64, 32)) return e;
+  GemmParams p{};
+  p.C_out = C_out; p.C_in = C_in; p.B = 1;
+  p.k_blocks = C_in / kBlockK;
+  p.n_taps = k;
+  for (int j = 0; j < k; ++j) { p.tap_xrow[j] = 0; p.tap_col[j] = (j - (k - 1) / 2) * Bp; p.tap_acc[j] = 0; }
+  p.scale = nullptr; p.shift = bias; p.act = V100_ACT_NONE; p.has_res = 0; p.dtype = dtype;
+  p.t_tiles = int((N + bn - 1) / bn);
+  if (bn == 256 && C_out % (2 * kBlockM) == 0) {
+    p.m_tiles = C_out / (2 * kBlockM);
+    p.num_tiles = p.m_tiles * p.t_tiles;
+    return launch_gemm_pair(tw, tx, ty, ty, p, stream);
+  }
+  p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
+  p.num_tiles = p.m_tiles * p.t_tiles;
+  if (bn == 256) return launch_gemm<256, 1, OUT_BF16, 3>(tw, tx, ty, ty, p, stream);
+  return launch_gemm<128, 1, OUT_BF16, 4>(tw, tx, ty, ty, p, stream);
 }
 
 // xs[b][s*C + c][t] = x[b][c][t + 1 - s], s = 0,1,2, zero outside [0,T): the three time-shifted views the

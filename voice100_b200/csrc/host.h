@@ -58,6 +58,8 @@ int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C
 int conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
            int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad, int dtype,
            cudaStream_t stream);
+int conv1d_tm(const void* x, const void* Wp, const float* bias, void* y, int C_in, int C_out, int T, int Bp, int k,
+              int dtype, cudaStream_t stream);
 int layernorm_gelu(const void* x, int64_t x_pitch, const float* gamma, const float* beta, float eps, void* y,
                    int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream);
 int ncw_to_tm(const void* x, int64_t x_pitch, void* y, int B, int C, int T, int Bp, cudaStream_t stream);

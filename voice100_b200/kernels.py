@@ -266,6 +266,21 @@ def ncw_to_tm(x: Ncw) -> Tm:
     return Tm(y, x.B, x.T, Bp)
 
 
+def conv1d_tm(x: Tm, Wp: torch.Tensor, bias: torch.Tensor, k: int) -> Tm:
+    """Dense Conv1d, stride 1, padding (k-1)/2, on a time-major tensor; Wp tap-major [C_out, k*C_in]."""
+    C_out = Wp.shape[0]
+    assert Wp.shape[1] == k * x.C and Wp.dtype == x.data.dtype
+    y = torch.empty((C_out, x.T * x.Bp), device=x.data.device, dtype=x.data.dtype)
+    _lib.call("v100_conv1d_tm", x.data.data_ptr(), Wp.data_ptr(), bias.data_ptr(), y.data_ptr(), x.C, C_out, x.T,
+              x.Bp, k, dt(x.data), _stream())
+    return Tm(y, x.B, x.T, x.Bp)
+
+
+def layernorm_gelu_tm(x: Tm, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> Tm:
+    layernorm_gelu(x.as_ncw(), gamma, beta, eps)
+    return x
+
+
 def tm_to_ncw(x: Tm) -> Ncw:
     y = empty_ncw(x.B, x.C, x.T, x.data.device, x.data.dtype)
     _lib.call("v100_tm_to_ncw", x.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, x.Bp, _stream())

@@ -94,6 +94,28 @@ class ConvLayers(StorageDtypeMixin, nn.Sequential):
             x = K.layernorm_gelu(x, w["gamma"], w["beta"], w["eps"])
         return x
 
+    def run_to_tm(self, x: K.Ncw) -> K.Tm:
+        """Same blocks, result in the time-major layout the recurrent layers want.  The trailing run of stride-1
+        "same"-padded convolutions is evaluated ON the time-major tensor (v100_conv1d_tm: taps are aligned column
+        offsets, no tap stack); the layout change happens in front of it."""
+        ws = self._prepared.get()
+        n_tm = 0
+        for w in reversed(ws):
+            if w["transpose"] or w["stride"] != 1 or 2 * w["pad"] + 1 != w["k"] or w["k"] > 5 or \
+                    (w["wp"].shape[1] // w["k"]) % 64 != 0:
+                break
+            n_tm += 1
+        for w in ws[:len(ws) - n_tm]:
+            if w["transpose"]:
+                x = K.convtranspose_k5s2(x, w["wp"], w["bias"])
+            else:
+                x = K.conv1d(x, w["wp"], w["bias"], w["k"], w["stride"], w["pad"])
+            x = K.layernorm_gelu(x, w["gamma"], w["beta"], w["eps"])
+        tm = K.ncw_to_tm(x)
+        for w in ws[len(ws) - n_tm:]:
+            tm = K.layernorm_gelu_tm(K.conv1d_tm(tm, w["wp"], w["bias"], w["k"]), w["gamma"], w["beta"], w["eps"])
+        return tm
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """fp32 [B, C, T] -> fp32 [B, C', T'] (module-level parity with the reference's nn.Sequential)."""
         require_eval_cuda(self, x)
@@ -167,8 +189,7 @@ class AudioToAlignText(StorageDtypeMixin, nn.Module):
     def _run(self, x: K.Ncw, x_len: torch.Tensor):
         """16-bit Ncw features -> (fp32 head output over the time-major tensor, that tensor's geometry)."""
         w = self._prepared.get()
-        tm = K.ncw_to_tm(self.encoder.run(x))
-        tm = _run_lstm(tm, w["lstm"], x_len)
+        tm = _run_lstm(self.encoder.run_to_tm(x), w["lstm"], x_len)
         return K.conv1x1_f32(tm.as_ncw(), *w["head"]), tm
 
     def forward(self, audio: torch.Tensor, audio_len: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
