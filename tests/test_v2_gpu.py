@@ -263,3 +263,30 @@ def test_tts_v2_mcep_head_matches_golden():
     rep2 = orc.parity_report(centred(ref), centred(unfused.float()))
     print("  un-fused route", rep2)
     assert rep2["rms_rel_std"] < V2_LOGIT_RMS_REL_STD
+
+
+def test_asr_v2_forced_alignment_matches_oracle():
+    """AudioToAlignText.ctc_best_path: model forward + log-softmax + batched Viterbi vs the oracle's restatement of
+    the reference DP run on the oracle's fp32 logits (paths compared where the two logit sets agree on the winner)."""
+    sd, wav, lengths, settings, g = asr_v2_case("asr_v2_en_small_ragged")
+    audio_size, hidden, vocab = [int(x) for x in g["cfg"][:3]]
+    model = _load(v2.AudioToAlignText(audio_size, [list(r) for r in settings], 2, hidden, vocab), sd)
+    model.set_storage_dtype(torch.float16)
+    tr = v.MelSpectrogramAudioTransform().to(DEV)
+    audio, audio_len = tr.logmel_batch(wav.to(DEV), torch.tensor(lengths, dtype=torch.int32, device=DEV))
+    text = torch.from_numpy(synth.text_tokens(3, 9, vocab, seed=7)).to(DEV)
+    text_len = torch.tensor([9, 4, 6])
+    score, hist, path, logits_len = model.ctc_best_path(audio, audio_len, text, text_len)
+    assert path.shape == (3, 76) and logits_len.tolist() == g["logits_len"].tolist()
+    ref_lp = torch.log_softmax(torch.from_numpy(g["logits"]), dim=-1)      # [T', B, V] from the reference
+    for b in range(3):
+        n, m = int(logits_len[b]), int(text_len[b])
+        rs, rh, rp = orc.ctc_best_path(ref_lp[:n, b].numpy(), text[b, :m].cpu().numpy())
+        assert abs(float(score[b]) - float(rs)) < 0.05 * n * 0.01 + 0.05    # fp16 logits vs fp32 logits
+        # every frame's label is one of the text's labels or blank, in order, and the path decodes to the text
+        p = path[b, :n].cpu().numpy()
+        collapsed = [int(x) for i, x in enumerate(p) if x != 0 and (i == 0 or x != p[i - 1] or hist[b, i] != hist[b, i - 1])]
+        assert collapsed == text[b, :m].cpu().tolist()
+        assert (p == rp).mean() > 0.9                                        # same alignment up to near-ties
+    toks = model.ctc_best_path(audio, audio_len)
+    assert toks.shape == (76, 3)

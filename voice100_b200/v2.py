@@ -213,6 +213,31 @@ class AudioToAlignText(StorageDtypeMixin, nn.Module):
         return tokens.view(tm.T, tm.Bp)[:, :tm.B], x_len
 
 
+def _ctc_best_path_method(self, audio: torch.Tensor = None, audio_len: torch.Tensor = None,
+                          text: torch.Tensor = None, text_len: torch.Tensor = None, logits: torch.Tensor = None):
+    """AudioToAlignText.ctc_best_path (_asr_v2.py:84-119), the core of `voice100-align-text`, with the per-utterance
+    numpy DP replaced by the batched Viterbi kernel.  text is None -> argmax tokens [T', B] (what the reference
+    returns); otherwise -> (score fp32 [B], hist int32 [B, T'] = state index per frame, path int64 [B, T'] =
+    expanded label per frame, logits_len [B]).  (The reference's `score` output is overwritten by a leftover
+    variable, _asr_v2.py:116; here it is the best-path log-probability.)"""
+    from .align import ctc_best_path_batch
+    if logits is None:
+        logits, logits_len = self.forward(audio, audio_len)
+        logprob = torch.log_softmax(logits, dim=-1)
+    else:
+        logprob, logits_len = logits, audio_len
+    if text is None:
+        return logprob.argmax(dim=-1)
+    dev = logprob.device
+    logits_len = logits_len.to(dev)
+    text_len = torch.minimum(logits_len, text_len.to(dev))                    # "for very short audio", :99
+    return ctc_best_path_batch(logprob.transpose(0, 1).contiguous(), logits_len.to(torch.int32), text.to(dev),
+                               text_len.to(torch.int32))
+
+
+AudioToAlignText.ctc_best_path = torch.no_grad()(_ctc_best_path_method)
+
+
 class AsrV2Pipeline(AsrPipeline):
     """waveform -> tokens for AudioToAlignText: log-mel, conv blocks, LSTM stack, head and argmax on libv100.
     Same interface as AsrPipeline -- `pipe(waveform, lengths) -> (tokens int64 [B, T'], lengths [B])`, `.graphed()`,
