@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 4
+#define V100_ABI_VERSION 5
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
@@ -38,6 +38,13 @@ extern "C" {
 
 #define V100_DTYPE_BF16 0
 #define V100_DTYPE_F16  1
+
+/* waveform sample types of v100_logmel */
+#define V100_WAV_F32 0   /* fp32 samples in [-1, 1] (what torchaudio.load returns)              */
+#define V100_WAV_I16 1   /* int16 PCM; scaled by 1/32768 in the kernel = torchaudio.load of 16-bit WAV */
+
+/* sticky bits OR-ed into the optional device status word of the index-consuming kernels */
+#define V100_STATUS_BAD_INDEX 1  /* an embedding id outside [0, V) (nn.Embedding raises IndexError) */
 
 #define V100_ACT_NONE  0
 #define V100_ACT_RELU6 1
@@ -56,15 +63,19 @@ const char* v100_last_error(void);
  * (voice100/data_modules.py:276-281,290-291; torchaudio MelSpectrogram: reflect pad 256,
  * 512-sample frames every 160, periodic Hann(400) centred, |rFFT|^2, 64 HTK mel filters) and
  * the BLANK_AUDIO feature padding of generate_audio_text_batch (data_modules.py:446-455).
- *   wav      fp32 [B][wav_pitch] samples, clip i valid for len[i] samples (len[i] > 256)
+ *   wav      [B][wav_pitch] samples of `wav_dtype` (V100_WAV_F32 | V100_WAV_I16); clip i is valid for len[i]
+ *            samples; len[i] is clamped to [0, L_max] on the device (L_max <= wav_pitch = row capacity).
+ *            torchaudio refuses clips of <= 256 samples (reflect padding); here they are evaluated with the
+ *            reflected index clamped into the clip, and a clip of 0 samples yields BLANK_AUDIO only.
  *   fb_*     the sparse mel filterbank: filter m covers bins [fb_start[m], fb_start[m]+fb_count[m])
- *            with weights fb_w[fb_off[m] ...]  (built by the host from the torchaudio formula)
+ *            with weights fb_w[fb_off[m] ...], fb_nnz weights in all (built by the host from the torchaudio formula)
  *   out      see V100_MEL_*;  T = frames written per clip (>= max_i 1 + len[i]/160)
+ *   frames_out  optional int32 [B]: 1 + len[i]/160, the `audio_len` of the batch (data_modules.py:448)
  */
-int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch,
+int v100_logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
                 const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off,
-                const float* fb_w, float log_offset,
-                void* out, int T, int64_t out_pitch, int out_mode, void* stream);
+                const float* fb_w, int fb_nnz, float log_offset,
+                void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out, void* stream);
 
 /*
  * fp32 [B][T][C] features -> 16-bit NCW [B][C][pitch].  Replaces the transpose at the top of
@@ -132,18 +143,21 @@ int v100_convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, co
 /*
  * Embedding lookup into NCW: y[b][c][t] = table[ids[b][t]][c].  Replaces nn.Embedding +
  * transpose (voice100/models/tts.py:81-83,174-175).  ids int64 [B][T]; table [V][C] of 16-bit elements
- * (either storage type: the rows are copied, not converted).
+ * (either storage type: the rows are copied, not converted).  An id outside [0, V) -- an IndexError in the
+ * reference -- yields a zero column and sets V100_STATUS_BAD_INDEX in *status (optional device int32, sticky:
+ * the caller zeroes it and reads it back when it wants the check).
  */
 int v100_embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch,
-                         int B, int T, int V, int C, void* stream);
+                         int B, int T, int V, int C, int32_t* status, void* stream);
 
 /*
  * CTC head tail: fp32 NCW logits [B][V][pitch] -> logits [B][T][V] fp32 (optional) and greedy
  * tokens int64 [B][T] (first maximal index).  Replaces transpose(1,2) (asr.py:114) and
- * logits.argmax(-1) (tests/test_onnx.py:40).
+ * logits.argmax(-1) (tests/test_onnx.py:40).  With audio_len/out_len (both or neither; int32 [B]) it also
+ * writes out_len[b] = (audio_len[b] + 1) / 2 = AudioToTextCTC.output_length (asr.py:81-82,118-122).
  */
 int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null, int64_t* tokens,
-                      int B, int V, int T, void* stream);
+                      int B, int V, int T, const int32_t* audio_len, int32_t* out_len, void* stream);
 
 /*
  * CTC collapse on the device: per row, within the first valid_len[b] tokens (all T when valid_len is
@@ -159,27 +173,32 @@ int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* 
  * Batched CTC forced alignment (Viterbi best path over the blank-expanded label sequence).  Replaces the
  * per-utterance numpy DP `ctc_best_path` (voice100/models/align.py:18-66, max_move = 3) that the v2 aligner
  * calls through .cpu().numpy() for every utterance (voice100/models/_asr_v2.py:100-119) -- SURVEY.md 8f #3.
- *   logprob  fp32 [B][T][V] log-probabilities;  logit_len int32 [B] valid frames;
+ *   logprob  fp32 [B][T][V] log-probabilities, or raw logits with normalize != 0: the kernel then applies
+ *            log_softmax over V itself (_asr_v2.py:95);  logit_len int32 [B] valid frames;
  *   text     int64 [B][L] labels (0 = blank never appears inside);  text_len int32 [B];
  *   workspace uint8 [B][T][2L+1] back-pointers (caller-provided scratch);
  *   score fp32 [B]; path int32 [B][T] = state index per frame (the reference's best_path);
  *   path_labels int64 [B][T] = expanded label per frame (best_labels); entries past logit_len are 0.
- * An utterance whose frames cannot reach the end of its text (2*logit_len < 2*text_len+1, an IndexError in the
- * reference) gets score = NaN and path = -1.
+ * Where the reference raises IndexError the utterance gets score = NaN and path = -1: frames that cannot reach
+ * state 2*text_len - 1 (exactly the reference's rule, align.py:57-58: with one state missing the result is valid
+ * only if the last live score is not the larger one), an empty text, or a label outside [0, V).
  */
 int v100_ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text,
                        const int32_t* text_len, uint8_t* workspace, float* score, int32_t* path,
-                       int64_t* path_labels, int B, int T, int V, int L, void* stream);
+                       int64_t* path_labels, int B, int T, int V, int L, int normalize, void* stream);
 
 /*
- * WORLD head tail: fp32 NCW [B][260][pitch] -> hasf0[B][T], f0[B][T], logspc[B][T][257],
- * codeap[B][T][1], with std*x+mean and f0 := 0 where hasf0 < 0 when `unnormalize` != 0.
- * Replaces split + WORLDNorm.unnormalize + where (tts.py:181-190,196-200; _layers_v1.py:131-138).
- * mean/std fp32 [259] ordered f0, logspc[257], codeap (ignored when unnormalize == 0).
+ * WORLD head tail: fp32 NCW decoder output -> hasf0[B][T], f0[B][T], logspc[B][T][S], (hascodeap[B][T][A],)
+ * codeap[B][T][A]; with `unnormalize` != 0: std*x+mean, f0 := 0 where hasf0 < 0 and (layout 2) codeap := 0 where
+ * hascodeap < 0.  S = logspc_size (257, or 25 with use_mcep), A = codeap_size.
+ *   layout 1: channels [hasf0 | f0 | logspc(S) | codeap(A)] -- AlignTextToAudioModel: split + WORLDNorm.unnormalize
+ *             + where (tts.py:181-190,196-200; _layers_v1.py:131-138); hascodeap is ignored
+ *   layout 2: channels [hasf0 | f0 | logspc(S) | hascodeap(A) | codeap(A)] -- AlignTextToAudio (_tts_v2.py:65-71,80-91)
+ * mean/std fp32 [1 + S + A] ordered f0, logspc, codeap (ignored when unnormalize == 0).  hasf0/hascodeap may be NULL.
  */
 int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std,
-                        float* hasf0, float* f0, float* logspc, float* codeap,
-                        int B, int T, int unnormalize, void* stream);
+                        float* hasf0, float* f0, float* logspc, float* hascodeap, float* codeap,
+                        int B, int T, int logspc_size, int codeap_size, int layout, int unnormalize, void* stream);
 
 /* fp32 NCW [B][C][pitch] -> fp32 [B][T][C] (align head output [B][L][2]). */
 int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream);

@@ -138,17 +138,25 @@ def gen_viterbi(seed=41):
     """Forced-alignment vectors from the reference's own ctc_best_path (voice100/models/align.py:18-66)."""
     from voice100.models.align import ctc_best_path as ref_best_path
     out = {}
-    cases = [(60, 7), (200, 31), (751, 120), (40, 19), (3, 1)]
+    # the T == L cases reach only S - 1 states: the reference then succeeds or raises IndexError depending on the
+    # last two live scores (align.py:57-58); (9, 10) and (1, 1) always/sometimes fail
+    cases = [(60, 7), (200, 31), (751, 120), (40, 19), (3, 1), (12, 12), (30, 30), (7, 7), (31, 31), (9, 10), (1, 1),
+             (13, 13), (14, 14)]
     for ci, (T, L) in enumerate(cases):
         lp, labels = viterbi_case(T, L, seed + ci)
-        score, path, best_labels = ref_best_path(lp, labels)
+        try:
+            score, path, best_labels = ref_best_path(lp, labels)
+            out[f"c{ci}_fail"] = np.int64(0)
+        except IndexError:
+            score, path, best_labels = np.nan, np.full(T, -1), np.zeros(T)
+            out[f"c{ci}_fail"] = np.int64(1)
         out[f"c{ci}_score"] = np.float32(score)
         out[f"c{ci}_path"] = path.astype(np.int32)
         out[f"c{ci}_labels"] = best_labels.astype(np.int64)
     out["cases"] = np.asarray(cases, np.int64)
     out["seed"] = np.int64(seed)
     np.savez_compressed(os.path.join(OUT, "viterbi.npz"), **out)
-    print("viterbi", cases)
+    print("viterbi", cases, "IndexError:", [int(out[f"c{ci}_fail"]) for ci in range(len(cases))])
 
 
 def gen_asr_v2(name, settings, hidden, vocab, batch, samples, lengths, seed):
@@ -235,6 +243,46 @@ def gen_mcep(seed=61):
     print("mcep", tuple(mcep.shape), "->", tuple(logspc.shape), "logspc std %.3f" % float(logspc.std()))
 
 
+def gen_tts_v1_mcep(seed=71):
+    """AlignTextToAudioModel(use_mcep=True): 25 mel-cepstrum outputs (voice100/models/tts.py:153,164)."""
+    B, T, H, V = 2, 30, 512, 29
+    aligntext = torch.from_numpy(synth.text_tokens(B, T, V, seed=seed))
+    model = AlignTextToAudioModel(vocab_size=V, hidden_size=H, learning_rate=1e-3, use_mcep=True)
+    load(model, synth.audio_state_dict(V, H, seed=seed, randomize_bn=True, randomize_norm=True, logspc_size=25))
+    bn = calibrate(model, aligntext)
+    with torch.no_grad():
+        hasf0, f0_hat, mcep_hat, codeap_hat = model(aligntext)
+        f0, mcep, codeap = model.predict(aligntext)
+    np.savez_compressed(
+        os.path.join(OUT, "tts_v1_mcep.npz"), hasf0_logits=hasf0.numpy(), f0_hat=f0_hat.numpy(),
+        mcep_hat=mcep_hat.numpy(), codeap_hat=codeap_hat.numpy(), f0=f0.numpy(), mcep=mcep.numpy(),
+        codeap=codeap.numpy(), cfg=np.asarray([V, H, B, T, seed], np.int64), **bn)
+    print("tts_v1_mcep", tuple(mcep.shape), "audio_size", model.audio_size)
+
+
+def gen_tokenizer(seed=81):
+    """ids -> decode -> merge_repeated through the reference's CharTokenizer / BasicTokenizer (voice100/text.py:
+    74-145) on CTC-like id sequences (runs, blanks, out-of-vocabulary ids)."""
+    import json
+    from voice100.text import BasicTokenizer, CharTokenizer
+    rng = np.random.default_rng(seed)
+    out = {}
+    for name, tok in (("char", CharTokenizer()), ("en", BasicTokenizer("en")), ("ja", BasicTokenizer("ja"))):
+        cases = []
+        for _ in range(40):
+            ids = []
+            for _ in range(int(rng.integers(0, 25))):
+                t = int(rng.choice([0, 0, int(rng.integers(0, tok.vocab_size)), int(rng.integers(-2, tok.vocab_size + 3))]))
+                ids += [t] * int(rng.integers(1, 5))
+            decoded = tok.decode(torch.tensor(ids, dtype=torch.long))
+            cases.append(dict(ids=ids, decoded=decoded, merged=tok.merge_repeated(decoded),
+                              reencoded=tok.encode(decoded).tolist()))
+        out[name] = dict(vocab_size=tok.vocab_size, cases=cases)
+    with open(os.path.join(OUT, "tokenizer.json"), "w") as f:
+        json.dump(out, f)
+    print("tokenizer", {k: len(v["cases"]) for k, v in out.items()})
+
+
 def viterbi_case(T, L, seed):
     from voice100_b200.synth import viterbi_inputs
     return viterbi_inputs(T, L, 29, seed)
@@ -251,5 +299,9 @@ if __name__ == "__main__":
                lengths=[24000, 9000, 17777], seed=23)
     gen_asr_v2("asr_v2_en_base", synth.ASR_V2_BASE_ENCODER, 512, 29, batch=2, samples=16000,
                lengths=[16000, 16000], seed=24)
+    gen_asr("asr_ja_phone_base_ragged", hidden=512, embed=512, vocab=44, batch=3, samples=24000,
+            lengths=[9000, 17777, 24000], seed=25)        # BASELINE.json configs[4] at its real width
     gen_tts_v2()
     gen_mcep()
+    gen_tts_v1_mcep()
+    gen_tokenizer()

@@ -81,10 +81,11 @@ def mel_power(waveform: torch.Tensor, sample_rate=16000, n_fft=512, win_length=4
     lead = x.shape[:-1]
     x = x.reshape(-1, x.shape[-1])
     spec = torch.stft(x, n_fft=n_fft, hop_length=hop_length, win_length=win_length,
-                      window=torch.hann_window(win_length, periodic=True), center=True,
+                      window=torch.hann_window(win_length, periodic=True, device=x.device), center=True,
                       pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
     power = spec.abs().pow(2.0)                                    # [N, n_fft/2+1, T]
-    mel = torch.matmul(power.transpose(-1, -2), mel_filterbank(sample_rate, n_fft, n_mels)).transpose(-1, -2)
+    fb = mel_filterbank(sample_rate, n_fft, n_mels).to(x.device)    # (device-aware only for bench.py's GPU-eager leg)
+    mel = torch.matmul(power.transpose(-1, -2), fb).transpose(-1, -2)
     return mel.reshape(*lead, n_mels, -1)
 
 
@@ -304,11 +305,12 @@ def voice_decoder(x: torch.Tensor, sd: SD, p="decoder", calib=None) -> torch.Ten
 
 
 def audio_forward(aligntext: torch.Tensor, sd: SD, calib=None):
-    """AlignTextToAudioModel.forward -> (hasf0_logits[B,T'], f0_hat[B,T'], logspc_hat[B,T',257],
-    codeap_hat[B,T',1]), T' = 2T-1 (tts.py:172-190)."""
+    """AlignTextToAudioModel.forward -> (hasf0_logits[B,T'], f0_hat[B,T'], logspc_hat[B,T',S],
+    codeap_hat[B,T',1]), T' = 2T-1 (tts.py:172-190); S = 257 bins, or 25 mel-cepstra with use_mcep (tts.py:164),
+    read off the head's width."""
     x = F.embedding(aligntext, sd["embedding.weight"]).transpose(1, 2)
     x = voice_decoder(x, sd, "decoder", calib).transpose(1, 2)
-    hasf0, f0, logspc, codeap = torch.split(x, [1, 1, 257, 1], dim=2)
+    hasf0, f0, logspc, codeap = torch.split(x, [1, 1, x.shape[2] - 3, 1], dim=2)
     return hasf0[:, :, 0], f0[:, :, 0], logspc, codeap
 
 
@@ -494,6 +496,8 @@ def ctc_best_path(logprob: np.ndarray, labels: np.ndarray):
     lab = np.zeros(2 * len(labels) + 1, dtype=np.asarray(labels).dtype)
     lab[1::2] = labels
     S = lab.shape[0]
+    if S < 2:
+        raise IndexError("empty text (the reference indexes labels[1], align.py:31)")
     NEG = np.float32(-np.inf)
     score = np.full(S, NEG, dtype=logprob.dtype)
     score[:2] = logprob[0, lab[:2]]
@@ -515,9 +519,12 @@ def ctc_best_path(logprob: np.ndarray, labels: np.ndarray):
         score[:nxt_active] = cands[pick, cols]
         back[i, :nxt_active] = srcs[pick, cols]
         active = nxt_active
-    if active < S:
+    # align.py:57-58 works on the `active` live scores: j = S + (-1 if scores[-1] > scores[-2] else -2); scores[j]
+    # raises IndexError when j >= active, i.e. always with two or more states missing, and with exactly one state
+    # missing only if the last live score is the larger one
+    j = S - 1 if score[active - 1] > score[active - 2] else S - 2
+    if j >= active:
         raise IndexError("too few frames to reach the end of the text (same failure as the reference)")
-    j = S - 1 if score[S - 1] > score[S - 2] else S - 2
     best = score[j]
     path = np.zeros(T, dtype=np.int32)
     for i in range(T - 1, -1, -1):

@@ -43,6 +43,14 @@ def tts_case():
     return sd_a, sd_v, text, align, g
 
 
+def tts_v1_mcep_case():
+    """-> (state_dict, aligntext int64 [B, T], golden) for AlignTextToAudioModel(use_mcep=True)"""
+    g = golden("tts_v1_mcep")
+    V, H, B, T, seed = [int(x) for x in g["cfg"]]
+    sd = with_bn(synth.audio_state_dict(V, H, seed=seed, randomize_bn=True, randomize_norm=True, logspc_size=25), g)
+    return sd, torch.from_numpy(synth.text_tokens(B, T, V, seed=seed)), g
+
+
 def asr_v2_case(name):
     """-> (state_dict, waveform, lengths, encoder settings, golden npz) for an AudioToAlignText fixture"""
     g = golden(name)
@@ -63,3 +71,43 @@ def tts_v2_case():
     text = torch.from_numpy(synth.text_tokens(B, L, V, seed=seed))
     align = synth.synthetic_alignment(B, L, seed=seed)
     return sd_a, sd_v, text, align, g
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# STATED TOLERANCES of the ASR path (DESIGN.md section 4 has the error budget they come from).
+# bf16 storage through 28 convolutions of a random-init, BN-calibrated network, versus the fp32 reference:
+BF16_VS_FP32 = dict(max_rel_std=0.45, rms_rel_std=0.08, raw_agreement=0.90)
+# fp16 storage (3 more mantissa bits), versus the fp32 reference:
+F16_VS_FP32 = dict(max_rel_std=0.08, rms_rel_std=0.015, raw_agreement=0.97)
+# versus the oracle evaluated with the SAME storage roundings (only accumulation order differs) -- the check that
+# can actually fail on a kernel bug:
+VS_STORAGE_MODEL = dict(max_rel_std=0.20, rms_rel_std=0.03, raw_agreement=0.97)
+# frames whose fp32 top-1/top-2 margin exceeds this FIXED multiple of std(logits) must decode identically
+GATE_MARGIN_REL_STD = 0.6
+
+
+def check_asr_parity(name, ref, logits, tokens, storage_ref=None, tol=BF16_VS_FP32, valid=None):
+    """ref/logits [B, T, V] (CPU), tokens [B, T]; `valid` = per-utterance frame counts to restrict the comparison to.
+    Prints what it measured and asserts the stated tolerances."""
+    import v100_oracle as orc
+    if valid is not None:
+        keep = torch.zeros(ref.shape[:2], dtype=torch.bool)
+        for b, n in enumerate(valid):
+            keep[b, : int(n)] = True
+        ref, logits, tokens = ref[keep][None], logits[keep][None], tokens[keep][None]
+        storage_ref = None if storage_ref is None else storage_ref[keep][None]
+    rep = orc.parity_report(ref, logits)
+    raw, gated, frac = orc.token_agreement(ref, tokens, GATE_MARGIN_REL_STD * rep["ref_std"])
+    print(f"{name}: vs fp32 max/std {rep['max_abs_rel_std']:.4f} rms/std {rep['rms_rel_std']:.4f} greedy raw {raw:.4f} "
+          f"gated(margin {GATE_MARGIN_REL_STD} std) {gated:.4f} on {frac:.2f} of frames")
+    assert rep["max_abs_rel_std"] < tol["max_rel_std"] and rep["rms_rel_std"] < tol["rms_rel_std"], rep
+    assert raw >= tol["raw_agreement"] and gated == 1.0, (raw, gated)
+    if storage_ref is not None:
+        rep2 = orc.parity_report(storage_ref, logits)
+        agree = float((storage_ref.argmax(-1) == tokens).float().mean())
+        print(f"{name}: vs same-storage oracle max/std {rep2['max_abs_rel_std']:.4f} rms/std {rep2['rms_rel_std']:.4f} "
+              f"greedy {agree:.4f}")
+        t = VS_STORAGE_MODEL
+        assert rep2["max_abs_rel_std"] < t["max_rel_std"] and rep2["rms_rel_std"] < t["rms_rel_std"], rep2
+        assert agree >= t["raw_agreement"], agree
+    return rep

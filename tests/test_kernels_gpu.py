@@ -74,6 +74,39 @@ def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res, dtype):
     assert rel_err(got, ref) < OUT_TOL[dtype], rel_err(got, ref)   # output rounding: 2^-8 (bf16) / 2^-11 (fp16)
 
 
+def test_conv_gemm_stress_is_deterministic():
+    """compute-sanitizer's racecheck/synccheck cannot vouch for the tcgen05 GEMM (false positives on mbarrier/TMEM
+    traffic, profiles/r01_sanitizer.md), so its synchronisation is stressed instead: 1,000 back-to-back launches per
+    shape at odd sizes (ragged T, K not a multiple of 64, C_out not a multiple of 128, residual, CTA pairs, more tiles
+    than SMs so both TMEM buffers and every smem stage are recycled), alternating with a different-shaped launch on the
+    same stream; every result must be bit-identical to the first, which itself matches fp32 PyTorch."""
+    shapes = [(2, 72, 200, 333, 1, False), (3, 1024, 256, 751, 0, True), (40, 128, 384, 520, 0, True),
+              (2, 512, 2048, 300, 1, False), (7, 264, 136, 77, 1, True)]
+    other_x = ncw(rnd(1, 64, 97, seed=33))
+    other_w = rnd(128, 64, seed=34, scale=0.1).to(torch.bfloat16)
+    other_b = torch.zeros(128, device=DEV)
+    for B, C_in, C_out, T, act, res in shapes:
+        x = rnd(B, C_in, T, seed=31)
+        W = rnd(C_out, C_in, seed=32, scale=1.0 / math.sqrt(C_in)).to(torch.bfloat16)
+        scale, shift = torch.rand(C_out, device=DEV) + 0.5, rnd(C_out, seed=35)
+        xn = ncw(x)
+        rn = ncw(rnd(B, C_out, T, seed=36)) if res else None
+        first = K.conv1x1(xn, W, scale, shift, act, rn)
+        ref = F.conv1d(xn.valid().float(), W.float()[:, :, None]) * scale[None, :, None] + shift[None, :, None]
+        if act == K.ACT_RELU6:
+            ref = ref.clamp(0, 6)
+        if res:
+            ref = ref + rn.valid().float()
+        assert rel_err(first.valid().float(), ref) < OUT_TOL[torch.bfloat16]
+        n_bad = torch.zeros((), device=DEV, dtype=torch.int64)
+        for it in range(1000):
+            y = K.conv1x1(xn, W, scale, shift, act, rn)
+            if it % 3 == 0:
+                K.conv1x1(other_x, other_w, None, other_b, 0)
+            n_bad += (y.valid() != first.valid()).sum()
+        assert int(n_bad) == 0, (B, C_in, C_out, T, int(n_bad))
+
+
 @pytest.mark.parametrize("B,C_in,C_out,T", [(2, 256, 29, 751), (3, 512, 44, 100), (2, 256, 260, 277), (1, 512, 2, 24)])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_conv1x1_f32out_matches_torch(B, C_in, C_out, T, dtype):
@@ -189,6 +222,60 @@ def test_logmel_ragged_batch_bf16_ncw():
     assert (got[0, int(ref_len[0]):] == torch.tensor(orc.BLANK_AUDIO).to(torch.bfloat16).float()).all()
 
 
+def test_logmel_int16_pcm_equals_fp32():
+    """int16 PCM input scaled by 1/32768 in the kernel == fp32 samples s/32768 (what torchaudio.load returns for a
+    16-bit WAV, data_modules.py:288): bit-identical features in every output mode, half the input bytes."""
+    tr = MelSpectrogramAudioTransform().to(DEV)
+    B, L = 5, 16000 * 2 + 123
+    g = torch.Generator().manual_seed(6)
+    pcm = torch.randint(-32768, 32768, (B, L), generator=g, dtype=torch.int32).to(torch.int16)
+    pcm[1] = (pcm[1].float() * 0.01).to(torch.int16)                       # a quiet clip
+    wav = pcm.float() / 32768.0
+    lengths = torch.tensor([L, L - 777, 5000, L - 1, 300], dtype=torch.int32)
+    a32, n32 = tr.logmel_batch(wav.to(DEV), lengths.to(DEV))
+    a16, n16 = tr.logmel_batch(pcm.to(DEV), lengths.to(DEV))
+    assert torch.equal(a32, a16) and torch.equal(n32, n16) and n16.tolist() == [1 + int(n) // 160 for n in lengths]
+    b32, _ = tr.logmel_batch(wav.to(DEV), lengths.to(DEV), ncw_dtype=torch.bfloat16)
+    b16, _ = tr.logmel_batch(pcm.to(DEV), lengths.to(DEV), ncw_dtype=torch.bfloat16)
+    assert torch.equal(b32.valid(), b16.valid())
+    ref, _ = orc.logmel_batch(wav, lengths.tolist())
+    np.testing.assert_allclose(a16.cpu().numpy(), ref.numpy(), rtol=0, atol=3e-3)
+    assert torch.equal(tr.melspec(pcm[0].to(DEV)), tr.melspec(wav[0].to(DEV)))
+    # an odd row pitch (rows not 4-byte aligned for int16): the scalar load path gives the same features
+    odd = torch.zeros((B, L + 1), dtype=torch.int16)
+    odd[:, :L] = pcm
+    c16, _ = tr.logmel_batch(odd.to(DEV)[:, :L + 1], lengths.to(DEV))
+    assert torch.equal(c16[:, : a16.shape[1]], a16)
+
+
+def test_logmel_short_and_empty_clips_are_safe():
+    """torchaudio refuses clips of <= n_fft/2 samples (reflect padding).  Device-resident lengths cannot be checked
+    without a sync, so the kernel must stay in bounds: lengths are clamped to [0, L_max], the reflected index is
+    clamped into the clip, an empty slot yields BLANK_AUDIO only (the filler slots of a fixed-shape graph batch).
+    Host-resident lengths are validated and raise."""
+    from voice100_b200 import V100Error
+    tr = MelSpectrogramAudioTransform().to(DEV)
+    L = 4000
+    big = torch.randn(6, L, device=DEV) * 0.1
+    wav = big[1:5]                                                     # neighbours on both sides would be read by a bug
+    lengths = torch.tensor([0, 1, 256, 10 ** 6], dtype=torch.int32, device=DEV)
+    audio, audio_len = tr.logmel_batch(wav, lengths)
+    torch.cuda.synchronize()
+    assert torch.isfinite(audio).all()
+    assert audio_len.tolist() == [1, 1, 2, 1 + L // 160]               # 1 + len // 160 with len clamped to L_max
+    assert (audio[0] == orc.BLANK_AUDIO).all() and (audio[1, 1:] == orc.BLANK_AUDIO).all()
+    full, _ = tr.logmel_batch(wav, torch.tensor([L] * 4, dtype=torch.int32, device=DEV))
+    assert torch.equal(audio[3], full[3])                              # the over-long length was clamped to the row
+    ref = orc.logmel_clip(wav[3].cpu())
+    np.testing.assert_allclose(audio[3].cpu().numpy(), ref.numpy(), rtol=0, atol=3e-3)
+    for bad in ([L, 200, L, L], [L, L, L + 1, L]):
+        with pytest.raises(V100Error):
+            tr.logmel_batch(wav, torch.tensor(bad, dtype=torch.int32))
+    tr.logmel_batch(wav, torch.tensor([L, 0, 257, L], dtype=torch.int32))   # 0 = empty slot, 257 = shortest legal clip
+    with pytest.raises(V100Error):
+        tr.melspec(wav[0, :256])
+
+
 # ------------------------------------------------------------------------------------------------
 # small layout / head kernels
 # ------------------------------------------------------------------------------------------------
@@ -220,6 +307,46 @@ def test_layout_and_head_kernels():
     torch.testing.assert_close(codeap, (std[258] * v[:, 259:] + mean[258]).transpose(1, 2), rtol=1e-6, atol=1e-6)
     h2, f2, l2, c2 = K.world_finalize(w, None, None, False)
     assert torch.equal(f2, v[:, 1]) and torch.equal(l2, v[:, 2:259].transpose(1, 2))
+    # output_length emitted by the CTC tail (asr.py:81-82)
+    alen = torch.tensor([101, 100, 1, 0], dtype=torch.int32, device=DEV)
+    _, tok2, olen = K.ctc_finalize(lg, False, alen)
+    assert torch.equal(tok2, tokens) and olen.tolist() == [51, 50, 1, 0] and olen.dtype == torch.int32
+    # ids outside the table: IndexError like nn.Embedding (and the flag is cleared for the next call)
+    bad = ids.clone()
+    bad[1, 4] = 29
+    with pytest.raises(IndexError):
+        K.embedding_ncw(bad, table)
+    bad[1, 4] = -1
+    with pytest.raises(IndexError):
+        K.embedding_ncw(bad, table)
+    assert torch.equal(K.embedding_ncw(ids, table).valid(), e.valid())
+
+
+@pytest.mark.parametrize("S,A,layout", [(257, 1, 1), (25, 1, 1), (257, 1, 2), (25, 1, 2), (25, 3, 2), (40, 2, 1)])
+def test_world_finalize_layouts(S, A, layout):
+    """v1 layout [hasf0|f0|logspc(S)|codeap(A)] (tts.py:181-200) and v2 layout with the hascodeap gate
+    (_tts_v2.py:65-91), S = 257 bins or 25 mel-cepstra, against the reference's split / unnormalize / where."""
+    B, T = 3, 77
+    C = 2 + S + (2 if layout == 2 else 1) * A
+    y = K.Ncw(torch.randn(B, C, 80, device=DEV), T)
+    mean, std = torch.randn(1 + S + A, device=DEV), torch.rand(1 + S + A, device=DEV) + 0.5
+    x = y.valid().transpose(1, 2)                                   # [B, T, C] as the reference sees it
+    sizes = [1, 1, S, A] if layout == 1 else [1, 1, S, A, A]
+    parts = torch.split(x, sizes, dim=2)
+    out = K.world_finalize(y, None, None, False, S, A, layout)
+    assert torch.equal(out[0], parts[0][:, :, 0]) and torch.equal(out[1], parts[1][:, :, 0])
+    for got, ref in zip(out[2:], parts[2:]):
+        assert torch.equal(got, ref)
+    out = K.world_finalize(y, mean, std, True, S, A, layout)
+    f0 = torch.where(parts[0][:, :, 0] < 0, torch.zeros(1, device=DEV), std[0] * parts[1][:, :, 0] + mean[0])
+    logspc = std[1:1 + S] * parts[2] + mean[1:1 + S]
+    codeap = std[1 + S:] * parts[-1] + mean[1 + S:]
+    if layout == 2:
+        codeap = torch.where(parts[3] < 0, torch.zeros(1, device=DEV), codeap)
+    torch.testing.assert_close(out[1], f0, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out[2], logspc, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(out[-1], codeap, rtol=1e-6, atol=1e-6)
+    assert ((out[1] == 0) == (parts[0][:, :, 0] < 0)).all()
 
 
 def test_ctc_collapse_matches_reference_text_rule():
@@ -261,7 +388,7 @@ def test_ctc_best_path_matches_oracle_bit_exact():
     n_frames, n_text, refs = [], [], []
     for ci, (T, L) in enumerate(cases):
         a, lab = synth.viterbi_inputs(T, L, 29, int(g["seed"]) + ci)
-        refs.append((g[f"c{ci}_score"], g[f"c{ci}_path"], g[f"c{ci}_labels"]))
+        refs.append(None if int(g[f"c{ci}_fail"]) else (g[f"c{ci}_score"], g[f"c{ci}_path"], g[f"c{ci}_labels"]))
         lp[ci, :T], text[ci, :L] = torch.from_numpy(a), torch.from_numpy(lab)
         n_frames.append(T); n_text.append(L)
     for ei, (T, L, seed) in enumerate(extra):
@@ -283,6 +410,22 @@ def test_ctc_best_path_matches_oracle_bit_exact():
         assert np.array_equal(hist[b, :T].cpu().numpy(), ref[1]) and np.array_equal(path[b, :T].cpu().numpy(), ref[2]), b
         assert (hist[b, T:] == 0).all()
     assert refs[-1] is None
+    # raw logits in, log_softmax folded into the kernel (_asr_v2.py:95): same paths, scores to fp32 round-off
+    logits = (lp * 3.0 + torch.randn(B, T_max, 1)).to(DEV)              # any per-frame shift: log_softmax removes it
+    s2, h2, p2, _ = v.ctc_best_path_batch(logits, torch.tensor(n_frames), text.to(DEV), torch.tensor(n_text), normalize=True)
+    s3, h3, p3, _ = v.ctc_best_path_batch(torch.log_softmax(logits, -1), torch.tensor(n_frames), text.to(DEV), torch.tensor(n_text))
+    ok = ~torch.isnan(s3)
+    assert torch.equal(torch.isnan(s2), torch.isnan(s3))
+    torch.testing.assert_close(s2[ok], s3[ok], rtol=2e-5, atol=1e-3)
+    agree = (h2[ok] == h3[ok]).float().mean()
+    assert agree > 0.999, agree                                         # (a 1-ulp tie may move a boundary by a frame)
+    # a label outside [0, V): IndexError for host-resident text, NaN / -1 for that utterance when it lives on the device
+    bad = text.clone()
+    bad[1, 2] = 29
+    with pytest.raises(IndexError):
+        v.ctc_best_path_batch(lp.to(DEV), torch.tensor(n_frames), bad, torch.tensor(n_text))
+    s4, h4, _, _ = v.ctc_best_path_batch(lp.to(DEV), torch.tensor(n_frames), bad.to(DEV), torch.tensor(n_text))
+    assert torch.isnan(s4[1]) and (h4[1] == -1).all() and float(s4[0]) == float(score[0]) and torch.equal(h4[0], hist[0])
 
 
 def test_errors_are_loud():

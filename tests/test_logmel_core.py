@@ -16,25 +16,33 @@ HARNESS = r"""
 #include <cmath>
 using namespace v100;
 extern "C" void fft16_host(float* v) { fft16(reinterpret_cast<cpx*>(v)); }
-// the 16-thread register decomposition of logmel.cu, thread by thread, with its shared-memory indexing
+// the 16-thread register decomposition of logmel.cu, thread by thread: two fft16 passes around the stride-17
+// exchange, then the conjugate partner Z[256-k] taken from register 15-k2 of lane (16-q)&15 (own register (16-k2)&15
+// for q = 0) -- what the kernel fetches with __shfl_sync -- and both bins of the pair from one complex multiply
 extern "C" void rfft512_power_host(const float* frame, float* power) {
   static cpx tw[512];
   for (int k = 0; k < 512; ++k) { tw[k].x = (float)cos(-2.0*M_PI*k/512.0); tw[k].y = (float)sin(-2.0*M_PI*k/512.0); }
-  cpx E[16 * 17], Z[256];
+  cpx E[16 * 17], R[16][16];
   for (int q = 0; q < 16; ++q) {            // thread q: FFT over r, twiddle, write column q of the exchange
     cpx v[16];
     for (int r = 0; r < 16; ++r) { const int n = q + 16 * r; v[r] = cpx{frame[2 * n], frame[2 * n + 1]}; }
     fft16(v);
     for (int k1 = 0; k1 < 16; ++k1) E[k1 * 17 + q] = cmul(v[k1], tw[(2 * q * k1) & 511]);
   }
-  for (int k1 = 0; k1 < 16; ++k1) {         // thread k1: FFT over q -> Z[k1 + 16 k2]
-    cpx v[16];
-    for (int q = 0; q < 16; ++q) v[q] = E[k1 * 17 + q];
-    fft16(v);
-    for (int k2 = 0; k2 < 16; ++k2) Z[k1 + 16 * k2] = v[k2];
+  for (int k1 = 0; k1 < 16; ++k1) {         // thread k1: FFT over q -> registers R[k1][k2] = Z[k1 + 16 k2]
+    for (int q = 0; q < 16; ++q) R[k1][q] = E[k1 * 17 + q];
+    fft16(R[k1]);
   }
-  for (int k = 0; k < 256; ++k) power[k] = rfft512_power_pair(Z[k], Z[(256 - k) & 255], tw[k]);
-  power[256] = rfft512_power_pair(Z[0], Z[0], tw[256]);
+  for (int q = 0; q < 16; ++q) {
+    const int partner = (16 - q) & 15;
+    for (int k2 = 0; k2 < 8; ++k2) {
+      const cpx zn = q == 0 ? R[0][(16 - k2) & 15] : R[partner][15 - k2];
+      const cpx w32 = cpx{(float)cos(-2.0*M_PI*k2/32.0), (float)sin(-2.0*M_PI*k2/32.0)};
+      const int k = q + 16 * k2;
+      rfft512_power_both(R[q][k2], zn, cmul(tw[q], w32), &power[k], &power[256 - k]);
+    }
+  }
+  power[128] = rfft512_power_pair(R[0][8], R[0][8], cpx{0.0f, -1.0f});
 }
 """
 
@@ -85,9 +93,10 @@ def test_fft16_matches_numpy(host_fft):
 
 
 def test_shared_memory_accesses_are_conflict_free():
-    """The kernel's 64-bit shared-memory accesses of one half-warp (16 lanes x 8 bytes = one 128-byte wavefront when
-    the 16 lanes hit 16 different bank pairs): exchange writes E[k1*17 + q], exchange reads E[q*17 + qq], spectrum
-    writes Z[q + 16 k2] and partner reads Z[(256 - q - 16 k2) & 255]."""
+    """Bank arithmetic of logmel.cu.  64-bit exchange accesses of one half-warp (16 lanes x 8 bytes = one 128-byte
+    wavefront when the lanes hit 16 different bank pairs): writes E[k1*17 + q], reads E[q*17 + qq].  32-bit power
+    stores of a whole warp into P[bin*33 + frame] (the two half-warps hold frames 16 apart): 32 distinct banks for
+    both the k = q + 16 k2 and the 256 - k stores.  Mel-phase loads P[(s0+tap)*33 + lane]: 32 distinct banks."""
     def bank_pairs(idx):
         return len({i % 16 for i in idx})
     for k1 in range(16):
@@ -95,9 +104,28 @@ def test_shared_memory_accesses_are_conflict_free():
     for qq in range(16):
         assert bank_pairs([q * 17 + qq for q in range(16)]) == 16      # what the padding to 17 buys
         assert bank_pairs([q * 16 + qq for q in range(16)]) == 1       # ... and what 16 would cost
-    for k2 in range(16):
-        assert bank_pairs([q + 16 * k2 for q in range(16)]) == 16
-        assert bank_pairs([(256 - q - 16 * k2) & 255 for q in range(16)]) == 16
+    for fl in range(16):
+        for k2 in range(8):
+            lo = [(q + 16 * k2) * 33 + fl + 16 * h for h in range(2) for q in range(16)]
+            hi = [(256 - q - 16 * k2) * 33 + fl + 16 * h for h in range(2) for q in range(16)]
+            assert len({i % 32 for i in lo}) == 32 and len({i % 32 for i in hi}) == 32
+            bad = [(q + 16 * k2) * 33 + fl + h for h in range(2) for q in range(16)]   # adjacent frames would collide
+            assert len({i % 32 for i in bad}) < 32
+    for row in (0, 7, 256):
+        assert len({(row * 33 + lane) % 32 for lane in range(32)}) == 32
+
+
+def test_every_power_bin_is_written_once():
+    """The pair scheme of logmel.cu covers bins 0..256 exactly once: k = q + 16 k2 (k2 < 8), its partner 256 - k,
+    and bin 128 from lane 0."""
+    seen = [0] * 257
+    for q in range(16):
+        for k2 in range(8):
+            k = q + 16 * k2
+            seen[k] += 1
+            seen[256 - k] += 1
+    seen[128] += 1
+    assert seen == [1] * 257
 
 
 def test_frame_pipeline_matches_oracle(host_fft):

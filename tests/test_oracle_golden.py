@@ -3,6 +3,7 @@ oracle/gen_golden.py) and against the known-answer anchors of SURVEY.md section 
 import math
 
 import numpy as np
+import pytest
 import torch
 
 import v100_oracle as orc
@@ -80,6 +81,49 @@ def test_asr_ja_ragged_matches_reference():
     _asr("asr_ja_phone_ragged")
 
 
+def test_asr_ja_base_ragged_matches_reference():
+    """BASELINE.json configs[4] at its real width: AudioToTextCTC(64, 512, 44, 512), ragged clips."""
+    _asr("asr_ja_phone_base_ragged")
+
+
+def test_tts_v1_mcep_matches_reference():
+    """AlignTextToAudioModel(use_mcep=True), 25 mel-cepstrum outputs (tts.py:153,164)."""
+    from helpers import tts_v1_mcep_case
+    sd, aligntext, g = tts_v1_mcep_case()
+    with torch.no_grad():
+        hasf0, f0_hat, mcep_hat, codeap_hat = orc.audio_forward(aligntext, sd)
+        f0, mcep, codeap = orc.audio_predict(aligntext, sd)
+    assert mcep.shape == g["mcep"].shape == (aligntext.shape[0], 2 * aligntext.shape[1] - 1, 25)
+    np.testing.assert_allclose(hasf0.numpy(), g["hasf0_logits"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(mcep_hat.numpy(), g["mcep_hat"], rtol=0, atol=2e-4)
+    np.testing.assert_allclose(mcep.numpy(), g["mcep"], rtol=0, atol=1e-3)
+    np.testing.assert_allclose(codeap.numpy(), g["codeap"], rtol=0, atol=1e-3)
+    safe = np.abs(g["hasf0_logits"]) > 1e-3
+    assert ((f0.numpy() == 0) == (g["f0"] == 0))[safe].all()
+
+
+def test_tokenizers_match_reference():
+    """voice100_b200.text (host tail of greedy decoding) against the reference's CharTokenizer / BasicTokenizer
+    outputs stored by oracle/gen_golden.py:gen_tokenizer (voice100/text.py:74-145)."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from voice100_b200.text import BasicTokenizer, CharTokenizer
+    with open(os.path.join(GOLDEN, "tokenizer.json")) as f:
+        g = json.load(f)
+    toks = {"char": CharTokenizer(), "en": BasicTokenizer("en"), "ja": BasicTokenizer("ja")}
+    assert {k: t.vocab_size for k, t in toks.items()} == {"char": 29, "en": 71, "ja": 44}
+    for name, tok in toks.items():
+        assert tok.vocab_size == g[name]["vocab_size"]
+        for case in g[name]["cases"]:
+            decoded = tok.decode(case["ids"])
+            assert decoded == case["decoded"], (name, case["ids"])
+            assert tok.merge_repeated(decoded) == case["merged"], (name, decoded)
+            assert tok.encode(decoded).tolist() == case["reencoded"]
+    with pytest.raises(ValueError):
+        BasicTokenizer("fr")
+
+
 def test_tts_matches_reference():
     sd_a, sd_v, text, align, g = tts_case()
     with torch.no_grad():
@@ -119,11 +163,16 @@ def test_viterbi_matches_reference():
     g = golden("viterbi")
     for ci, (T, L) in enumerate(g["cases"]):
         lp, labels = synth.viterbi_inputs(int(T), int(L), 29, int(g["seed"]) + ci)
+        if int(g[f"c{ci}_fail"]):                                 # the reference raised IndexError (align.py:57-58)
+            with pytest.raises(IndexError):
+                orc.ctc_best_path(lp, labels)
+            continue
         score, path, best_labels = orc.ctc_best_path(lp, labels)
         assert np.float32(score) == g[f"c{ci}_score"]
         assert np.array_equal(path, g[f"c{ci}_path"]) and np.array_equal(best_labels, g[f"c{ci}_labels"])
         # structural properties of any valid alignment
         assert path[0] in (0, 1) and path[-1] in (2 * L - 1, 2 * L) and (np.diff(path) >= 0).all() and (np.diff(path) <= 2).all()
+    assert sum(int(g[f"c{ci}_fail"]) for ci in range(len(g["cases"]))) >= 3     # both outcomes of T == L are pinned
 
 
 # ---- v2 models (LayerNorm/GELU conv blocks + bidirectional LSTM) ----

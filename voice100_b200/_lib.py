@@ -15,7 +15,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes; mirrors include/v100.h declaration by declaration
 SIGNATURES = {
     "v100_abi_version": [],
-    "v100_logmel": [_p, _p, _i, _l, _p, _p, _p, _p, _f, _p, _i, _l, _i, _p],
+    "v100_logmel": [_p, _i, _p, _i, _l, _i, _p, _p, _p, _p, _i, _f, _p, _i, _l, _i, _p, _p],
     "v100_ntc_f32_to_ncw16": [_p, _p, _i, _i, _i, _l, _i, _p],
     "v100_ncw_f32_to_16": [_p, _p, _l, _i, _i, _i, _i, _p],
     "v100_ncw_16_to_f32": [_p, _l, _p, _i, _i, _i, _i, _p],
@@ -24,11 +24,11 @@ SIGNATURES = {
     "v100_dwconv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
     "v100_dwconv1d_simt": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _p],
     "v100_convtranspose1d_k5s2": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _p],
-    "v100_embedding_ncw16": [_p, _p, _p, _l, _i, _i, _i, _i, _p],
-    "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p],
+    "v100_embedding_ncw16": [_p, _p, _p, _l, _i, _i, _i, _i, _p, _p],
+    "v100_ctc_finalize": [_p, _l, _p, _p, _i, _i, _i, _p, _p, _p],
     "v100_ctc_collapse": [_p, _p, _p, _p, _i, _i, _i, _p],
-    "v100_ctc_best_path": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "v100_ctc_best_path": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
     "v100_conv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "v100_conv1d_tm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -38,7 +38,7 @@ SIGNATURES = {
     "v100_lstm_layer": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 _lib = None
 
 

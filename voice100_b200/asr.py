@@ -72,22 +72,26 @@ class AudioToTextCTC(StorageDtypeMixin, nn.Module):
         self.decoder = LinearCharDecoder(embed_size, vocab_size)
         self.eval()
 
-    def _run(self, x: K.Ncw, want_logits: bool):
-        return K.ctc_finalize(self.decoder.run(self.encoder.run(x)), want_logits)
+    def _run(self, x: K.Ncw, want_logits: bool, audio_len: torch.Tensor = None):
+        return K.ctc_finalize(self.decoder.run(self.encoder.run(x)), want_logits, audio_len)
 
     def forward(self, audio: torch.Tensor) -> torch.Tensor:
         """audio fp32 [B, T, audio_size] -> logits fp32 [B, (T+1)//2, vocab_size]."""
         require_eval_cuda(self, audio)
         return self._run(K.ntc_f32_to_ncw(audio.float().contiguous(), self.storage_dtype), True)[0]
 
-    def greedy(self, audio) -> torch.Tensor:
+    def greedy(self, audio, audio_len: torch.Tensor = None):
         """CTC best-path tokens int64 [B, (T+1)//2] = forward(audio).argmax(-1) without materialising the
-        logits.  `audio` is fp32 [B, T, 64] or the bf16 Ncw produced by logmel_batch(ncw_bf16=True)."""
+        logits.  `audio` is fp32 [B, T, 64] or the bf16 Ncw produced by logmel_batch(ncw_bf16=True).
+        With `audio_len` (int32 [B] on the device) -> (tokens, output_length(audio_len)), both from one kernel."""
         if isinstance(audio, K.Ncw):
             require_eval_cuda(self, audio.data)
-            return self._run(audio, False)[1]
-        require_eval_cuda(self, audio)
-        return self._run(K.ntc_f32_to_ncw(audio.float().contiguous(), self.storage_dtype), False)[1]
+            x = audio
+        else:
+            require_eval_cuda(self, audio)
+            x = K.ntc_f32_to_ncw(audio.float().contiguous(), self.storage_dtype)
+        out = self._run(x, False, audio_len)
+        return out[1] if audio_len is None else (out[1], out[2])
 
     def output_length(self, audio_len: torch.Tensor) -> torch.Tensor:
         return self.encoder.output_length(audio_len)
@@ -102,9 +106,11 @@ class AsrPipeline:
 
     @torch.no_grad()
     def __call__(self, waveform: torch.Tensor, lengths: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """device waveform fp32 [B, L], lengths [B] -> (tokens int64 [B, T'], valid lengths int [B])."""
+        """device waveform fp32 or int16 PCM [B, L], lengths [B] -> (tokens int64 [B, T'], valid lengths int32 [B]).
+        Three kinds of kernel and nothing else: log-mel (also emits audio_len), the conv stack, the CTC tail (also
+        emits output_length)."""
         feats, audio_len = self.transform.logmel_batch(waveform, lengths, ncw_dtype=self.model.storage_dtype)
-        return self.model.greedy(feats), self.model.output_length(audio_len)
+        return self.model.greedy(feats, audio_len)
 
     @torch.no_grad()
     def transcribe_ids(self, waveform: torch.Tensor, lengths: torch.Tensor, blank: int = 0):
@@ -114,30 +120,32 @@ class AsrPipeline:
         return K.ctc_collapse(tokens, out_len, blank)
 
     @torch.no_grad()
-    def _capture(self, batch: int, samples: int, dev):
+    def _capture(self, batch: int, samples: int, dev, wav_dtype=torch.float32):
         """-> (graph, static waveform, static lengths, static tokens, static out_len) for one fixed shape."""
-        wav_s = torch.zeros((batch, samples), dtype=torch.float32, device=dev)
-        len_s = torch.full((batch,), samples, dtype=torch.int32, device=dev)
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):          # warm-up outside capture: one-time function attributes, caches
-            for _ in range(2):
-                self(wav_s, len_s)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            tok_s, out_s = self(wav_s, len_s)
+        with torch.cuda.device(dev):
+            wav_s = torch.zeros((batch, samples), dtype=wav_dtype, device=dev)
+            len_s = torch.full((batch,), samples, dtype=torch.int32, device=dev)
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):          # warm-up outside capture: one-time function attributes, caches
+                for _ in range(2):
+                    self(wav_s, len_s)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                tok_s, out_s = self(wav_s, len_s)
         return graph, wav_s, len_s, tok_s, out_s
 
     @torch.no_grad()
-    def graphed(self, batch: int, samples: int, device="cuda"):
-        """Capture the whole path (log-mel -> encoder -> head -> argmax, 30 kernel launches) for one fixed
-        [batch, samples] shape into a CUDA graph.  Replaying it removes the per-launch gaps: 8-10 % at
+    def graphed(self, batch: int, samples: int, device="cuda", wav_dtype=torch.float32):
+        """Capture the whole path (log-mel -> encoder -> head -> argmax: 30 launches, all libv100 kernels) for one
+        fixed [batch, samples] shape into a CUDA graph.  Replaying it removes the per-launch gaps: 8-10 % at
         256 x 15 s, 2.5x at 8 x 10 s (which is ~0.3 ms of GPU work behind ~0.7 ms of launches).
-        Returns `run(waveform, lengths) -> (tokens, out_len)`; the outputs are static buffers overwritten by
-        the next replay; `run.graph.replay()` re-runs on the current contents of `run.waveform/.lengths`."""
+        `wav_dtype` torch.float32 or torch.int16 (PCM).  Returns `run(waveform, lengths) -> (tokens, out_len)`; the
+        outputs are static buffers overwritten by the next replay; `run.graph.replay()` re-runs on the current
+        contents of `run.waveform/.lengths`."""
         dev = torch.device(device)
-        graph, wav_s, len_s, tok_s, out_s = self._capture(batch, samples, dev)
+        graph, wav_s, len_s, tok_s, out_s = self._capture(batch, samples, dev, wav_dtype)
 
         def run(waveform: torch.Tensor, lengths: torch.Tensor):
             wav_s.copy_(waveform, non_blocking=True)
@@ -150,6 +158,7 @@ class AsrPipeline:
     @torch.no_grad()
     def submit_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):
         """Asynchronous end-to-end call: host buffers in (pin them for full PCIe speed), host tokens out.
+        `waveform` is fp32 or int16 PCM (half the H2D bytes; identical features for 16-bit sources).
         The batch is cut into `chunks` groups of utterances; each group has its own captured CUDA graph with
         static device buffers.  H2D copies run on a side stream straight into those buffers, so chunk i+1
         uploads while chunk i computes, and each chunk's tokens come back with an async D2H.  Returns a
@@ -159,9 +168,10 @@ class AsrPipeline:
         while batch i still computes.  `chunks=1` gives the best throughput (whole-batch kernels, uploads hidden
         behind the previous batch), more chunks give a shorter latency for a single batch."""
         dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         B, L = waveform.shape
         n = max(1, min(chunks, B))
-        cur = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None or self._copy_stream.device != dev:
             self._copy_stream = torch.cuda.Stream(dev)
             self._host_out, self._slot, self._chunk_graphs = {}, 0, {}
@@ -173,32 +183,34 @@ class AsrPipeline:
             self._host_out[key] = (torch.empty((B, T_out), dtype=torch.int64).pin_memory(),
                                    torch.empty((B,), dtype=torch.int32).pin_memory())
         tok_h, len_h = self._host_out[key]
-        staged = []
-        for i in range(n):
-            a, b = B * i // n, B * (i + 1) // n
-            gkey = (i, b - a, L, slot)
-            if gkey not in self._chunk_graphs:
-                self._chunk_graphs[gkey] = list(self._capture(b - a, L, dev)) + [None]
-            cg = self._chunk_graphs[gkey]
-            graph, wav_s, len_s, tok_s, out_s, done = cg
-            with torch.cuda.stream(self._copy_stream):
-                if done is not None:
-                    self._copy_stream.wait_event(done)   # the previous replay has finished reading wav_s
-                wav_s.copy_(waveform[a:b], non_blocking=True)
-                len_s.copy_(lengths[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self._copy_stream)
-            staged.append((a, b, cg, ev))
-        for a, b, cg, ev in staged:
-            graph, wav_s, len_s, tok_s, out_s, _ = cg
-            cur.wait_event(ev)
-            graph.replay()
-            tok_h[a:b].copy_(tok_s, non_blocking=True)
-            len_h[a:b].copy_(out_s.to(torch.int32), non_blocking=True)
-            cg[5] = torch.cuda.Event()
-            cg[5].record(cur)
-        done_all = torch.cuda.Event()
-        done_all.record(cur)
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            staged = []
+            for i in range(n):
+                a, b = B * i // n, B * (i + 1) // n
+                gkey = (i, b - a, L, slot, waveform.dtype)
+                if gkey not in self._chunk_graphs:
+                    self._chunk_graphs[gkey] = list(self._capture(b - a, L, dev, waveform.dtype)) + [None]
+                cg = self._chunk_graphs[gkey]
+                graph, wav_s, len_s, tok_s, out_s, done = cg
+                with torch.cuda.stream(self._copy_stream):
+                    if done is not None:
+                        self._copy_stream.wait_event(done)   # the previous replay has finished reading wav_s
+                    wav_s.copy_(waveform[a:b], non_blocking=True)
+                    len_s.copy_(lengths[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                staged.append((a, b, cg, ev))
+            for a, b, cg, ev in staged:
+                graph, wav_s, len_s, tok_s, out_s, _ = cg
+                cur.wait_event(ev)
+                graph.replay()
+                tok_h[a:b].copy_(tok_s, non_blocking=True)
+                len_h[a:b].copy_(out_s, non_blocking=True)
+                cg[5] = torch.cuda.Event()
+                cg[5].record(cur)
+            done_all = torch.cuda.Event()
+            done_all.record(cur)
         return _Ticket(done_all, tok_h, len_h)
 
     def transcribe_host(self, waveform: torch.Tensor, lengths: torch.Tensor, device="cuda", chunks: int = 4):

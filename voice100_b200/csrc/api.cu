@@ -1,6 +1,7 @@
 // extern "C" surface of libv100.so (see include/v100.h) + host plumbing.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "host.h"
@@ -15,6 +16,14 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("V100_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 int num_sms() {
@@ -86,11 +95,12 @@ extern "C" {
 int v100_abi_version(void) { return V100_ABI_VERSION; }
 const char* v100_last_error(void) { return g_err; }
 
-int v100_logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const int32_t* fb_start,
-                const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T,
-                int64_t out_pitch, int out_mode, void* stream) {
-  return logmel(wav, len, B, wav_pitch, fb_start, fb_count, fb_off, fb_w, log_offset, out, T, out_pitch, out_mode,
-                STREAM(stream));
+int v100_logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
+                const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, int fb_nnz,
+                float log_offset, void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out,
+                void* stream) {
+  return logmel(wav, wav_dtype, len, B, wav_pitch, L_max, fb_start, fb_count, fb_off, fb_w, fb_nnz, log_offset, out, T,
+                out_pitch, out_mode, frames_out, STREAM(stream));
 }
 
 int v100_ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, void* stream) {
@@ -135,13 +145,13 @@ int v100_convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, co
 }
 
 int v100_embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
-                         void* stream) {
-  return embedding_ncw16(ids, table, y, y_pitch, B, T, V, C, STREAM(stream));
+                         int32_t* status, void* stream) {
+  return embedding_ncw16(ids, table, y, y_pitch, B, T, V, C, status, STREAM(stream));
 }
 
 int v100_ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits_or_null, int64_t* tokens, int B, int V,
-                      int T, void* stream) {
-  return ctc_finalize(y_ncw, y_pitch, logits_or_null, tokens, B, V, T, STREAM(stream));
+                      int T, const int32_t* audio_len, int32_t* out_len, void* stream) {
+  return ctc_finalize(y_ncw, y_pitch, logits_or_null, tokens, B, V, T, audio_len, out_len, STREAM(stream));
 }
 
 int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
@@ -151,14 +161,16 @@ int v100_ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* 
 
 int v100_ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
                        uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V,
-                       int L, void* stream) {
-  return ctc_best_path(logprob, logit_len, text, text_len, workspace, score, path, path_labels, B, T, V, L,
+                       int L, int normalize, void* stream) {
+  return ctc_best_path(logprob, logit_len, text, text_len, workspace, score, path, path_labels, B, T, V, L, normalize,
                        STREAM(stream));
 }
 
 int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0,
-                        float* f0, float* logspc, float* codeap, int B, int T, int unnormalize, void* stream) {
-  return world_finalize(y_ncw, y_pitch, mean, std, hasf0, f0, logspc, codeap, B, T, unnormalize, STREAM(stream));
+                        float* f0, float* logspc, float* hascodeap, float* codeap, int B, int T, int logspc_size,
+                        int codeap_size, int layout, int unnormalize, void* stream) {
+  return world_finalize(y_ncw, y_pitch, mean, std, hasf0, f0, logspc, hascodeap, codeap, B, T, logspc_size,
+                        codeap_size, layout, unnormalize, STREAM(stream));
 }
 
 int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream) {

@@ -97,6 +97,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
 
+  pdl_trigger();   // persistent grid: every CTA is resident, the next kernel may queue up behind our tail
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
@@ -130,6 +131,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; from here on we read its output
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -476,8 +478,7 @@ static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUten
     configured_dev = dev;
   }
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tw, tx, ty, tr, p);
-  V100_CUDA(cudaGetLastError());
+  V100_CUDA(launch_pdl(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tw, tx, ty, tr, p));
   return 0;
 }
 
@@ -496,8 +497,7 @@ static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const 
   }
   int pairs = num_sms() / 2;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
-  kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(tw, tx, ty, tr, p);
-  V100_CUDA(cudaGetLastError());
+  V100_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tw, tx, ty, tr, p));
   return 0;
 }
 

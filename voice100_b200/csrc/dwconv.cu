@@ -105,6 +105,8 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
   const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
   const int n_tiles = (len + s + 127) / 128;
   const int n_chunks = min(kDwRow / 8, 16 * n_tiles + 2 * Q);   // 16-byte chunks the tiles actually read
+  pdl_trigger();
+  pdl_wait();        // (x is the previous kernel's output)
   dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane, n_chunks);   // first row in flight
 
   // zero-extended filter: ws[16 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
@@ -212,6 +214,7 @@ dw_s2_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsi
   __shared__ __align__(8) float ws_all[kDwWarps][2 * kS2MaxWords];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.y * kDwWarps + warp;
+  pdl_trigger();
   if (c >= C) return;
   const int b = blockIdx.z;
   const int oc0 = blockIdx.x * kS2Chunk;
@@ -220,6 +223,7 @@ dw_s2_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsi
   const int e = p8 - p;                       // xs[2*ol + j + e] = x[2*(oc0+ol) + j - p]
   unsigned short* xs = xs_all[warp];
   float* ws = ws_all[warp];
+  pdl_wait();
   const unsigned short* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
   const int ia = 2 * oc0 - p8;
   for (int v = lane; v < kS2Row / 8; v += 32) {
@@ -274,6 +278,8 @@ dw_simt_kernel(const unsigned short* __restrict__ x, long long x_pitch, const un
                long long y_pitch, int C, int T_in, int T_out, int k, int stride, int act) {
   const int c = blockIdx.y, b = blockIdx.z;
   const int o0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+  pdl_trigger();
+  pdl_wait();
   if (o0 >= T_out) return;
   const int p = (k - 1) >> 1;
   const unsigned short* xrow = x + (static_cast<long long>(b) * C + c) * x_pitch;
@@ -309,10 +315,11 @@ static void launch_dw_mma_dt(const void* x, int64_t x_pitch, const void* w, cons
   auto xp = static_cast<const unsigned short*>(x);
   auto wp = static_cast<const unsigned short*>(w);
   auto yp = static_cast<unsigned short*>(y);
+  const long long xpl = x_pitch, ypl = y_pitch;
   if (act == V100_ACT_RELU6)
-    dw_mma_kernel<Q, true, DT><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
+    launch_pdl(dw_mma_kernel<Q, true, DT>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T, k);
   else
-    dw_mma_kernel<Q, false, DT><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, B, C, T, k);
+    launch_pdl(dw_mma_kernel<Q, false, DT>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T, k);
 }
 
 template <int Q>
@@ -352,16 +359,18 @@ int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, 
     }
   } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
     dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
+    const long long xpl = x_pitch, ypl = y_pitch;
     if (dtype == DT_F16)
-      dw_s2_kernel<DT_F16><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, act);
+      launch_pdl(dw_s2_kernel<DT_F16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, C, T_in, T_out, k, act);
     else
-      dw_s2_kernel<DT_BF16><<<grid, kDwWarps * 32, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, act);
+      launch_pdl(dw_s2_kernel<DT_BF16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, C, T_in, T_out, k, act);
   } else {
     dim3 grid((T_out + 1023) / 1024, C, B);
+    const long long xpl = x_pitch, ypl = y_pitch;
     if (dtype == DT_F16)
-      dw_simt_kernel<DT_F16><<<grid, 128, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, stride, act);
+      launch_pdl(dw_simt_kernel<DT_F16>, grid, dim3(128), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, C, T_in, T_out, k, stride, act);
     else
-      dw_simt_kernel<DT_BF16><<<grid, 128, 0, stream>>>(xp, x_pitch, wp, scale, shift, yp, y_pitch, C, T_in, T_out, k, stride, act);
+      launch_pdl(dw_simt_kernel<DT_BF16>, grid, dim3(128), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, C, T_in, T_out, k, stride, act);
   }
   V100_CUDA(cudaGetLastError());
   return 0;

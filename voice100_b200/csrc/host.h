@@ -21,6 +21,26 @@ int num_sms();
       return ::v100::fail(static_cast<int>(e__), "%s -> %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
+// Launch with programmatic stream serialization (see pdl_wait / pdl_trigger in common.cuh): the kernel may start
+// while the previous kernel of the stream is still draining.  ONLY for kernels that call pdl_wait() before touching
+// data of the chain.  V100_PDL=0 in the environment turns the attribute off (plain stream order) for A/B runs.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // 16-bit tensor maps, 128-byte swizzle, zero fill out of bounds.  Dimensions innermost first.
 int make_tmap_2d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t stride1_bytes, int box0, int box1);
 int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t d0, int64_t d1, int64_t d2, int64_t stride1_bytes,
@@ -35,23 +55,25 @@ int convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const f
 int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
              int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype, int force_simt,
              cudaStream_t stream);
-int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const int32_t* fb_start,
-           const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T,
-           int64_t out_pitch, int out_mode, cudaStream_t stream);
+int logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
+           const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, int fb_nnz,
+           float log_offset, void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out,
+           cudaStream_t stream);
 int ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, cudaStream_t stream);
 int ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream);
 int ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, cudaStream_t stream);
 int embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
-                    cudaStream_t stream);
+                    int32_t* status, cudaStream_t stream);
 int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* tokens, int B, int V, int T,
-                 cudaStream_t stream);
+                 const int32_t* audio_len, int32_t* out_len, cudaStream_t stream);
 int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, int32_t* out_len, int B, int T,
                  int blank, cudaStream_t stream);
 int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
                   uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V, int L,
-                  cudaStream_t stream);
+                  int normalize, cudaStream_t stream);
 int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* std, float* hasf0, float* f0,
-                   float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream);
+                   float* logspc, float* hascodeap, float* codeap, int B, int T, int logspc_size, int codeap_size,
+                   int layout, int unnormalize, cudaStream_t stream);
 int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream);
 
 // v2 models (seq.cu)

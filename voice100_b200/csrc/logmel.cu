@@ -3,215 +3,272 @@
 //
 // Replaces reflect-pad + unfold + window + cuFFT R2C + abs/pow + sgemm + add/log + transpose
 // (>= 6 library launches, and a 257-bin complex spectrum written to and read back from HBM).
-// Sixteen threads transform one frame: 256 = 16 x 16, two 16-point FFTs in registers with one transpose
-// through shared memory in between (logmel_core.h); a CTA of 8 warps produces a [64 mel x 64 frame] tile so
-// that the NCW output rows are written as full 128-byte lines.  The kernel is bound by FFT arithmetic and
-// shared-memory traffic, not by HBM (64 KB in + 12.8 KB out per audio-second); see DESIGN.md.
+//
+// Round-2 structure (the round-1 kernel spent 6,144 CTA prologues on sincospif tables, 17 M bank-conflict
+// wavefronts in the mel stage and ran at 24 % warp occupancy):
+//   * persistent CTAs walk [clip, 32-frame] tiles; the window, the W256^(q k1) twiddle table and the filter
+//     descriptors are built once per CTA;
+//   * FFT phase: sixteen threads per frame (logmel_core.h), two 16-point FFTs in registers around one 16 x 16
+//     transpose through a stride-17 shared buffer; the conjugate partner Z[256-k] of the real-FFT unpacking is
+//     always an upper-half register of lane (16-q)&15, so it comes by warp shuffle, not through shared memory,
+//     and one complex multiply serves both bins of a conjugate pair;
+//   * the 257 power bins of the tile's 32 frames go to P[bin][frame] (stride 33, conflict-free for the two
+//     half-warps of a warp, whose frames are 16 apart);
+//   * mel phase: LANE = FRAME.  A warp applies one filter at a time to 32 frames: P[(s0+tap)*33 + lane] is one
+//     conflict-free wavefront per tap and the weight is a warp-uniform broadcast;
+//   * input is fp32 or int16 PCM (scaled by 1/32768 in the kernel = what torchaudio.load produces for 16-bit WAV,
+//     so the two entry forms are bit-identical on such data) -- the int16 form halves the H2D stream.
+// The kernel is bound by instruction issue and shared-memory wavefronts, not by HBM (64 KB in + 12.8 KB out per
+// audio-second); see DESIGN.md.
 #include "common.cuh"
 #include "host.h"
 #include "logmel_core.h"
 
+#include <cstdlib>
+
 namespace v100 {
 
-constexpr int kMelWarps = 8;
-constexpr int kMelFrames = 64;  // frames per CTA
 constexpr int kNMels = 64;
 constexpr int kNFft = 512, kWin = 400, kHop = 160, kWinLeft = (kNFft - kWin) / 2;  // data_modules.py:266-269
-constexpr int kMelMaxTaps = 24;   // longest mel filter (bins); the HTK bank at 512/16 kHz/64 needs 20
-// shared memory: twiddles, window pairs, mel weights, output tile, and per half-warp an exchange buffer (16 x 17
-// complex, reused for the 257 power bins) and the packed spectrum Z (256 complex)
-constexpr int kMelExch = 16 * 17 + 8;  // + 8: consecutive half-warps' buffers start 16 banks apart, so the 32-bit
-                                       // power-spectrum accesses of the two frames of a warp do not collide
-constexpr int kMelSmemBytes = 512 * 8 + 256 * 8 + kMelMaxTaps * kNMels * 4 + kNMels * (kMelFrames + 1) * 4 +
-                              2 * kMelWarps * (kMelExch + 256) * 8;
+constexpr int kMelTile = 32;         // frames per tile
+constexpr int kPStride = 33;
+constexpr int kMelMaxNnz = 64 * 32;  // accepted filter-bank size (the HTK bank at 512/16 kHz/64 has 500)
 
-__global__ void __launch_bounds__(kMelWarps * 32, 2)
-logmel_kernel(const float* __restrict__ wav, const int32_t* __restrict__ len, long long wav_pitch,
-              const int32_t* __restrict__ fb_start, const int32_t* __restrict__ fb_count,
-              const int32_t* __restrict__ fb_off, const float* __restrict__ fb_w, float log_offset, void* out, int T,
-              long long out_pitch, int out_mode) {
+template <int NW>
+struct MelCfg {
+  static constexpr int kHalfWarps = 2 * NW;
+  static constexpr int kIters = kMelTile / kHalfWarps;          // FFT passes per tile
+  static constexpr int kWinBytes = 256 * 8;                     // float2 window of samples (2n, 2n+1)
+  static constexpr int kTwBytes = 16 * 16 * 8;                  // W256^(q k1) as [k1][q]
+  static constexpr int kFbBytes = 3 * kNMels * 4;               // start, count, offset
+  static constexpr int kEBytes = kHalfWarps * 16 * 17 * 8;      // exchange buffers (reused as the NTC output tile)
+  static constexpr int kPBytes = (257 * kPStride * 4 + 15) & ~15;
+  static constexpr int kSmemBytes = kWinBytes + kTwBytes + kFbBytes + kEBytes + kPBytes;
+  static_assert(kIters >= 1 && kIters * kHalfWarps == kMelTile, "a tile is a whole number of passes");
+  static_assert(kEBytes >= kMelTile * (kNMels + 1) * 4, "the NTC output tile aliases the exchange buffers");
+};
+
+struct MelParams {
+  const void* wav;
+  const int32_t* len;
+  long long wav_pitch;
+  int L_max;
+  const int32_t *fb_start, *fb_count, *fb_off;
+  const float* fb_w;
+  float log_offset;
+  void* out;
+  int T;
+  long long out_pitch;
+  int out_mode;
+  int32_t* frames_out;
+  int tiles_per_clip, total_tiles;
+};
+
+template <int NW, bool I16>
+__global__ void __launch_bounds__(NW * 32, NW == 16 ? 2 : 3)
+logmel_kernel(const MelParams p) {
+  using Cfg = MelCfg<NW>;
   extern __shared__ __align__(16) uint8_t mel_smem[];
-  cpx* tw = reinterpret_cast<cpx*>(mel_smem);                                  // [512] exp(-2 pi i k / 512)
-  float2* win2 = reinterpret_cast<float2*>(tw + 512);                          // [256] window of samples 2n, 2n+1
-  float (*melw)[kNMels] = reinterpret_cast<float (*)[kNMels]>(win2 + 256);      // [kMelMaxTaps][64] tap-major
-  float (*tile)[kMelFrames + 1] = reinterpret_cast<float (*)[kMelFrames + 1]>(melw + kMelMaxTaps);  // [64][65]
-  cpx* exch = reinterpret_cast<cpx*>(tile + kNMels);                           // [16 half-warps][16 x 17]
-  cpx* zbuf = exch + 2 * kMelWarps * kMelExch;                                 // [16 half-warps][256]
+  float2* win2 = reinterpret_cast<float2*>(mel_smem);                                   // [256]
+  cpx* twt = reinterpret_cast<cpx*>(mel_smem + Cfg::kWinBytes);                         // [16 k1][16 q]
+  int* fbs = reinterpret_cast<int*>(mel_smem + Cfg::kWinBytes + Cfg::kTwBytes);         // [3][64]
+  cpx* exch = reinterpret_cast<cpx*>(mel_smem + Cfg::kWinBytes + Cfg::kTwBytes + Cfg::kFbBytes);
+  float* P = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(exch) + Cfg::kEBytes);  // [257][33]
+  float* otile = reinterpret_cast<float*>(exch);                                        // [32][65] (NTC mode)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int f0 = blockIdx.x * kMelFrames;
+  const float in_scale = I16 ? (1.0f / 32768.0f) : 1.0f;
+  pdl_trigger();
 
-  for (int k = threadIdx.x; k < 512; k += blockDim.x) {
-    float sn, cs;
-    sincospif(-float(k) / 256.0f, &sn, &cs);  // exp(-2*pi*i*k/512)
-    tw[k] = cpx{cs, sn};
-  }
-  for (int n = threadIdx.x; n < 256; n += blockDim.x) {   // periodic Hann(400) centred in the 512 frame
+  // ---- once per CTA: window, twiddles, filter descriptors ----
+  for (int n = threadIdx.x; n < 256; n += NW * 32) {   // periodic Hann(400) centred in the 512 frame
     float w2[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int m = 2 * n + h - kWinLeft;
-      w2[h] = (m >= 0 && m < kWin) ? 0.5f - 0.5f * cospif(float(2 * m) / float(kWin)) : 0.0f;
+      w2[h] = (m >= 0 && m < kWin) ? (0.5f - 0.5f * cospif(float(2 * m) / float(kWin))) * in_scale : 0.0f;
     }
     win2[n] = make_float2(w2[0], w2[1]);
   }
-  for (int i = threadIdx.x; i < kMelMaxTaps * kNMels; i += blockDim.x) {   // melw[tap][filter], zero padded
-    const int tap = i / kNMels, m = i - tap * kNMels;
-    melw[tap][m] = tap < __ldg(fb_count + m) ? __ldg(fb_w + __ldg(fb_off + m) + tap) : 0.0f;
+  for (int i = threadIdx.x; i < 256; i += NW * 32) {   // twt[k1][q] = exp(-2 pi i q k1 / 256)
+    const int k1 = i >> 4, qq = i & 15;
+    float sn, cs;
+    sincospif(-float((2 * qq * k1) & 511) / 256.0f, &sn, &cs);
+    twt[i] = cpx{cs, sn};
   }
+  for (int i = threadIdx.x; i < kNMels; i += NW * 32) {
+    fbs[i] = __ldg(p.fb_start + i);
+    fbs[kNMels + i] = __ldg(p.fb_count + i);
+    fbs[2 * kNMels + i] = __ldg(p.fb_off + i);
+  }
+  const int q = lane & 15, half = lane >> 4;
+  cpx wq;                                              // exp(-2 pi i q / 512)
+  {
+    float sn, cs;
+    sincospif(-float(q) / 256.0f, &sn, &cs);
+    wq = cpx{cs, sn};
+  }
+  cpx* E = exch + (warp * 2 + half) * (16 * 17);
+  const int partner_lane = (lane & 16) | ((16 - q) & 15);
+  const float blank = p.out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(p.log_offset);
   __syncthreads();
+  pdl_wait();   // the tables above overlapped the previous kernel; the waveform / output buffers may still be in use by it
 
-  // ---- sixteen threads per frame (logmel_core.h, "register-resident variant"); a warp works on two frames ----
-  const int q = lane & 15, hw = warp * 2 + (lane >> 4);
-  cpx* E = exch + hw * kMelExch;
-  cpx* Z = zbuf + hw * 256;
-  float* P = reinterpret_cast<float*>(E);  // the power spectrum reuses the exchange buffer (257 <= 544 floats)
-  cpx twq[16];                             // W256^(q k1), constant per thread
-#pragma unroll
-  for (int k1 = 0; k1 < 16; ++k1) twq[k1] = tw[(2 * q * k1) & 511];
-  const cpx wq = tw[q];                    // exp(-2 pi i (q + 16 k2) / 512) = wq * exp(-2 pi i k2 / 32)
-  int s0[4], cmax[4];                      // this thread's mel filters q + 16 i
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    s0[i] = __ldg(fb_start + q + 16 * i);
-    int c = __ldg(fb_count + q + 16 * i);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
-    cmax[i] = c;                           // trip count of the 16 filters handled together
-  }
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int b = tile / p.tiles_per_clip;
+    const int f0 = (tile - b * p.tiles_per_clip) * kMelTile;
+    const int L = min(max(__ldg(p.len + b), 0), p.L_max);
+    const int n_frames = L > 0 ? 1 + L / kHop : 0;     // frames with data; the rest of the row is BLANK_AUDIO
+    if (p.frames_out != nullptr && f0 == 0 && threadIdx.x == 0) p.frames_out[b] = 1 + L / kHop;
+    const float* xf = static_cast<const float*>(p.wav) + static_cast<long long>(b) * p.wav_pitch;
+    const short* xi = static_cast<const short*>(p.wav) + static_cast<long long>(b) * p.wav_pitch;
+    const bool vec_ok = I16 ? ((reinterpret_cast<uintptr_t>(xi) & 3) == 0) : ((reinterpret_cast<uintptr_t>(xf) & 7) == 0);
 
-  const int L = len[b];
-  const int n_frames = 1 + L / kHop;
-  const float* x = wav + static_cast<long long>(b) * wav_pitch;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
-  const float blank = out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(log_offset);
-
-  for (int fi = 0; fi < kMelFrames / (2 * kMelWarps); ++fi) {
-    // the two half-warps of a warp take frames 16 apart: their tile[mel][frame] stores land 16 banks apart
-    const int fl = 16 * (2 * (fi >> 1) + (hw & 1)) + 2 * (hw >> 1) + (fi & 1);
-    const int t = f0 + fl;
-    const bool valid = t < n_frames;
-    if (!__any_sync(0xffffffffu, valid)) {
+    // ---------------- FFT phase: one frame per half-warp and pass ----------------
+#pragma unroll 1
+    for (int it = 0; it < Cfg::kIters; ++it) {
+      const int fl = warp + NW * it + 16 * half;       // the two frames of a warp are 16 apart (P bank layout)
+      const int t = f0 + fl;
+      const bool valid = t < n_frames;
+      if (!__any_sync(0xffffffffu, valid)) continue;   // nothing to transform; the mel phase writes `blank`
+      // frame t covers reflect-padded samples [160 t, 160 t + 512) = clip samples 160 t - 256 + m; this thread
+      // takes the complex points n = q + 16 r (samples 2n, 2n+1); the window is zero for n < 28 and n >= 228
+      cpx v[16];
+      const int base = kHop * t - kNFft / 2;
+      v[0] = cpx{0.0f, 0.0f};
+      v[15] = cpx{0.0f, 0.0f};
+      if (valid && vec_ok && base + kWinLeft >= 0 && base + kWinLeft + kWin <= L) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) tile[q + 16 * i][fl] = blank;
-      continue;
-    }
-    // frame t covers reflect-padded samples [160 t, 160 t + 512) = clip samples 160 t - 256 + m;
-    // this thread takes the complex points n = q + 16 r (samples 2n, 2n+1); the window is zero for n < 28, n >= 228
-    cpx v[16];
-    const int base = kHop * t - kNFft / 2;
-    v[0] = cpx{0.0f, 0.0f};
-    v[15] = cpx{0.0f, 0.0f};
-    if (valid && vec_ok && base + kWinLeft >= 0 && base + kWinLeft + kWin <= L) {
-#pragma unroll
-      for (int r = 1; r < 15; ++r) {
-        const int n = q + 16 * r;
-        float2 sv = make_float2(0.0f, 0.0f);
-        if (n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) sv = __ldg(reinterpret_cast<const float2*>(x + base + 2 * n));
-        const float2 w2 = win2[n];
-        v[r] = cpx{sv.x * w2.x, sv.y * w2.y};
-      }
-    } else {
-#pragma unroll
-      for (int r = 1; r < 15; ++r) {
-        const int n = q + 16 * r;
-        const float2 w2 = win2[n];
-        float sv[2] = {0.0f, 0.0f};
-        if (valid && n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            int i = base + 2 * n + h;
-            i = i < 0 ? -i : i;
-            i = i >= L ? 2 * (L - 1) - i : i;
-            sv[h] = __ldg(x + i);
+        for (int r = 1; r < 15; ++r) {
+          const int n = q + 16 * r;
+          float2 sv = make_float2(0.0f, 0.0f);
+          if (n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) {
+            if constexpr (I16) {
+              const short2 s2 = __ldg(reinterpret_cast<const short2*>(xi + base + 2 * n));
+              sv = make_float2(float(s2.x), float(s2.y));
+            } else {
+              sv = __ldg(reinterpret_cast<const float2*>(xf + base + 2 * n));
+            }
           }
+          const float2 w2 = win2[n];
+          v[r] = cpx{sv.x * w2.x, sv.y * w2.y};
         }
-        v[r] = cpx{sv[0] * w2.x, sv[1] * w2.y};
+      } else {
+#pragma unroll
+        for (int r = 1; r < 15; ++r) {
+          const int n = q + 16 * r;
+          const float2 w2 = win2[n];
+          float sv[2] = {0.0f, 0.0f};
+          if (valid && n >= kWinLeft / 2 && n < (kWinLeft + kWin) / 2) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              int i = base + 2 * n + h;
+              i = i < 0 ? -i : i;
+              i = i >= L ? 2 * (L - 1) - i : i;
+              i = min(max(i, 0), L - 1);               // clips of <= 256 samples (torchaudio refuses them): stay in bounds
+              sv[h] = I16 ? float(__ldg(xi + i)) : __ldg(xf + i);
+            }
+          }
+          v[r] = cpx{sv[0] * w2.x, sv[1] * w2.y};
+        }
       }
+      fft16(v);                                              // over r:  Y[q][k1]
+      E[q] = v[0];
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) E[k1 * 17 + q] = cmul(v[k1], twt[k1 * 16 + q]);
+      __syncwarp();
+#pragma unroll
+      for (int qq = 0; qq < 16; ++qq) v[qq] = E[q * 17 + qq]; // this thread is now k1 = q
+      __syncwarp();                                          // E is free for the next pass
+      fft16(v);                                              // over q:  v[k2] = Z[q + 16 k2]
+      // conjugate pairs (k, 256 - k), k = q + 16 k2 < 128: Z[256 - k] is register 15 - k2 of lane (16 - q) & 15
+      // (for q = 0: this thread's own register (16 - k2) & 15)
+      float* Pf = P + fl;
+#pragma unroll
+      for (int k2 = 0; k2 < 8; ++k2) {
+        cpx zn;
+        zn.x = __shfl_sync(0xffffffffu, v[15 - k2].x, partner_lane);
+        zn.y = __shfl_sync(0xffffffffu, v[15 - k2].y, partner_lane);
+        if (q == 0) zn = v[(16 - k2) & 15];
+        float ck, sk;
+        sincospif(-float(k2) / 16.0f, &sk, &ck);             // exp(-2 pi i 16 k2 / 512): compile-time constants
+        float pk, pn;
+        rfft512_power_both(v[k2], zn, cmul(wq, cpx{ck, sk}), &pk, &pn);
+        const int k = q + 16 * k2;
+        Pf[k * kPStride] = pk;
+        Pf[(256 - k) * kPStride] = pn;
+      }
+      if (q == 0) Pf[128 * kPStride] = rfft512_power_pair(v[8], v[8], cpx{0.0f, -1.0f});
     }
-    fft16(v);                                              // over r:  Y[q][k1]
-    E[q] = v[0];
-#pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) E[k1 * 17 + q] = cmul(v[k1], twq[k1]);
-    __syncwarp();
-#pragma unroll
-    for (int qq = 0; qq < 16; ++qq) v[qq] = E[q * 17 + qq]; // this thread is now k1 = q
-    fft16(v);                                              // over q:  v[k2] = Z[q + 16 k2]
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) Z[q + 16 * k2] = v[k2];
-    __syncwarp();                                          // (every lane is past its reads of E: P may overwrite it)
-#pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) {
-      float ck, sk;
-      sincospif(-float(k2) / 16.0f, &sk, &ck);             // exp(-2 pi i 16 k2 / 512): compile-time constants
-      const int k = q + 16 * k2;
-      P[k] = rfft512_power_pair(v[k2], Z[(256 - k) & 255], cmul(wq, cpx{ck, sk}));
-    }
-    if (q == 0) P[256] = rfft512_power_pair(v[0], v[0], cpx{-1.0f, 0.0f});
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = q + 16 * i;
-      float acc = 0.0f;                                    // melw is zero past each filter's own length; P stays in range
-      for (int tap = 0; tap < cmax[i]; ++tap) acc = fmaf(melw[tap][m], P[min(s0[i] + tap, 256)], acc);
-      tile[m][fl] = !valid ? blank : (out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + log_offset));
-    }
-    __syncwarp();                                          // P (= E) is free for the next frame
-  }
-  __syncthreads();
+    __syncthreads();
 
-  const int tid = threadIdx.x;
-  if (out_mode == V100_MEL_LOG_BF16_NCW || out_mode == V100_MEL_LOG_F16_NCW) {
-    const int m = tid >> 2, fs = (tid & 3) * 16;
-    unsigned short* row = static_cast<unsigned short*>(out) + (static_cast<long long>(b) * kNMels + m) * out_pitch;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int t = f0 + fs + 8 * h;
-      if (t < out_pitch) {
-        const float* s = &tile[m][fs + 8 * h];
-        uint4 v;
-        if (out_mode == V100_MEL_LOG_F16_NCW) {
-          v.x = pack_f16x2(s[0], s[1]); v.y = pack_f16x2(s[2], s[3]);
-          v.z = pack_f16x2(s[4], s[5]); v.w = pack_f16x2(s[6], s[7]);
-        } else {
-          v.x = pack_bf16x2(s[0], s[1]); v.y = pack_bf16x2(s[2], s[3]);
-          v.z = pack_bf16x2(s[4], s[5]); v.w = pack_bf16x2(s[6], s[7]);
+    // ---------------- mel phase: lane = frame, one filter at a time per warp ----------------
+    {
+      const int t = f0 + lane;
+      const bool valid = t < n_frames;
+      const float* Pl = P + lane;
+#pragma unroll 1
+      for (int m = warp; m < kNMels; m += NW) {
+        const int s0 = fbs[m], cnt = fbs[kNMels + m];
+        const float* w = p.fb_w + fbs[2 * kNMels + m];
+        const float* Pm = Pl + s0 * kPStride;
+        float acc = 0.0f;
+        for (int tap = 0; tap < cnt; ++tap) acc = fmaf(__ldg(w + tap), Pm[tap * kPStride], acc);
+        const float val = !valid ? blank : (p.out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + p.log_offset));
+        if (p.out_mode == V100_MEL_LOG_F32_NTC) {
+          otile[lane * (kNMels + 1) + m] = val;
+        } else if (t < p.out_pitch) {
+          const long long o = (static_cast<long long>(b) * kNMels + m) * p.out_pitch + t;
+          if (p.out_mode == V100_MEL_POWER_F32_NCW) static_cast<float*>(p.out)[o] = val;
+          else if (p.out_mode == V100_MEL_LOG_F16_NCW) static_cast<unsigned short*>(p.out)[o] = f2h<DT_F16>(val);
+          else static_cast<unsigned short*>(p.out)[o] = f2h<DT_BF16>(val);
         }
-        *reinterpret_cast<uint4*>(row + t) = v;
       }
     }
-  } else if (out_mode == V100_MEL_POWER_F32_NCW) {
-    const int m = tid >> 2, fs = (tid & 3) * 16;
-    float* row = static_cast<float*>(out) + (static_cast<long long>(b) * kNMels + m) * out_pitch;
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      const int t = f0 + fs + 4 * h;
-      if (t < out_pitch) {
-        const float* s = &tile[m][fs + 4 * h];
-        *reinterpret_cast<float4*>(row + t) = make_float4(s[0], s[1], s[2], s[3]);
+    __syncthreads();
+    if (p.out_mode == V100_MEL_LOG_F32_NTC) {   // out[b][t][64]: transpose through the tile
+      for (int i = threadIdx.x; i < kMelTile * (kNMels / 4); i += NW * 32) {
+        const int fl = i >> 4, m4 = (i & 15) * 4;
+        const int t = f0 + fl;
+        if (t < p.T) {
+          const float* s = otile + fl * (kNMels + 1) + m4;
+          *reinterpret_cast<float4*>(static_cast<float*>(p.out) + (static_cast<long long>(b) * p.T + t) * kNMels + m4) =
+              make_float4(s[0], s[1], s[2], s[3]);
+        }
       }
-    }
-  } else {  // V100_MEL_LOG_F32_NTC: out[b][t][64]
-    const int fl = tid >> 2, ms = (tid & 3) * 16;
-    const int t = f0 + fl;
-    if (t < T) {
-      float* row = static_cast<float*>(out) + (static_cast<long long>(b) * T + t) * kNMels + ms;
-#pragma unroll
-      for (int h = 0; h < 4; ++h)
-        *reinterpret_cast<float4*>(row + 4 * h) =
-            make_float4(tile[ms + 4 * h][fl], tile[ms + 4 * h + 1][fl], tile[ms + 4 * h + 2][fl], tile[ms + 4 * h + 3][fl]);
+      __syncthreads();
     }
   }
 }
 
-int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const int32_t* fb_start,
-           const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T,
-           int64_t out_pitch, int out_mode, cudaStream_t stream) {
+template <int NW, bool I16>
+static int launch_logmel(const MelParams& p, cudaStream_t stream) {
+  using Cfg = MelCfg<NW>;
+  auto kern = logmel_kernel<NW, I16>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V100_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured_dev = dev;
+  }
+  const int per_sm = NW == 16 ? 2 : 3;
+  const int grid = p.total_tiles < per_sm * num_sms() ? p.total_tiles : per_sm * num_sms();
+  V100_CUDA(launch_pdl(kern, dim3(grid), dim3(NW * 32), Cfg::kSmemBytes, stream, p));
+  return 0;
+}
+
+int logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
+           const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, int fb_nnz,
+           float log_offset, void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out,
+           cudaStream_t stream) {
   if (wav == nullptr || len == nullptr || out == nullptr || fb_start == nullptr || fb_count == nullptr ||
       fb_off == nullptr || fb_w == nullptr)
     return fail(V100_E_INVALID, "logmel: null pointer");
-  if (B <= 0 || T <= 0 || B > 65535) return fail(V100_E_INVALID, "logmel: bad B=%d or T=%d", B, T);
+  if (wav_dtype != V100_WAV_F32 && wav_dtype != V100_WAV_I16) return fail(V100_E_INVALID, "logmel: wav_dtype must be V100_WAV_F32 or V100_WAV_I16");
+  if (B <= 0 || T <= 0) return fail(V100_E_INVALID, "logmel: bad B=%d or T=%d", B, T);
+  if (L_max < 0 || wav_pitch < L_max) return fail(V100_E_INVALID, "logmel: wav_pitch %lld < L_max %d", (long long)wav_pitch, L_max);
+  if (fb_nnz < 0 || fb_nnz > kMelMaxNnz) return fail(V100_E_UNSUPPORTED, "logmel: filter bank with %d weights (max %d)", fb_nnz, kMelMaxNnz);
   if (out_mode == V100_MEL_LOG_BF16_NCW || out_mode == V100_MEL_LOG_F16_NCW) {
     if (out_pitch < T || (out_pitch & 7) || (reinterpret_cast<uintptr_t>(out) & 15))
       return fail(V100_E_INVALID, "logmel: 16-bit NCW pitch must be >= T and a multiple of 8, base 16B aligned");
@@ -223,18 +280,19 @@ int logmel(const float* wav, const int32_t* len, int B, int64_t wav_pitch, const
   } else {
     return fail(V100_E_INVALID, "logmel: unknown out_mode %d", out_mode);
   }
-  static thread_local int configured_dev = -1;
-  int dev = 0;
-  V100_CUDA(cudaGetDevice(&dev));
-  if (configured_dev != dev) {
-    V100_CUDA(cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmemBytes));
-    configured_dev = dev;
-  }
-  dim3 grid((T + kMelFrames - 1) / kMelFrames, B);
-  logmel_kernel<<<grid, kMelWarps * 32, kMelSmemBytes, stream>>>(wav, len, wav_pitch, fb_start, fb_count, fb_off, fb_w,
-                                                     log_offset, out, T, out_pitch, out_mode);
-  V100_CUDA(cudaGetLastError());
-  return 0;
+  MelParams p{};
+  p.wav = wav; p.len = len; p.wav_pitch = wav_pitch; p.L_max = L_max;
+  p.fb_start = fb_start; p.fb_count = fb_count; p.fb_off = fb_off; p.fb_w = fb_w;
+  p.log_offset = log_offset; p.out = out; p.T = T; p.out_pitch = out_pitch; p.out_mode = out_mode;
+  p.frames_out = frames_out;
+  const long long cols = out_mode == V100_MEL_LOG_F32_NTC ? T : out_pitch;   // NCW rows are written to the pitch
+  p.tiles_per_clip = int((cols + kMelTile - 1) / kMelTile);
+  const long long total = static_cast<long long>(p.tiles_per_clip) * B;
+  if (total > 2147483647LL) return fail(V100_E_UNSUPPORTED, "logmel: too many tiles");
+  p.total_tiles = int(total);
+  static const int nw = getenv("V100_MEL_WARPS") ? atoi(getenv("V100_MEL_WARPS")) : 16;   // A/B runs
+  if (nw == 8) return wav_dtype == V100_WAV_I16 ? launch_logmel<8, true>(p, stream) : launch_logmel<8, false>(p, stream);
+  return wav_dtype == V100_WAV_I16 ? launch_logmel<16, true>(p, stream) : launch_logmel<16, false>(p, stream);
 }
 
 }  // namespace v100

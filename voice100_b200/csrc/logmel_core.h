@@ -86,4 +86,16 @@ V100_HD float rfft512_power_pair(cpx zk, cpx zn, cpx wk) {
   return re * re + im * im;
 }
 
+// Both halves of one conjugate pair at once: with E = (Z[k] + conj Z[N-k]) / 2 and O = -i (Z[k] - conj Z[N-k]) / 2,
+// X[k] = E + W^k O and X[256 - k] = conj(E - W^k O), so one complex multiply serves the two power bins.
+V100_HD void rfft512_power_both(cpx zk, cpx zn, cpx wk, float* pk, float* pn) {
+  const cpx e{0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+  const cpx o{0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x)};
+  const cpx wo = cmul(wk, o);
+  const float re = e.x + wo.x, im = e.y + wo.y;
+  const float rn = e.x - wo.x, in = e.y - wo.y;
+  *pk = re * re + im * im;
+  *pn = rn * rn + in * in;
+}
+
 }  // namespace v100

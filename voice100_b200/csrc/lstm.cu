@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <cstdlib>
+
 namespace v100 {
 
 // ------------------------------------------------------------------------------------------------
@@ -319,14 +321,33 @@ static int lstm_layer_pair(const void* gx, const void* w_hh, const int32_t* leng
   const size_t smem = 1024 + size_t(KB) * 4096 + 4 * kPairBatch * kPairUnits * 4 + 64;
   auto kern = dtype == DT_F16 ? lstm_pair_kernel<DT_F16> : lstm_pair_kernel<DT_BF16>;
   V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  // every CTA pair of a launch must be co-resident (one CTA per SM): (SMs / 2) pairs at most
-  const int max_groups = (num_sms() / 2) / (2 * p.pairs);
-  if (max_groups < 1) return fail(V100_E_UNSUPPORTED, "lstm_layer: device too small for H=%d", H);
+  // Every CTA pair of a launch must be co-resident: the chain of a (direction, group) hands h_t from pair to pair
+  // through a global counter.  Two guards: (1) the launch is sized from what the occupancy calculator says fits on
+  // this device (one CTA per SM, clusters of two), and refused if not even one group fits; (2) it is a COOPERATIVE
+  // launch, so the hardware starts it only when all of its CTAs can be resident -- a concurrent kernel or MPS
+  // client that holds SMs delays the launch instead of leaving half a chain spinning until the poll traps.
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kPairThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];                 // (the cluster shape is the kernel's compile-time __cluster_dims__)
+  attrs[0].id = cudaLaunchAttributeCooperative;
+  attrs[0].val.cooperative = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 0;
+  cfg.gridDim = dim3(2 * p.pairs * 2);          // one group: 2 directions x pairs clusters x 2 CTAs
+  int max_clusters = 0;
+  V100_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+  const int max_groups = max_clusters / (2 * p.pairs);
+  if (max_groups < 1)
+    return fail(V100_E_UNSUPPORTED, "lstm_layer: H=%d needs %d co-resident CTA pairs, this device fits %d", H, 2 * p.pairs, max_clusters);
+  static const bool cooperative = getenv("V100_LSTM_NONCOOP") == nullptr;
+  cfg.numAttrs = cooperative ? 1 : 0;
   for (int g0 = 0; g0 < p.groups_total; g0 += max_groups) {
     p.group0 = g0;
     p.groups = p.groups_total - g0 < max_groups ? p.groups_total - g0 : max_groups;
-    kern<<<2 * p.groups * p.pairs * 2, kPairThreads, smem, stream>>>(tm_h, p);
-    V100_CUDA(cudaGetLastError());
+    cfg.gridDim = dim3(2 * p.groups * p.pairs * 2);
+    V100_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_h, p));
   }
   return 0;
 }

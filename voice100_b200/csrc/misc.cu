@@ -82,7 +82,7 @@ int ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T,
 // y[b][c][t] = table[ids[b][t]][c]; one thread = one channel x 8 time steps (16-byte store).
 __global__ void __launch_bounds__(256)
 embedding_kernel(const int64_t* __restrict__ ids, const unsigned short* __restrict__ table,
-                 unsigned short* __restrict__ y, long long y_pitch, int T, int V, int C) {
+                 unsigned short* __restrict__ y, long long y_pitch, int T, int V, int C, int32_t* __restrict__ status) {
   const int b = blockIdx.z;
   const int c = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int t0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 8;
@@ -95,9 +95,11 @@ embedding_kernel(const int64_t* __restrict__ ids, const unsigned short* __restri
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int t = t0 + i + h;
-      long long id = t < T ? ids[static_cast<long long>(b) * T + t] : 0;
-      id = id < 0 ? 0 : (id >= V ? V - 1 : id);
-      v[h] = t < T ? tab[id * C + c] : 0;
+      const long long id = t < T ? ids[static_cast<long long>(b) * T + t] : 0;
+      const bool ok = id >= 0 && id < V;
+      // nn.Embedding raises IndexError for such an id; a kernel cannot, so the row is zero and the flag is set
+      if (!ok && status != nullptr && c == 0) atomicOr(status, V100_STATUS_BAD_INDEX);
+      v[h] = (t < T && ok) ? tab[id * C + c] : 0;
     }
     o[i >> 1] = uint32_t(v[0]) | (uint32_t(v[1]) << 16);
   }
@@ -105,14 +107,14 @@ embedding_kernel(const int64_t* __restrict__ ids, const unsigned short* __restri
 }
 
 int embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pitch, int B, int T, int V, int C,
-                       cudaStream_t stream) {
+                    int32_t* status, cudaStream_t stream) {
   if (ids == nullptr || table == nullptr || y == nullptr) return fail(V100_E_INVALID, "embedding: null pointer");
   if (B <= 0 || T <= 0 || V <= 0 || C <= 0 || B > 65535) return fail(V100_E_INVALID, "embedding: bad sizes");
   if (y_pitch < T || (y_pitch & 7) || (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(V100_E_INVALID, "embedding: pitch must be >= T and a multiple of 8, base 16B aligned");
   dim3 grid((T + 255) / 256, (C + 7) / 8, B);
   embedding_kernel<<<grid, 256, 0, stream>>>(ids, static_cast<const unsigned short*>(table),
-                                             static_cast<unsigned short*>(y), y_pitch, T, V, C);
+                                             static_cast<unsigned short*>(y), y_pitch, T, V, C, status);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
@@ -120,9 +122,15 @@ int embedding_ncw16(const int64_t* ids, const void* table, void* y, int64_t y_pi
 // fp32 NCW [B][V][pitch] -> logits [B][T][V] (optional) + greedy tokens (first maximal index).
 __global__ void __launch_bounds__(128)
 ctc_finalize_kernel(const float* __restrict__ y, long long pitch, float* __restrict__ logits,
-                    int64_t* __restrict__ tokens, int V, int T) {
+                    int64_t* __restrict__ tokens, int V, int T, const int32_t* __restrict__ audio_len,
+                    int32_t* __restrict__ out_len) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * 128 + threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
+  // ConvVoiceEncoder.output_length (asr.py:81-82): (audio_len + 1) // 2, emitted here so the pipeline needs no
+  // separate element-wise launch
+  if (out_len != nullptr && blockIdx.x == 0 && threadIdx.x == 0) out_len[b] = (audio_len[b] + 1) / 2;
   if (t >= T) return;
   const float* col = y + static_cast<long long>(b) * V * pitch + t;
   float best = col[0];
@@ -138,12 +146,13 @@ ctc_finalize_kernel(const float* __restrict__ y, long long pitch, float* __restr
 }
 
 int ctc_finalize(const float* y_ncw, int64_t y_pitch, float* logits, int64_t* tokens, int B, int V, int T,
-                 cudaStream_t stream) {
+                 const int32_t* audio_len, int32_t* out_len, cudaStream_t stream) {
   if (y_ncw == nullptr || tokens == nullptr) return fail(V100_E_INVALID, "ctc_finalize: null pointer");
+  if ((audio_len == nullptr) != (out_len == nullptr)) return fail(V100_E_INVALID, "ctc_finalize: audio_len and out_len go together");
   if (B <= 0 || V <= 0 || T <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "ctc_finalize: bad sizes");
   dim3 grid((T + 127) / 128, B);
-  ctc_finalize_kernel<<<grid, 128, 0, stream>>>(y_ncw, y_pitch, logits, tokens, V, T);
-  V100_CUDA(cudaGetLastError());
+  V100_CUDA(launch_pdl(ctc_finalize_kernel, grid, dim3(128), 0, stream, y_ncw, static_cast<long long>(y_pitch), logits,
+                       tokens, V, T, audio_len, out_len));
   return 0;
 }
 
@@ -190,43 +199,75 @@ int ctc_collapse(const int64_t* tokens, const int64_t* valid_len, int64_t* out, 
 // is one parallel sweep over the states, back-pointers go to a caller-provided workspace.  Arithmetic is the
 // reference's: fp32 `score[k] + logprob[i][label[v]]`, candidates j = 0,1,2 (stay / advance / skip, the skip
 // never lands on a blank), first maximum wins, the active prefix grows by two states per step.
+// With `normalize` the input is raw logits and the kernel applies log_softmax itself (_asr_v2.py:95):
+// lse[i] = max + log(sum exp(x - max)) per frame, one warp per frame, kept in shared memory.
 __global__ void __launch_bounds__(256)
 ctc_best_path_kernel(const float* __restrict__ logprob, const int32_t* __restrict__ logit_len,
                      const int64_t* __restrict__ text, const int32_t* __restrict__ text_len,
                      uint8_t* __restrict__ back, float* __restrict__ score, int32_t* __restrict__ path,
-                     int64_t* __restrict__ path_labels, int T, int V, int L) {
+                     int64_t* __restrict__ path_labels, int T, int V, int L, int normalize) {
   extern __shared__ float vit_smem[];
   const int b = blockIdx.x;
   const int S_max = 2 * L + 1;
   float* sc0 = vit_smem;
   float* sc1 = vit_smem + S_max;
   int* lab = reinterpret_cast<int*>(vit_smem + 2 * S_max);
+  float* lse = vit_smem + 3 * S_max;                 // [T] when normalize
+  __shared__ int bad_label;
   const int n = min(max(logit_len[b], 0), T);
   const int l = min(max(text_len[b], 0), L);
   const int S = 2 * l + 1;
   const float* lp = logprob + static_cast<long long>(b) * T * V;
   uint8_t* bk = back + static_cast<long long>(b) * T * S_max;
   const float NEG_INF = __int_as_float(0xff800000);
+  const float NAN_F = __int_as_float(0x7fc00000);
 
+  if (threadIdx.x == 0) bad_label = 0;
+  __syncthreads();
   for (int v = threadIdx.x; v < S; v += blockDim.x) {
-    lab[v] = (v & 1) ? static_cast<int>(text[static_cast<long long>(b) * L + (v >> 1)]) : 0;
+    long long lb = (v & 1) ? text[static_cast<long long>(b) * L + (v >> 1)] : 0;
+    if (lb < 0 || lb >= V) { bad_label = 1; lb = 0; }   // numpy would raise IndexError: reject the utterance
+    lab[v] = static_cast<int>(lb);
     sc0[v] = NEG_INF;
   }
-  __syncthreads();
-  if (n == 0) {
-    if (threadIdx.x == 0) score[b] = __int_as_float(0x7fc00000);
-    return;
+  if (normalize) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < n; i += 8) {
+      const float* row = lp + static_cast<long long>(i) * V;
+      float mx = NEG_INF;
+      for (int v = lane; v < V; v += 32) mx = fmaxf(mx, row[v]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float sum = 0.0f;
+      for (int v = lane; v < V; v += 32) sum += expf(row[v] - mx);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) { lse[2 * i] = mx; lse[2 * i + 1] = logf(sum); }
+    }
   }
-  if (threadIdx.x < 2 && threadIdx.x < S) sc0[threadIdx.x] = lp[lab[threadIdx.x]];
+  __syncthreads();
+  auto fail_row = [&]() {
+    if (threadIdx.x == 0) score[b] = NAN_F;
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+      path[static_cast<long long>(b) * T + i] = -1;
+      path_labels[static_cast<long long>(b) * T + i] = 0;
+    }
+  };
+  if (n == 0 || bad_label) { fail_row(); return; }
+  // log_softmax(x) = (x - max) - log(sum exp(x - max)), the order torch evaluates it in
+  auto emit = [&](int i, int v) -> float {
+    const float x = lp[static_cast<long long>(i) * V + lab[v]];
+    return normalize ? (x - lse[2 * i]) - lse[2 * i + 1] : x;
+  };
+  if (threadIdx.x < 2 && threadIdx.x < S) sc0[threadIdx.x] = emit(0, threadIdx.x);
   __syncthreads();
   int len = min(2, S);
   float* prev = sc0;
   float* next = sc1;
   for (int i = 1; i < n; ++i) {
     const int len_next = min(len + 2, S);
-    const float* row = lp + static_cast<long long>(i) * V;
     for (int v = threadIdx.x; v < len_next; v += blockDim.x) {
-      const float e = row[lab[v]];
+      const float e = emit(i, v);
       float best = NEG_INF;
       int best_j = 0;
 #pragma unroll
@@ -245,36 +286,34 @@ ctc_best_path_kernel(const float* __restrict__ logprob, const int32_t* __restric
     float* t = prev; prev = next; next = t;
     len = len_next;
   }
+  // the reference ends with  j = labels_len + (-1 if scores[-1] > scores[-2] else -2); best = scores[j]  on the
+  // `len` live scores: IndexError when len < 2 (empty text) or j >= len -- i.e. always when fewer than S - 1 states
+  // were reached, and for len == S - 1 only when the last live score is the larger one (align.py:57-58)
+  int j = (len >= 2) ? S + ((prev[len - 1] > prev[len - 2]) ? -1 : -2) : S;
+  if (j >= len) { fail_row(); return; }
   if (threadIdx.x == 0) {
-    if (len < S || S < 2) {
-      // the reference indexes scores[labels_len - 1] here and raises IndexError: too few frames for this text
-      score[b] = __int_as_float(0x7fc00000);
-      for (int i = 0; i < T; ++i) { path[static_cast<long long>(b) * T + i] = -1; path_labels[static_cast<long long>(b) * T + i] = 0; }
-    } else {
-      int j = S + ((prev[S - 1] > prev[S - 2]) ? -1 : -2);
-      score[b] = prev[j];
-      for (int i = n - 1; i >= 0; --i) {
-        path[static_cast<long long>(b) * T + i] = j;
-        path_labels[static_cast<long long>(b) * T + i] = lab[j];
-        if (i > 0) {
-          const uint8_t code = bk[static_cast<long long>(i) * S_max + j];
-          j = code == 3 ? 0 : j - code;
-        }
+    score[b] = prev[j];
+    for (int i = n - 1; i >= 0; --i) {
+      path[static_cast<long long>(b) * T + i] = j;
+      path_labels[static_cast<long long>(b) * T + i] = lab[j];
+      if (i > 0) {
+        const uint8_t code = bk[static_cast<long long>(i) * S_max + j];
+        j = code == 3 ? 0 : j - code;
       }
-      for (int i = n; i < T; ++i) { path[static_cast<long long>(b) * T + i] = 0; path_labels[static_cast<long long>(b) * T + i] = 0; }
     }
+    for (int i = n; i < T; ++i) { path[static_cast<long long>(b) * T + i] = 0; path_labels[static_cast<long long>(b) * T + i] = 0; }
   }
 }
 
 int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t* text, const int32_t* text_len,
                   uint8_t* workspace, float* score, int32_t* path, int64_t* path_labels, int B, int T, int V, int L,
-                  cudaStream_t stream) {
+                  int normalize, cudaStream_t stream) {
   if (logprob == nullptr || logit_len == nullptr || text == nullptr || text_len == nullptr || workspace == nullptr ||
       score == nullptr || path == nullptr || path_labels == nullptr)
     return fail(V100_E_INVALID, "ctc_best_path: null pointer");
   if (B <= 0 || T <= 0 || V <= 0 || L <= 0) return fail(V100_E_INVALID, "ctc_best_path: bad sizes");
-  const size_t smem = size_t(3) * (2 * L + 1) * 4;
-  if (smem > 200 * 1024) return fail(V100_E_UNSUPPORTED, "ctc_best_path: text length %d too long for shared memory", L);
+  const size_t smem = size_t(3) * (2 * L + 1) * 4 + (normalize ? size_t(2) * T * 4 : 0);
+  if (smem > 200 * 1024) return fail(V100_E_UNSUPPORTED, "ctc_best_path: text length %d / %d frames too long for shared memory", L, T);
   static thread_local int configured_dev = -1;
   int dev = 0;
   V100_CUDA(cudaGetDevice(&dev));
@@ -283,7 +322,7 @@ int ctc_best_path(const float* logprob, const int32_t* logit_len, const int64_t*
     configured_dev = dev;
   }
   ctc_best_path_kernel<<<B, 256, smem, stream>>>(logprob, logit_len, text, text_len, workspace, score, path,
-                                                 path_labels, T, V, L);
+                                                 path_labels, T, V, L, normalize);
   V100_CUDA(cudaGetLastError());
   return 0;
 }
@@ -314,24 +353,36 @@ int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C
   return 0;
 }
 
-// WORLD head tail.  Channel order of the decoder output (tts.py:160-167,181-190):
-//   0 = hasf0 logit, 1 = f0, 2..258 = logspc[257], 259 = codeap.
-// mean/std index: 0 = f0, 1..257 = logspc, 258 = codeap.
+// WORLD head tail: split the decoder output into its parameter groups, un-normalise (WORLDNorm.unnormalize,
+// _layers_v1.py:131-138) and apply the presence gates, transposing NCW -> [B][T][.] on the way.
+//   layout 1 (AlignTextToAudioModel, tts.py:160-167,181-190):  [hasf0 | f0 | logspc(S) | codeap(A)]
+//   layout 2 (AlignTextToAudio, _tts_v2.py:65-71,80-91):       [hasf0 | f0 | logspc(S) | hascodeap(A) | codeap(A)]
+// S = logspc_size (257 bins, or 25 mel-cepstra with use_mcep), A = codeap_size.
+// mean/std index: 0 = f0, 1..S = logspc, S+1..S+A = codeap.  With `unnormalize`: v = std*v + mean, f0 = 0 where
+// hasf0 < 0, and (layout 2) codeap = 0 where hascodeap < 0.
 __global__ void __launch_bounds__(256)
 world_finalize_kernel(const float* __restrict__ y, long long pitch, const float* __restrict__ mean,
                       const float* __restrict__ stdv, float* __restrict__ hasf0, float* __restrict__ f0,
-                      float* __restrict__ logspc, float* __restrict__ codeap, int T, int unnormalize) {
+                      float* __restrict__ logspc, float* __restrict__ hascodeap, float* __restrict__ codeap, int T,
+                      int S, int A, int layout, int unnormalize) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  constexpr int C = 260;
+  const int i_hc = 2 + S;                               // first hascodeap channel (layout 2)
+  const int i_ap = layout == 2 ? 2 + S + A : 2 + S;     // first codeap channel
+  const int C = i_ap + A;
+  const float* yb = y + static_cast<long long>(b) * C * pitch;
   for (int r = ty; r < 32; r += 8) {
     const int c = c0 + r, t = t0 + tx;
     float v = 0.0f;
     if (c < C && t < T) {
-      v = y[(static_cast<long long>(b) * C + c) * pitch + t];
-      if (unnormalize && c >= 1) v = fmaf(stdv[c - 1], v, mean[c - 1]);
-      if (unnormalize && c == 1 && y[(static_cast<long long>(b) * C) * pitch + t] < 0.0f) v = 0.0f;
+      v = yb[static_cast<long long>(c) * pitch + t];
+      if (unnormalize) {
+        if (c >= 1 && c < i_hc) v = fmaf(stdv[c - 1], v, mean[c - 1]);
+        else if (c >= i_ap) v = fmaf(stdv[1 + S + (c - i_ap)], v, mean[1 + S + (c - i_ap)]);
+        if (c == 1 && yb[t] < 0.0f) v = 0.0f;
+        if (layout == 2 && c >= i_ap && yb[static_cast<long long>(i_hc + (c - i_ap)) * pitch + t] < 0.0f) v = 0.0f;
+      }
     }
     tile[r][tx] = v;
   }
@@ -343,19 +394,25 @@ world_finalize_kernel(const float* __restrict__ y, long long pitch, const float*
     const long long bt = static_cast<long long>(b) * T + t;
     if (c == 0) { if (hasf0) hasf0[bt] = v; }
     else if (c == 1) f0[bt] = v;
-    else if (c < 259) logspc[bt * 257 + (c - 2)] = v;
-    else codeap[bt] = v;
+    else if (c < i_hc) logspc[bt * S + (c - 2)] = v;
+    else if (c < i_ap) { if (hascodeap) hascodeap[bt * A + (c - i_hc)] = v; }
+    else codeap[bt * A + (c - i_ap)] = v;
   }
 }
 
 int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const float* stdv, float* hasf0, float* f0,
-                   float* logspc, float* codeap, int B, int T, int unnormalize, cudaStream_t stream) {
+                   float* logspc, float* hascodeap, float* codeap, int B, int T, int logspc_size, int codeap_size,
+                   int layout, int unnormalize, cudaStream_t stream) {
   if (y_ncw == nullptr || f0 == nullptr || logspc == nullptr || codeap == nullptr)
     return fail(V100_E_INVALID, "world_finalize: null pointer");
+  if (layout != 1 && layout != 2) return fail(V100_E_INVALID, "world_finalize: layout must be 1 (v1) or 2 (v2)");
+  if (logspc_size <= 0 || codeap_size <= 0) return fail(V100_E_INVALID, "world_finalize: bad logspc/codeap size");
   if (unnormalize && (mean == nullptr || stdv == nullptr)) return fail(V100_E_INVALID, "world_finalize: null mean/std");
   if (B <= 0 || T <= 0 || B > 65535 || y_pitch < T) return fail(V100_E_INVALID, "world_finalize: bad sizes");
-  dim3 grid((T + 31) / 32, (260 + 31) / 32, B);
-  world_finalize_kernel<<<grid, 256, 0, stream>>>(y_ncw, y_pitch, mean, stdv, hasf0, f0, logspc, codeap, T, unnormalize);
+  const int C = 2 + logspc_size + (layout == 2 ? 2 : 1) * codeap_size;
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B);
+  world_finalize_kernel<<<grid, 256, 0, stream>>>(y_ncw, y_pitch, mean, stdv, hasf0, f0, logspc, hascodeap, codeap, T,
+                                                  logspc_size, codeap_size, layout, unnormalize);
   V100_CUDA(cudaGetLastError());
   return 0;
 }

@@ -87,26 +87,39 @@ class MelSpectrogramAudioTransform(nn.Module):
         lead, L = waveform.shape[:-1], waveform.shape[-1]
         if L <= self.n_fft // 2:
             raise V100Error(f"clips must be longer than {self.n_fft // 2} samples (reflect padding)")
-        wav = waveform.reshape(-1, L).to(torch.float32).contiguous()
+        wav = self._samples(waveform.reshape(-1, L))
         lengths = torch.full((wav.shape[0],), L, dtype=torch.int32, device=wav.device)
         T = self.num_frames(L)
-        out = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, K.MEL_POWER_F32_NCW)
+        out, _ = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, K.MEL_POWER_F32_NCW)
         return out.valid().reshape(*lead, self.n_mels, T)
 
+    @staticmethod
+    def _samples(waveform: torch.Tensor) -> torch.Tensor:
+        """fp32 samples, or int16 PCM passed through untouched (the kernel scales by 1/32768, which is what
+        torchaudio.load returns for a 16-bit WAV -- data_modules.py:288 -- so both forms give identical features)."""
+        if waveform.dtype == torch.int16:
+            return waveform.contiguous()
+        return waveform.to(torch.float32).contiguous()
+
     def logmel_batch(self, waveform: torch.Tensor, lengths: torch.Tensor, ncw_bf16: bool = False, ncw_dtype=None):
-        """waveform fp32 [B, L_max], lengths [B] samples ->
+        """waveform fp32 (or int16 PCM) [B, L_max], lengths [B] samples ->
         (audio fp32 [B, T_max, 64] padded with BLANK_AUDIO  |  16-bit Ncw [B, 64, pitch] when `ncw_dtype`
-         (torch.bfloat16 / torch.float16) or `ncw_bf16` is given,  audio_len int32 [B])."""
+         (torch.bfloat16 / torch.float16) or `ncw_bf16` is given,  audio_len int32 [B] = 1 + len // 160).
+        Host-resident `lengths` are validated like torchaudio does (reflect padding needs > n_fft/2 samples, 0 =
+        an empty filler slot); device-resident ones are clamped to [0, L_max] by the kernel."""
         if ncw_bf16 and ncw_dtype is None:
             ncw_dtype = torch.bfloat16
         if not waveform.is_cuda:
             raise V100Error("MelSpectrogramAudioTransform runs only on CUDA tensors (no CPU path)")
-        wav = waveform.to(torch.float32).contiguous()
+        wav = self._samples(waveform)
+        if not lengths.is_cuda and lengths.numel():
+            lo, hi = int(lengths.min()), int(lengths.max())
+            if hi > wav.shape[1] or ((lengths > 0) & (lengths <= self.n_fft // 2)).any():
+                raise V100Error(f"clip lengths must be 0 (empty slot) or in ({self.n_fft // 2}, {wav.shape[1]}]; got [{lo}, {hi}]")
         lengths = lengths.to(device=wav.device, dtype=torch.int32).contiguous()
         T = self.num_frames(wav.shape[1])
         mode = K.MEL_LOG_F32_NTC if ncw_dtype is None else (K.MEL_LOG_F16_NCW if K.dt(ncw_dtype) == 1 else K.MEL_LOG_BF16_NCW)
-        out = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, mode)
-        return out, 1 + torch.div(lengths, self.hop_length, rounding_mode="trunc")
+        return K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, mode)
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
         """One clip `[L] -> [T, 64]` log-mel features.  (The reference's forward takes a file path and does

@@ -25,8 +25,25 @@ def dt(t) -> int:
     return DTYPE_CODE[d]
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _call(anchor, name, *args):
+    """Invoke entry point `name` on the device that holds `anchor` (a tensor or Ncw/Tm): the C side launches on
+    cudaGetDevice()'s device, so that device is made current for the call and the stream passed is ITS current
+    stream -- a model living on cuda:1 works without torch.cuda.set_device(1)."""
+    t = anchor if isinstance(anchor, torch.Tensor) else anchor.data
+    dev = t.device
+    if dev.type != "cuda":
+        raise _lib.V100Error("voice100_b200 kernels need CUDA tensors (there is no CPU path)")
+    if torch.cuda.current_device() == dev.index:
+        return _lib.call(name, *args, torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        return _lib.call(name, *args, torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _same_device(*tensors):
+    """All operands of one call must live on one GPU (a mixed call would hand the kernel a foreign pointer)."""
+    devs = {(t if isinstance(t, torch.Tensor) else t.data).device for t in tensors if t is not None}
+    if len(devs) > 1:
+        raise _lib.V100Error(f"operands of one kernel call live on different devices: {sorted(map(str, devs))}")
 
 
 def _ptr(t):
@@ -73,8 +90,13 @@ def _cuda(t: torch.Tensor, dtype=None):
 
 
 def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: int, mode: int):
-    """wav fp32 [B, L]; lengths int32 [B] (device); fb = (start, count, off, w) device tensors."""
-    _cuda(wav, torch.float32), _cuda(lengths, torch.int32)
+    """wav fp32 or int16 PCM [B, L]; lengths int32 [B] (device); fb = (start, count, off, w) device tensors.
+    -> (features, audio_len int32 [B] = 1 + len // 160, written by the same kernel)."""
+    _cuda(lengths, torch.int32)
+    if wav.dtype not in (torch.float32, torch.int16):
+        raise _lib.V100Error(f"waveforms must be float32 or int16 PCM, got {wav.dtype}")
+    _cuda(wav)
+    _same_device(wav, lengths, fb[3])
     B = wav.shape[0]
     if mode in (MEL_LOG_BF16_NCW, MEL_LOG_F16_NCW):
         out = empty_ncw(B, 64, T, wav.device, torch.bfloat16 if mode == MEL_LOG_BF16_NCW else torch.float16)
@@ -85,17 +107,18 @@ def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: i
     else:
         out = torch.empty((B, T, 64), device=wav.device, dtype=torch.float32)
         optr, pitch = out.data_ptr(), 64
-    _lib.call("v100_logmel", wav.data_ptr(), lengths.data_ptr(), B, wav.stride(0), fb[0].data_ptr(),
-              fb[1].data_ptr(), fb[2].data_ptr(), fb[3].data_ptr(), float(log_offset), optr, T, pitch, mode,
-              _stream())
-    return out
+    frames = torch.empty((B,), device=wav.device, dtype=torch.int32)
+    _call(wav, "v100_logmel", wav.data_ptr(), 1 if wav.dtype == torch.int16 else 0, lengths.data_ptr(), B,
+          wav.stride(0), wav.shape[1], fb[0].data_ptr(), fb[1].data_ptr(), fb[2].data_ptr(), fb[3].data_ptr(),
+          fb[3].numel(), float(log_offset), optr, T, pitch, mode, frames.data_ptr())
+    return out, frames
 
 
 def ntc_f32_to_ncw(x: torch.Tensor, dtype=torch.bfloat16) -> Ncw:
     _cuda(x, torch.float32)
     B, T, Cc = x.shape
     y = empty_ncw(B, Cc, T, x.device, dtype)
-    _lib.call("v100_ntc_f32_to_ncw16", x.data_ptr(), y.data.data_ptr(), B, T, Cc, y.pitch, dt(dtype), _stream())
+    _call(x, "v100_ntc_f32_to_ncw16", x.data_ptr(), y.data.data_ptr(), B, T, Cc, y.pitch, dt(dtype))
     return y
 
 
@@ -103,13 +126,13 @@ def ncw_from_f32(x: torch.Tensor, dtype=torch.bfloat16) -> Ncw:
     _cuda(x, torch.float32)
     B, Cc, T = x.shape
     y = empty_ncw(B, Cc, T, x.device, dtype)
-    _lib.call("v100_ncw_f32_to_16", x.data_ptr(), y.data.data_ptr(), y.pitch, B, Cc, T, dt(dtype), _stream())
+    _call(x, "v100_ncw_f32_to_16", x.data_ptr(), y.data.data_ptr(), y.pitch, B, Cc, T, dt(dtype))
     return y
 
 
 def ncw_to_f32(x: Ncw) -> torch.Tensor:
     y = torch.empty((x.B, x.C, x.T), device=x.data.device, dtype=torch.float32)
-    _lib.call("v100_ncw_16_to_f32", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, dt(x.data), _stream())
+    _call(x, "v100_ncw_16_to_f32", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, dt(x.data))
     return y
 
 
@@ -117,12 +140,13 @@ def conv1x1(x: Ncw, W: torch.Tensor, scale, shift, act: int, res: Ncw = None) ->
     C_out, C_in = W.shape
     assert C_in == x.C, (C_in, x.C)
     assert W.dtype == x.data.dtype, "weights and activations must share the storage dtype"
+    _same_device(x, W, scale, shift, res)
     y = empty_ncw(x.B, C_out, x.T, x.data.device, x.data.dtype)
     if res is not None:
         assert res.data.shape == y.data.shape and res.T == x.T and res.data.dtype == x.data.dtype
-    _lib.call("v100_conv1x1", x.data.data_ptr(), x.pitch, W.data_ptr(), _ptr(scale), shift.data_ptr(),
+    _call(x, "v100_conv1x1", x.data.data_ptr(), x.pitch, W.data_ptr(), _ptr(scale), shift.data_ptr(),
               None if res is None else res.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, C_in, C_out, x.T,
-              act, dt(x.data), _stream())
+              act, dt(x.data))
     return y
 
 
@@ -130,18 +154,19 @@ def conv1x1_f32(x: Ncw, W: torch.Tensor, bias: torch.Tensor) -> Ncw:
     C_out, C_in = W.shape
     assert C_in == x.C and W.dtype == x.data.dtype
     y = Ncw(torch.empty((x.B, C_out, x.pitch), device=x.data.device, dtype=torch.float32), x.T)
-    _lib.call("v100_conv1x1_f32out", x.data.data_ptr(), x.pitch, W.data_ptr(), bias.data_ptr(), y.data.data_ptr(),
-              y.pitch, x.B, C_in, C_out, x.T, dt(x.data), _stream())
+    _call(x, "v100_conv1x1_f32out", x.data.data_ptr(), x.pitch, W.data_ptr(), bias.data_ptr(), y.data.data_ptr(),
+              y.pitch, x.B, C_in, C_out, x.T, dt(x.data))
     return y
 
 
 def dwconv(x: Ncw, w: torch.Tensor, scale, shift, k: int, stride: int, act: int, simt: bool = False) -> Ncw:
     T_out = (x.T - 1) // stride + 1
     assert w.dtype == x.data.dtype
+    _same_device(x, w, scale, shift)
     y = empty_ncw(x.B, x.C, T_out, x.data.device, x.data.dtype)
-    _lib.call("v100_dwconv1d_simt" if simt else "v100_dwconv1d", x.data.data_ptr(), x.pitch,
+    _call(x, "v100_dwconv1d_simt" if simt else "v100_dwconv1d", x.data.data_ptr(), x.pitch,
               w.data_ptr(), _ptr(scale), shift.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, k, stride,
-              act, dt(x.data), _stream())
+              act, dt(x.data))
     return y
 
 
@@ -150,28 +175,56 @@ def convtranspose_k5s2(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor) -> Ncw:
     assert Wp.shape[1] == 5 * x.C and Wp.dtype == x.data.dtype
     y = empty_ncw(x.B, C_out, 2 * x.T - 1, x.data.device, x.data.dtype)
     ws = torch.empty((x.B, 3 * x.C, x.pitch), device=x.data.device, dtype=x.data.dtype)
-    _lib.call("v100_convtranspose1d_k5s2", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
-              ws.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, dt(x.data), _stream())
+    _call(x, "v100_convtranspose1d_k5s2", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(),
+              ws.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, dt(x.data))
     return y
 
 
-def embedding_ncw(ids: torch.Tensor, table: torch.Tensor) -> Ncw:
+_status_words = {}
+
+
+def _status_word(device) -> torch.Tensor:
+    """One sticky int32 status word per device (V100_STATUS_* bits), shared by the index-consuming kernels."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _status_words:
+        _status_words[key] = torch.zeros((1,), device=device, dtype=torch.int32)
+    return _status_words[key]
+
+
+def embedding_ncw(ids: torch.Tensor, table: torch.Tensor, validate: bool = True) -> Ncw:
+    """ids int64 [B, T] -> 16-bit Ncw [B, C, T].  nn.Embedding raises IndexError for an id outside [0, V); with
+    `validate` (default) so does this wrapper -- it reads the kernel's sticky status word back, one tiny D2H sync.
+    Pass validate=False inside CUDA-graph capture (the column of a bad id is then zero and the flag stays set)."""
     _cuda(ids, torch.int64)
+    _same_device(ids, table)
     B, T = ids.shape
     V, Cc = table.shape
     dt(table)
     y = empty_ncw(B, Cc, T, ids.device, table.dtype)
-    _lib.call("v100_embedding_ncw16", ids.data_ptr(), table.data_ptr(), y.data.data_ptr(), y.pitch, B, T, V, Cc,
-              _stream())
+    status = _status_word(ids.device)
+    _call(ids, "v100_embedding_ncw16", ids.data_ptr(), table.data_ptr(), y.data.data_ptr(), y.pitch, B, T, V, Cc,
+          status.data_ptr())
+    if validate and not torch.cuda.is_current_stream_capturing():
+        if int(status.item()) & 1:
+            status.zero_()
+            raise IndexError(f"embedding id outside [0, {V}) (nn.Embedding raises the same IndexError)")
     return y
 
 
-def ctc_finalize(y: Ncw, want_logits: bool = True):
+def ctc_finalize(y: Ncw, want_logits: bool = True, audio_len: torch.Tensor = None):
+    """-> (logits [B, T, V] or None, tokens int64 [B, T]) and, when `audio_len` (int32 [B], device) is given, also
+    out_len int32 [B] = (audio_len + 1) // 2 written by the same kernel (AudioToTextCTC.output_length)."""
     B, V, T = y.B, y.C, y.T
     logits = torch.empty((B, T, V), device=y.data.device, dtype=torch.float32) if want_logits else None
     tokens = torch.empty((B, T), device=y.data.device, dtype=torch.int64)
-    _lib.call("v100_ctc_finalize", y.data.data_ptr(), y.pitch, _ptr(logits), tokens.data_ptr(), B, V, T, _stream())
-    return logits, tokens
+    out_len = None
+    if audio_len is not None:
+        _cuda(audio_len, torch.int32)
+        _same_device(y, audio_len)
+        out_len = torch.empty((B,), device=y.data.device, dtype=torch.int32)
+    _call(y, "v100_ctc_finalize", y.data.data_ptr(), y.pitch, _ptr(logits), tokens.data_ptr(), B, V, T,
+          _ptr(audio_len), _ptr(out_len))
+    return (logits, tokens) if audio_len is None else (logits, tokens, out_len)
 
 
 def ctc_collapse(tokens: torch.Tensor, valid_len: torch.Tensor = None, blank: int = 0):
@@ -181,15 +234,16 @@ def ctc_collapse(tokens: torch.Tensor, valid_len: torch.Tensor = None, blank: in
     out = torch.empty_like(tokens)
     out_len = torch.empty((B,), device=tokens.device, dtype=torch.int32)
     vl = None if valid_len is None else valid_len.to(device=tokens.device, dtype=torch.int64).contiguous()
-    _lib.call("v100_ctc_collapse", tokens.data_ptr(), _ptr(vl), out.data_ptr(), out_len.data_ptr(), B, T, int(blank),
-              _stream())
+    _call(tokens, "v100_ctc_collapse", tokens.data_ptr(), _ptr(vl), out.data_ptr(), out_len.data_ptr(), B, T, int(blank))
     return out, out_len
 
 
-def ctc_best_path(logprob: torch.Tensor, logit_len: torch.Tensor, text: torch.Tensor, text_len: torch.Tensor):
-    """logprob fp32 [B, T, V], logit_len [B], text int64 [B, L], text_len [B] ->
-    (score fp32 [B], path int32 [B, T] state indices, path_labels int64 [B, T])."""
+def ctc_best_path(logprob: torch.Tensor, logit_len: torch.Tensor, text: torch.Tensor, text_len: torch.Tensor,
+                  normalize: bool = False):
+    """logprob fp32 [B, T, V] (raw logits when `normalize`: the kernel applies log_softmax), logit_len [B],
+    text int64 [B, L], text_len [B] -> (score fp32 [B], path int32 [B, T] state indices, path_labels int64 [B, T])."""
     _cuda(logprob, torch.float32), _cuda(text, torch.int64)
+    _same_device(logprob, text)
     B, T, V = logprob.shape
     L = text.shape[1]
     dev = logprob.device
@@ -199,26 +253,33 @@ def ctc_best_path(logprob: torch.Tensor, logit_len: torch.Tensor, text: torch.Te
     score = torch.empty((B,), device=dev, dtype=torch.float32)
     path = torch.empty((B, T), device=dev, dtype=torch.int32)
     labels = torch.empty((B, T), device=dev, dtype=torch.int64)
-    _lib.call("v100_ctc_best_path", logprob.data_ptr(), ll.data_ptr(), text.data_ptr(), tl.data_ptr(), ws.data_ptr(),
-              score.data_ptr(), path.data_ptr(), labels.data_ptr(), B, T, V, L, _stream())
+    _call(logprob, "v100_ctc_best_path", logprob.data_ptr(), ll.data_ptr(), text.data_ptr(), tl.data_ptr(),
+          ws.data_ptr(), score.data_ptr(), path.data_ptr(), labels.data_ptr(), B, T, V, L, 1 if normalize else 0)
     return score, path, labels
 
 
-def world_finalize(y: Ncw, mean, std, unnormalize: bool):
+def world_finalize(y: Ncw, mean, std, unnormalize: bool, logspc_size: int = 257, codeap_size: int = 1,
+                   layout: int = 1):
+    """Decoder output Ncw fp32 -> layout 1: (hasf0, f0, logspc, codeap); layout 2: (hasf0, f0, logspc, hascodeap,
+    codeap).  See v100_world_finalize."""
     B, T, dev = y.B, y.T, y.data.device
-    assert y.C == 260
+    S, A = logspc_size, codeap_size
+    assert y.C == 2 + S + (2 if layout == 2 else 1) * A, (y.C, S, A, layout)
+    _same_device(y, mean, std)
     hasf0 = torch.empty((B, T), device=dev, dtype=torch.float32)
     f0 = torch.empty((B, T), device=dev, dtype=torch.float32)
-    logspc = torch.empty((B, T, 257), device=dev, dtype=torch.float32)
-    codeap = torch.empty((B, T, 1), device=dev, dtype=torch.float32)
-    _lib.call("v100_world_finalize", y.data.data_ptr(), y.pitch, _ptr(mean), _ptr(std), hasf0.data_ptr(),
-              f0.data_ptr(), logspc.data_ptr(), codeap.data_ptr(), B, T, 1 if unnormalize else 0, _stream())
-    return hasf0, f0, logspc, codeap
+    logspc = torch.empty((B, T, S), device=dev, dtype=torch.float32)
+    hascodeap = torch.empty((B, T, A), device=dev, dtype=torch.float32) if layout == 2 else None
+    codeap = torch.empty((B, T, A), device=dev, dtype=torch.float32)
+    _call(y, "v100_world_finalize", y.data.data_ptr(), y.pitch, _ptr(mean), _ptr(std), hasf0.data_ptr(),
+          f0.data_ptr(), logspc.data_ptr(), _ptr(hascodeap), codeap.data_ptr(), B, T, S, A, layout,
+          1 if unnormalize else 0)
+    return (hasf0, f0, logspc, codeap) if layout == 1 else (hasf0, f0, logspc, hascodeap, codeap)
 
 
 def ncw_f32_to_ntc(y: Ncw) -> torch.Tensor:
     out = torch.empty((y.B, y.T, y.C), device=y.data.device, dtype=torch.float32)
-    _lib.call("v100_ncw_f32_to_ntc", y.data.data_ptr(), y.pitch, out.data_ptr(), y.B, y.C, y.T, _stream())
+    _call(y, "v100_ncw_f32_to_ntc", y.data.data_ptr(), y.pitch, out.data_ptr(), y.B, y.C, y.T)
     return out
 
 
@@ -231,15 +292,15 @@ def conv1d(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor, k: int, stride: int, pa
     T_out = (x.T + 2 * pad - k) // stride + 1
     y = empty_ncw(x.B, C_out, T_out, x.data.device, x.data.dtype)
     ws = torch.empty((x.B, k * x.C, y.pitch), device=x.data.device, dtype=x.data.dtype)
-    _lib.call("v100_conv1d", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(), ws.data_ptr(),
-              y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, k, stride, pad, dt(x.data), _stream())
+    _call(x, "v100_conv1d", x.data.data_ptr(), x.pitch, Wp.data_ptr(), bias.data_ptr(), ws.data_ptr(),
+              y.data.data_ptr(), y.pitch, x.B, x.C, C_out, x.T, k, stride, pad, dt(x.data))
     return y
 
 
 def layernorm_gelu(x: Ncw, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> Ncw:
     """LayerNorm over channels + GELU(erf), in place."""
-    _lib.call("v100_layernorm_gelu", x.data.data_ptr(), x.pitch, gamma.data_ptr(), beta.data_ptr(), float(eps),
-              x.data.data_ptr(), x.pitch, x.B, x.C, x.T, dt(x.data), _stream())
+    _call(x, "v100_layernorm_gelu", x.data.data_ptr(), x.pitch, gamma.data_ptr(), beta.data_ptr(), float(eps),
+              x.data.data_ptr(), x.pitch, x.B, x.C, x.T, dt(x.data))
     return x
 
 
@@ -262,7 +323,7 @@ class Tm:
 def ncw_to_tm(x: Ncw) -> Tm:
     Bp = pitch_of(x.B)
     y = torch.empty((x.C, x.T * Bp), device=x.data.device, dtype=x.data.dtype)
-    _lib.call("v100_ncw_to_tm", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, Bp, _stream())
+    _call(x, "v100_ncw_to_tm", x.data.data_ptr(), x.pitch, y.data_ptr(), x.B, x.C, x.T, Bp)
     return Tm(y, x.B, x.T, Bp)
 
 
@@ -271,8 +332,8 @@ def conv1d_tm(x: Tm, Wp: torch.Tensor, bias: torch.Tensor, k: int) -> Tm:
     C_out = Wp.shape[0]
     assert Wp.shape[1] == k * x.C and Wp.dtype == x.data.dtype
     y = torch.empty((C_out, x.T * x.Bp), device=x.data.device, dtype=x.data.dtype)
-    _lib.call("v100_conv1d_tm", x.data.data_ptr(), Wp.data_ptr(), bias.data_ptr(), y.data_ptr(), x.C, C_out, x.T,
-              x.Bp, k, dt(x.data), _stream())
+    _call(x, "v100_conv1d_tm", x.data.data_ptr(), Wp.data_ptr(), bias.data_ptr(), y.data_ptr(), x.C, C_out, x.T,
+              x.Bp, k, dt(x.data))
     return Tm(y, x.B, x.T, x.Bp)
 
 
@@ -283,7 +344,7 @@ def layernorm_gelu_tm(x: Tm, gamma: torch.Tensor, beta: torch.Tensor, eps: float
 
 def tm_to_ncw(x: Tm) -> Ncw:
     y = empty_ncw(x.B, x.C, x.T, x.data.device, x.data.dtype)
-    _lib.call("v100_tm_to_ncw", x.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, x.Bp, _stream())
+    _call(x, "v100_tm_to_ncw", x.data.data_ptr(), y.data.data_ptr(), y.pitch, x.B, x.C, x.T, x.Bp)
     return y
 
 
@@ -304,6 +365,6 @@ def lstm_layer(x: Tm, w_ih: torch.Tensor, bias: torch.Tensor, w_hh: torch.Tensor
     gx = conv1x1(x.as_ncw(), w_ih, None, bias, ACT_NONE)           # [1, 8H, T*Bp]: every step's input projection
     y = torch.empty((2 * H, x.T * x.Bp), device=x.data.device, dtype=x.data.dtype)
     ws = workspace if workspace is not None else lstm_workspace(x.B, H, x.data.device)
-    _lib.call("v100_lstm_layer", gx.data.data_ptr(), w_hh.data_ptr(), lengths.data_ptr(), y.data_ptr(),
-              ws.data_ptr(), x.B, x.Bp, x.T, H, dt(x.data), _stream())
+    _call(x, "v100_lstm_layer", gx.data.data_ptr(), w_hh.data_ptr(), lengths.data_ptr(), y.data_ptr(),
+              ws.data_ptr(), x.B, x.Bp, x.T, H, dt(x.data))
     return Tm(y, x.B, x.T, x.Bp)

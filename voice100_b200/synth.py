@@ -110,10 +110,10 @@ def align_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=Fal
 
 
 def audio_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=False, gain=1.0,
-                     randomize_norm=False):
-    """Weights for AlignTextToAudioModel(vocab_size, hidden_size, use_mcep=False)."""
+                     randomize_norm=False, logspc_size=257):
+    """Weights for AlignTextToAudioModel(vocab_size, hidden_size, use_mcep = (logspc_size == 25))."""
     half = hidden_size // 2
-    out_ch = 1 + 1 + 257 + 1  # hasf0, f0, logspc, codeap -- voice100/models/tts.py:160-167
+    out_ch = 1 + 1 + logspc_size + 1  # hasf0, f0, logspc, codeap -- voice100/models/tts.py:160-167
     sd: Dict[str, np.ndarray] = {}
     sd["embedding.weight"] = _rng(seed, "embedding.weight").standard_normal(
         (vocab_size, hidden_size)).astype(np.float32)
@@ -129,15 +129,15 @@ def audio_state_dict(vocab_size=29, hidden_size=512, seed=1234, randomize_bn=Fal
     if randomize_norm:
         sd["norm.f0_std"] = _uniform(seed, "norm.f0_std", (1,), 20.0, 60.0)
         sd["norm.f0_mean"] = _uniform(seed, "norm.f0_mean", (1,), 100.0, 200.0)
-        sd["norm.logspc_std"] = _uniform(seed, "norm.logspc_std", (257,), 0.5, 2.0)
-        sd["norm.logspc_mean"] = _uniform(seed, "norm.logspc_mean", (257,), -8.0, -2.0)
+        sd["norm.logspc_std"] = _uniform(seed, "norm.logspc_std", (logspc_size,), 0.5, 2.0)
+        sd["norm.logspc_mean"] = _uniform(seed, "norm.logspc_mean", (logspc_size,), -8.0, -2.0)
         sd["norm.codeap_std"] = _uniform(seed, "norm.codeap_std", (1,), 0.5, 2.0)
         sd["norm.codeap_mean"] = _uniform(seed, "norm.codeap_mean", (1,), -3.0, 0.0)
     else:  # voice100/models/_layers_v1.py:100-117 defaults
         sd["norm.f0_std"] = np.ones((1,), np.float32)
         sd["norm.f0_mean"] = np.zeros((1,), np.float32)
-        sd["norm.logspc_std"] = np.ones((257,), np.float32)
-        sd["norm.logspc_mean"] = np.zeros((257,), np.float32)
+        sd["norm.logspc_std"] = np.ones((logspc_size,), np.float32)
+        sd["norm.logspc_mean"] = np.zeros((logspc_size,), np.float32)
         sd["norm.codeap_std"] = np.ones((1,), np.float32)
         sd["norm.codeap_mean"] = np.zeros((1,), np.float32)
     return sd

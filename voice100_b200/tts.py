@@ -163,14 +163,13 @@ class WORLDNorm(nn.Module):
 class AlignTextToAudioModel(StorageDtypeMixin, nn.Module):
     def __init__(self, vocab_size: int, hidden_size: int, learning_rate: float = 1e-3, use_mcep: bool = False) -> None:
         super().__init__()
-        if use_mcep:
-            raise V100Error("use_mcep=True (25 mel-cepstrum outputs) is not on the accelerated path")
         self.hparams = dict(vocab_size=vocab_size, hidden_size=hidden_size, learning_rate=learning_rate,
                             use_mcep=use_mcep)
         self.hidden_size, self.vocab_size = hidden_size, vocab_size
         self.sample_rate, self.n_fft = 16000, 512
-        self.hasf0_size, self.f0_size, self.logspc_size, self.codeap_size = 1, 1, 257, 1
-        self.audio_size = 260
+        # tts.py:164: 25 mel-cepstrum coefficients with use_mcep, else the n_fft // 2 + 1 log-spectrum bins
+        self.hasf0_size, self.f0_size, self.logspc_size, self.codeap_size = 1, 1, (25 if use_mcep else 257), 1
+        self.audio_size = self.hasf0_size + self.f0_size + self.logspc_size + self.codeap_size
         self.embedding = nn.Embedding(vocab_size, hidden_size)
         self.decoder = VoiceDecoder(hidden_size, self.audio_size)
         self.norm = WORLDNorm(self.logspc_size, self.codeap_size)
@@ -184,13 +183,13 @@ class AlignTextToAudioModel(StorageDtypeMixin, nn.Module):
         return self.decoder.run(K.embedding_ncw(aligntext.contiguous(), w["table"]))
 
     def forward(self, aligntext: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        """aligntext int64 [B, T] -> (hasf0_logits [B,T'], f0_hat [B,T'], logspc_hat [B,T',257],
+        """aligntext int64 [B, T] -> (hasf0_logits [B,T'], f0_hat [B,T'], logspc_hat [B,T',logspc_size],
         codeap_hat [B,T',1]) normalised, T' = 2T-1."""
-        return K.world_finalize(self._decode(aligntext), None, None, False)
+        return K.world_finalize(self._decode(aligntext), None, None, False, self.logspc_size, self.codeap_size, 1)
 
     def predict(self, aligntext: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> (f0 [B,T'], logspc [B,T',257], codeap [B,T',1]) un-normalised, f0 = 0 where unvoiced."""
+        """-> (f0 [B,T'], logspc [B,T',logspc_size], codeap [B,T',1]) un-normalised, f0 = 0 where unvoiced."""
         y = self._decode(aligntext)
         mean, std = self._prepared.get()["norm"]
-        _, f0, logspc, codeap = K.world_finalize(y, mean, std, True)
+        _, f0, logspc, codeap = K.world_finalize(y, mean, std, True, self.logspc_size, self.codeap_size, 1)
         return f0, logspc, codeap

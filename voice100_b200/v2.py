@@ -221,18 +221,18 @@ def _ctc_best_path_method(self, audio: torch.Tensor = None, audio_len: torch.Ten
     expanded label per frame, logits_len [B]).  (The reference's `score` output is overwritten by a leftover
     variable, _asr_v2.py:116; here it is the best-path log-probability.)"""
     from .align import ctc_best_path_batch
+    normalize = logits is None      # fresh logits: log_softmax (_asr_v2.py:95) is folded into the Viterbi kernel
     if logits is None:
         logits, logits_len = self.forward(audio, audio_len)
-        logprob = torch.log_softmax(logits, dim=-1)
     else:
-        logprob, logits_len = logits, audio_len
+        logits_len = audio_len
     if text is None:
-        return logprob.argmax(dim=-1)
-    dev = logprob.device
+        return logits.argmax(dim=-1)                                          # argmax is invariant under log_softmax
+    dev = logits.device
     logits_len = logits_len.to(dev)
     text_len = torch.minimum(logits_len, text_len.to(dev))                    # "for very short audio", :99
-    return ctc_best_path_batch(logprob.transpose(0, 1).contiguous(), logits_len.to(torch.int32), text.to(dev),
-                               text_len.to(torch.int32))
+    return ctc_best_path_batch(logits.transpose(0, 1).contiguous(), logits_len.to(torch.int32), text.to(dev),
+                               text_len.to(torch.int32), normalize=normalize)
 
 
 AudioToAlignText.ctc_best_path = torch.no_grad()(_ctc_best_path_method)
@@ -373,31 +373,29 @@ class AlignTextToAudio(StorageDtypeMixin, nn.Module):
             self.norm.load_state_dict(torch.load(audio_stat))
         self._prepared = PreparedCache(self, lambda: dict(
             table=self.embedding.weight.detach().to(self.storage_dtype).contiguous(),
-            lstm=_prepare_lstm(self.lstm, self.storage_dtype), head=_head(self.projection, self.storage_dtype)))
+            lstm=_prepare_lstm(self.lstm, self.storage_dtype), head=_head(self.projection, self.storage_dtype),
+            norm=self.norm.packed()))
         self.eval()
 
-    def forward(self, aligntext: torch.Tensor, aligntext_len: torch.Tensor):
-        """aligntext int64 [B, T], lengths [B] -> (hasf0_logits [B,T'], f0_hat [B,T'], logspc_hat [B,T',S],
-        hascodeap_logits [B,T',A], codeap_hat [B,T',A]), T' = 2*max(len) - 1 for the shipped decoder."""
+    def _decode(self, aligntext: torch.Tensor, aligntext_len: torch.Tensor) -> K.Ncw:
         require_eval_cuda(self, aligntext)
         w = self._prepared.get()
         t_max = int(aligntext_len.max())                 # pad_packed_sequence trims to the longest utterance
         tm = K.ncw_to_tm(K.embedding_ncw(aligntext[:, :t_max].contiguous(), w["table"]))
         tm = _run_lstm(tm, w["lstm"], aligntext_len)
         x = self.decoder.run(K.tm_to_ncw(tm))
-        y = K.ncw_f32_to_ntc(K.conv1x1_f32(x, *w["head"]))           # [B, T', audio_size]
-        hasf0, f0, logspc, hascodeap, codeap = torch.split(
-            y, [self.f0_size, self.f0_size, self.logspc_size, self.codeap_size, self.codeap_size], dim=2)
-        return hasf0[:, :, 0], f0[:, :, 0], logspc, hascodeap, codeap
+        return K.conv1x1_f32(x, *w["head"])              # fp32 Ncw [B, audio_size, T']
+
+    def forward(self, aligntext: torch.Tensor, aligntext_len: torch.Tensor):
+        """aligntext int64 [B, T], lengths [B] -> (hasf0_logits [B,T'], f0_hat [B,T'], logspc_hat [B,T',S],
+        hascodeap_logits [B,T',A], codeap_hat [B,T',A]), T' = 2*max(len) - 1 for the shipped decoder."""
+        return K.world_finalize(self._decode(aligntext, aligntext_len), None, None, False, self.logspc_size,
+                                self.codeap_size, 2)
 
     def predict(self, aligntext: torch.Tensor, aligntext_len: torch.Tensor):
         """-> (f0 [B,T'], logspc [B,T',S], codeap [B,T',A]) un-normalised; f0 / codeap zeroed where their presence
-        logits are negative (_tts_v2.py:80-91)."""
-        hasf0, f0, logspc, hascodeap, codeap = self.forward(aligntext, aligntext_len)
-        n = self.norm
-        f0 = n.f0_std * f0 + n.f0_mean
-        logspc = n.logspc_std * logspc + n.logspc_mean
-        codeap = n.codeap_std * codeap + n.codeap_mean
-        f0 = torch.where(hasf0 < 0, torch.zeros((), dtype=f0.dtype, device=f0.device), f0)
-        codeap = torch.where(hascodeap < 0, torch.zeros((), dtype=codeap.dtype, device=codeap.device), codeap)
+        logits are negative (_tts_v2.py:80-91) -- split, WORLDNorm.unnormalize and both `where`s in one kernel."""
+        y = self._decode(aligntext, aligntext_len)
+        mean, std = self._prepared.get()["norm"]
+        _, f0, logspc, _, codeap = K.world_finalize(y, mean, std, True, self.logspc_size, self.codeap_size, 2)
         return f0, logspc, codeap

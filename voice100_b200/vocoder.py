@@ -80,8 +80,10 @@ class AlignTextToAudioPredict(nn.Module):
         rows_w += [Wsp, W[i_hc:i_hc + A], n.codeap_std.double()[:, None] * W[i_ap:i_ap + A]]
         rows_b += [bsp, b[i_hc:i_hc + A], n.codeap_std.double() * b[i_ap:i_ap + A] + n.codeap_mean.double()]
         dtype = m.storage_dtype
+        n_out = 1 + Wsp.shape[0] + A                       # un-normalisation is already in W', b': identity statistics
+        dev = W.device
         return dict(w=torch.cat(rows_w, 0).to(dtype).contiguous(), b=torch.cat(rows_b, 0).float().contiguous(),
-                    bins=Wsp.shape[0])
+                    bins=Wsp.shape[0], ident=(torch.zeros(n_out, device=dev), torch.ones(n_out, device=dev)))
 
     def forward(self, aligntext: torch.Tensor, aligntext_len: torch.Tensor) -> Tuple[torch.Tensor, ...]:
         m = self.model
@@ -91,9 +93,7 @@ class AlignTextToAudioPredict(nn.Module):
         tm = K.ncw_to_tm(K.embedding_ncw(aligntext[:, :t_max].contiguous(), mw["table"]))
         tm = _run_lstm(tm, mw["lstm"], aligntext_len)
         x = m.decoder.run(K.tm_to_ncw(tm))
-        y = K.ncw_f32_to_ntc(K.conv1x1_f32(x, w["w"], w["b"]))
-        hasf0, f0, logspc, hascodeap, codeap = torch.split(y, [1, 1, w["bins"], m.codeap_size, m.codeap_size], dim=2)
-        zero = torch.zeros((), dtype=y.dtype, device=y.device)
-        f0 = torch.where(hasf0[:, :, 0] < 0, zero, f0[:, :, 0])
-        codeap = torch.where(hascodeap < 0, zero, codeap)
+        # split + the f0 / codeap presence gates in one kernel (the statistics passed are the identity)
+        _, f0, logspc, _, codeap = K.world_finalize(K.conv1x1_f32(x, w["w"], w["b"]), w["ident"][0], w["ident"][1],
+                                                    True, w["bins"], m.codeap_size, 2)
         return f0, logspc, codeap
