@@ -77,6 +77,9 @@ def tts_v2_case():
 # STATED TOLERANCES of the ASR path (DESIGN.md section 4 has the error budget they come from).
 # bf16 storage through 28 convolutions of a random-init, BN-calibrated network, versus the fp32 reference:
 BF16_VS_FP32 = dict(max_rel_std=0.45, rms_rel_std=0.08, raw_agreement=0.90)
+# ... and for the NARROW fixture models (hidden 128: fewer terms per dot product average less rounding noise out; not a
+# configuration the reference ships), versus fp32:
+BF16_VS_FP32_NARROW = dict(max_rel_std=0.60, rms_rel_std=0.10, raw_agreement=0.90)
 # fp16 storage (3 more mantissa bits), versus the fp32 reference:
 F16_VS_FP32 = dict(max_rel_std=0.08, rms_rel_std=0.015, raw_agreement=0.97)
 # versus the oracle evaluated with the SAME storage roundings (only accumulation order differs) -- the check that

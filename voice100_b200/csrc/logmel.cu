@@ -32,7 +32,7 @@ constexpr int kNMels = 64;
 constexpr int kNFft = 512, kWin = 400, kHop = 160, kWinLeft = (kNFft - kWin) / 2;  // data_modules.py:266-269
 constexpr int kMelTile = 32;         // frames per tile
 constexpr int kPStride = 33;
-constexpr int kMelMaxNnz = 64 * 32;  // accepted filter-bank size (the HTK bank at 512/16 kHz/64 has 500)
+constexpr int kMelMaxNnz = 1024;     // accepted filter-bank size (the HTK bank at 512/16 kHz/64 has 500 weights)
 
 template <int NW>
 struct MelCfg {
@@ -40,7 +40,8 @@ struct MelCfg {
   static constexpr int kIters = kMelTile / kHalfWarps;          // FFT passes per tile
   static constexpr int kWinBytes = 256 * 8;                     // float2 window of samples (2n, 2n+1)
   static constexpr int kTwBytes = 16 * 16 * 8;                  // W256^(q k1) as [k1][q]
-  static constexpr int kFbBytes = 3 * kNMels * 4;               // start, count, offset
+  static constexpr int kFbBytes = 3 * kNMels * 4 + (kMelMaxNnz + 4 * kNMels) * 4;   // start, count, offset; weights, each
+                                                                // filter's run padded to a multiple of four
   static constexpr int kEBytes = kHalfWarps * 16 * 17 * 8;      // exchange buffers (reused as the NTC output tile)
   static constexpr int kPBytes = (257 * kPStride * 4 + 15) & ~15;
   static constexpr int kSmemBytes = kWinBytes + kTwBytes + kFbBytes + kEBytes + kPBytes;
@@ -96,10 +97,26 @@ logmel_kernel(const MelParams p) {
     sincospif(-float((2 * qq * k1) & 511) / 256.0f, &sn, &cs);
     twt[i] = cpx{cs, sn};
   }
-  for (int i = threadIdx.x; i < kNMels; i += NW * 32) {
-    fbs[i] = __ldg(p.fb_start + i);
-    fbs[kNMels + i] = __ldg(p.fb_count + i);
-    fbs[2 * kNMels + i] = __ldg(p.fb_off + i);
+  float* fbw = reinterpret_cast<float*>(fbs + 3 * kNMels);     // filter m's weights at fbw[fbs[2*64 + m] ...], 16-byte aligned,
+  if (threadIdx.x < 32) {                                      // zero-padded to a multiple of four taps
+    int run = 0;                                               // (one warp: exclusive scan of the padded counts)
+    for (int m0 = 0; m0 < kNMels; m0 += 32) {
+      const int m = m0 + lane;
+      const int cnt = __ldg(p.fb_count + m), pad = (cnt + 3) & ~3;
+      int incl = pad;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const int off = run + incl - pad;
+      fbs[m] = __ldg(p.fb_start + m);
+      fbs[kNMels + m] = pad;
+      fbs[2 * kNMels + m] = off;
+      const float* src = p.fb_w + __ldg(p.fb_off + m);
+      for (int i = 0; i < pad; ++i) fbw[off + i] = i < cnt ? __ldg(src + i) : 0.0f;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
   }
   const int q = lane & 15, half = lane >> 4;
   cpx wq;                                              // exp(-2 pi i q / 512)
@@ -209,11 +226,20 @@ logmel_kernel(const MelParams p) {
       const float* Pl = P + lane;
 #pragma unroll 1
       for (int m = warp; m < kNMels; m += NW) {
-        const int s0 = fbs[m], cnt = fbs[kNMels + m];
-        const float* w = p.fb_w + fbs[2 * kNMels + m];
+        const int s0 = fbs[m], cnt4 = fbs[kNMels + m];            // taps, rounded up to four (zero weights)
+        const float4* w4 = reinterpret_cast<const float4*>(fbw + fbs[2 * kNMels + m]);
+        // (a padded tap may point one to three rows past the filter: clamp the row, its weight is zero)
         const float* Pm = Pl + s0 * kPStride;
+        const int last = (256 - s0) * kPStride;
         float acc = 0.0f;
-        for (int tap = 0; tap < cnt; ++tap) acc = fmaf(__ldg(w + tap), Pm[tap * kPStride], acc);
+        for (int tap = 0; tap < cnt4; tap += 4) {                 // same summation order as a plain tap loop
+          const float4 w = w4[tap >> 2];                          // warp-uniform address: one broadcast
+          const int o = tap * kPStride;
+          acc = fmaf(w.x, Pm[min(o, last)], acc);
+          acc = fmaf(w.y, Pm[min(o + kPStride, last)], acc);
+          acc = fmaf(w.z, Pm[min(o + 2 * kPStride, last)], acc);
+          acc = fmaf(w.w, Pm[min(o + 3 * kPStride, last)], acc);
+        }
         const float val = !valid ? blank : (p.out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + p.log_offset));
         if (p.out_mode == V100_MEL_LOG_F32_NTC) {
           otile[lane * (kNMels + 1) + m] = val;
