@@ -131,6 +131,17 @@ int v100_dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* sc
   return dwconv1d(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, stride, act, dtype, 0, STREAM(stream));
 }
 
+int v100_dw_pack_pairs(const void* w, uint32_t* pairs, int C, int k, void* stream) {
+  return dw_pack_pairs(w, pairs, C, k, STREAM(stream));
+}
+
+int v100_expand_dw(const void* x, int64_t x_pitch, const void* W1, const float* scale1, const float* shift1,
+                   const uint32_t* dw_pairs, const float* scale2, const float* shift2, void* y, int64_t y_pitch,
+                   int B, int C_in, int H, int T, int k, int dtype, void* stream) {
+  return expand_dw(x, x_pitch, W1, scale1, shift1, dw_pairs, scale2, shift2, y, y_pitch, B, C_in, H, T, k, dtype,
+                   STREAM(stream));
+}
+
 // Same contract as v100_dwconv1d but always the plain CUDA-core kernel (any stride); exported so the tests can
 // cross-check the tensor-core kernel against it on the GPU.
 int v100_dwconv1d_simt(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift,

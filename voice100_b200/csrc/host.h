@@ -52,6 +52,10 @@ int conv1x1_f32out(const void* x, int64_t x_pitch, const void* W, const float* b
                    int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream);
 int convtranspose1d_k5s2(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
                          int64_t y_pitch, int B, int C_in, int C_out, int T, int dtype, cudaStream_t stream);
+int dw_pack_pairs(const void* w, uint32_t* pairs, int C, int k, cudaStream_t stream);
+int expand_dw(const void* x, int64_t x_pitch, const void* W1, const float* scale1, const float* shift1,
+              const uint32_t* dw_pairs, const float* scale2, const float* shift2, void* y, int64_t y_pitch, int B,
+              int C_in, int H, int T, int k, int dtype, cudaStream_t stream);
 int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, const float* shift, void* y,
              int64_t y_pitch, int B, int C, int T_in, int k, int stride, int act, int dtype, int force_simt,
              cudaStream_t stream);
