@@ -51,8 +51,9 @@ def load_peaks():
 # --------------------------------------------------------------------------------------------------
 # algorithmic work per launch (SURVEY.md section 8d / DESIGN.md): bf16 activations = 2 B
 # --------------------------------------------------------------------------------------------------
-def asr_work_model(B, T_in, hidden, embed, vocab, audio_size=64):
-    """-> list of dicts (kind, flops, bytes) in launch order for one step."""
+def asr_work_model(B, T_in, hidden, embed, vocab, audio_size=64, fused=True):
+    """-> list of dicts (kind, flops, bytes) in launch order for one step.  With `fused`, the stride-1 blocks run
+    expand + depthwise as one kernel ("expand_dw": the 4x-wide tensor between them is neither written nor read)."""
     from voice100_b200.synth import asr_encoder_blocks
     L = (T_in - 1) * 160  # samples per clip (frames = 1 + L//160)
     work = [dict(kind="logmel", flops=0.0, bytes=4.0 * B * L + 2.0 * 64 * B * T_in)]
@@ -60,10 +61,14 @@ def asr_work_model(B, T_in, hidden, embed, vocab, audio_size=64):
     for ci, co, k, s, res in asr_encoder_blocks(audio_size, embed, hidden):
         h = 4 * ci
         M = B * T
-        work.append(dict(kind="gemm", flops=2.0 * M * ci * h, bytes=2.0 * M * (ci + h) + 2.0 * ci * h))
         T_out = (T - 1) // s + 1
         Mo = B * T_out
-        work.append(dict(kind="dwconv", flops=2.0 * k * h * Mo, bytes=2.0 * h * (M + Mo) + 2.0 * h * k))
+        if fused and s == 1 and h % 256 == 0:
+            work.append(dict(kind="expand_dw", flops=2.0 * M * ci * h + 2.0 * k * h * Mo,
+                             bytes=2.0 * M * ci + 2.0 * Mo * h + 2.0 * ci * h + 4.0 * 128 * h))
+        else:
+            work.append(dict(kind="gemm", flops=2.0 * M * ci * h, bytes=2.0 * M * (ci + h) + 2.0 * ci * h))
+            work.append(dict(kind="dwconv", flops=2.0 * k * h * Mo, bytes=2.0 * h * (M + Mo) + 2.0 * h * k))
         work.append(dict(kind="gemm", flops=2.0 * Mo * h * co,
                          bytes=2.0 * Mo * (h + co) + (2.0 * Mo * co if res else 0.0) + 2.0 * h * co))
         T = T_out
@@ -590,7 +595,8 @@ def main():
 
     # ---- per-kernel device times (separate pass, CUDA events around every launch: kernels run one at a time, at
     #      burst clocks, so their roofline denominators are the BURST peaks) ----
-    work = asr_work_model(B, T_in, MODEL["hidden_size"], MODEL["embed_size"], args.vocab)
+    from voice100_b200 import blocks as _blocks
+    work = asr_work_model(B, T_in, MODEL["hidden_size"], MODEL["embed_size"], args.vocab, fused=_blocks.FUSE_EXPAND_DW)
     _lib.tracer = _Tracer(torch)
     prof_steps = min(K, 5)
     for i in range(prof_steps):
@@ -613,7 +619,7 @@ def main():
         gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9 if c["ms"] > 0 else 0.0
         entry = dict(ms_per_step=round(c["ms"], 4), launches=c["launches"], share=round(c["ms"] / total_kernel_ms, 4),
                      tflops=round(tf, 1), gbs=round(gbs, 1))
-        if kind == "gemm":
+        if kind in ("gemm", "expand_dw"):
             entry.update(bound="tensor", frac=round(tf / peaks["tf_burst"], 4), frac_burst=round(tf / peaks["tf_burst"], 4),
                          frac_sustained=round(tf / peaks["tf_sustained"], 4), hbm_frac=round(gbs / peaks["hbm_gbs"], 4))
         else:
@@ -632,18 +638,19 @@ def main():
             entry["algorithmic_bytes_per_step"] = classes[kind]["bytes"]
     dom = max(classes, key=lambda k: classes[k]["ms"])
     dc = classes[dom]
-    if dom == "gemm":
+    if dom in ("gemm", "expand_dw"):
         ach = dc["flops"] / dc["launches"] / (dc["ms"] / dc["launches"] * 1e-3) / 1e12
-        roofline = dict(kernel="conv_gemm_kernel (tcgen05)", bound="tensor", achieved=round(ach, 2),
+        roofline = dict(kernel="conv_gemm_kernel (tcgen05)" if dom == "gemm" else "expand_dw_kernel (tcgen05 GEMM + mma.sync depthwise epilogue)",
+                        bound="tensor", achieved=round(ach, 2),
                         peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4),
                         frac_burst=round(ach / peaks["tf_burst"], 4), frac_sustained=round(ach / peaks["tf_sustained"], 4),
                         peak_sustained=peaks["tf_sustained"],
-                        traffic=(tcls["gemm"]["dram_bytes_per_launch"] if "gemm" in tcls else None),
-                        traffic_note="ncu dram__bytes_read+write per launch, mean over the step's GEMM launches (%s); "
+                        traffic=(tcls[dom]["dram_bytes_per_launch"] if dom in tcls else None),
+                        traffic_note="ncu dram__bytes_read+write per launch, mean over the step's launches of this kernel (%s); "
                                      "algorithmic bytes per launch: %.0f" % (traffic.get("source", "n/a"), dc["bytes"] / dc["launches"]),
                         peak_source=peaks["source"] + "; `frac` divides by the BURST bf16 peak because the launches are "
                                     "event-timed one at a time at burst clocks; frac_sustained is against the power-capped peak",
-                        note="mean over the %d GEMM launches of a step (algorithmic FLOPs / CUDA-event time)" % dc["launches"])
+                        note="mean over the %d launches of this kernel in a step (algorithmic FLOPs / CUDA-event time)" % dc["launches"])
     else:
         ach = dc["bytes"] / (dc["ms"] * 1e-3) / 1e9
         roofline = dict(kernel=dom, bound="hbm", achieved=round(ach, 1), peak=peaks["hbm_gbs"], unit="GB/s",

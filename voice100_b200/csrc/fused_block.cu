@@ -37,15 +37,17 @@ constexpr int kABytes = kM * kK * 2;       // 16 KB of weights per stage and CTA
 constexpr int kBAtom = kK * 64 * 2;        // 8 KB: 64 k-rows x 64 time steps
 constexpr int kBBytes = 2 * kBAtom;        // this CTA's 128 of the tile's 256 time columns
 constexpr int kStage = kABytes + kBBytes;  // 32 KB
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kHalo = 88;                  // window columns kept from the previous tile (>= 2p + 2 for k <= 83)
 constexpr int kWinCols = kHalo + kN;       // 344
 constexpr int kWinPitch = kWinCols * 2;    // 688 B = 43 x 16: rows 16 B apart mod 128 -> conflict-free 16-byte stores
 constexpr int kWinBytes = kM * kWinPitch + 128;   // + zeroed slack: the zero-weight tail of the last row's window
-constexpr int kThreads = 384;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;               // four per TMEM lane quadrant: 64 columns to drain, 8 channels to filter each
+constexpr int kThreads = (4 + kEpiWarps) * 32;
 constexpr int kPairTab = 128;              // packed filter pairs per channel
-constexpr int kSmem = 1024 + kStages * kStage + kWinBytes + 256;
+constexpr int kTabBufs = 3;                // per-warp ring of staged pair tables (prefetch distance 2)
+constexpr int kTabBytes = kEpiWarps * kTabBufs * kPairTab * 4;
+constexpr int kSmem = 1024 + kStages * kStage + kWinBytes + kTabBytes + 256;
 static_assert(kSmem <= 232448, "exceeds 227 KB of shared memory");
 
 struct FusedParams {
@@ -85,7 +87,8 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* win = smem + kStages * kStage;                    // [128 channels][344 columns] 16-bit
-  uint64_t* bars = reinterpret_cast<uint64_t*>(win + kWinBytes);
+  uint32_t* tabs = reinterpret_cast<uint32_t*>(win + kWinBytes);   // [16 warps][3][128] staged pair tables
+  uint64_t* bars = reinterpret_cast<uint64_t*>(win + kWinBytes + kTabBytes);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
@@ -189,7 +192,7 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue: drain -> depthwise -> store =====================
     const int qd = warp & 3;              // TMEM lane quadrant = 32 channels
-    const int g = (warp - 4) >> 2;        // which 128 columns this warp drains / which 16 channels it filters
+    const int g = (warp - 4) >> 2;        // which 64 columns this warp drains / which 8 channels it filters
     const int row = qd * 32 + lane;       // channel row this thread drains
     const uint32_t lane_addr = tmem_base + (uint32_t(qd * 32) << 16);
     const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&tmem_empty[0]), 0);
@@ -199,22 +202,44 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const int cb = kHalo - 2 * p.p - 2 * p.e1;            // window column where a tile's data window starts (multiple of 4)
     const int tpair = 16 + 4 * tg - gq;                   // pair-table index of this lane's first fragment word
     uint8_t* my_row = win + row * kWinPitch;
+    uint32_t* my_tabs = tabs + (warp - 4) * kTabBufs * kPairTab;
+    constexpr int kRows = kM / kEpiWarps;                 // 8 channels per warp
+    const int r0 = qd * 32 + g * kRows;                   // this warp's first channel row
 
-    // one channel: Toeplitz fragments from the pair table, n_mma x 128 outputs starting at time tau0
-    auto filter_rows = [&](int ch0, int b, int tau0, int n_mma, bool move_halo) {
+    // Pair tables are staged two channels ahead with cp.async (16 bytes per lane = one 512-byte table per warp-wide
+    // copy) so that their L2 latency is never on the critical path; the sequence number `seq` counts the tables this
+    // warp has requested, table n lives in ring slot n % 3.  One commit group per request, empty when there is none.
+    auto request_table = [&](int ch, int slot) {
+      if (ch >= 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_tabs + slot * kPairTab + lane * 4)),
+                     "l"(p.pairs + static_cast<long long>(ch) * kPairTab + lane * 4) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // filter this warp's 8 channels: n_mma x 128 outputs starting at time tau0.  `next_ch0` = first channel of the CTA
+    // in the pass that follows (this unit's next tile / flush, or the next unit), -1 if there is none.
+    int seq = 0;                                          // tables consumed so far by this warp
+    auto filter_rows = [&](int ch0, int b, int tau0, int n_mma, bool move_halo, int next_ch0) {
 #pragma unroll 1
-      for (int i = 0; i < 16; ++i) {
-        const int r = qd * 32 + g * 16 + i;
+      for (int i = 0; i < kRows; ++i, ++seq) {
+        const int r = r0 + i;
         const int ch = ch0 + r;
         uint8_t* rp = win + r * kWinPitch;
-        const uint32_t* pt = p.pairs + static_cast<long long>(ch) * kPairTab + tpair;
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // table `seq` has landed (seq + 1 may be in flight)
+        __syncwarp();                                           // ... for every lane; and slot (seq + 2) % 3 is no longer read
+        {
+          const int i2 = i + 2;
+          const int nch = i2 < kRows ? ch0 + r0 + i2 : (next_ch0 >= 0 ? next_ch0 + r0 + (i2 - kRows) : -1);
+          request_table(nch, (seq + 2) % kTabBufs);
+        }
+        const uint32_t* pt = my_tabs + (seq % kTabBufs) * kPairTab + tpair;
         uint32_t af[Q][4];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          af[q][0] = __ldg(pt + 16 * q);          // (m = g    , kk = 4tg, 4tg+1)
-          af[q][1] = __ldg(pt + 16 * q - 8);      // (m = g + 8, kk = 4tg, 4tg+1)
-          af[q][2] = __ldg(pt + 16 * q + 2);      // (m = g    , kk = 4tg+2, 4tg+3)
-          af[q][3] = __ldg(pt + 16 * q - 6);      // (m = g + 8, kk = 4tg+2, 4tg+3)
+          af[q][0] = pt[16 * q];          // (m = g    , kk = 4tg, 4tg+1)
+          af[q][1] = pt[16 * q - 8];      // (m = g + 8, kk = 4tg, 4tg+1)
+          af[q][2] = pt[16 * q + 2];      // (m = g    , kk = 4tg+2, 4tg+3)
+          af[q][3] = pt[16 * q - 6];      // (m = g + 8, kk = 4tg+2, 4tg+3)
         }
         const float sc = p.scale2 ? __ldg(p.scale2 + ch) : 1.0f;
         const float sh = __ldg(p.shift2 + ch);
@@ -223,10 +248,10 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         auto finish = [&](float (&acc)[4], int tau) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[j] = fmaf(acc[j], sc, sh);
-          const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
-          const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
-          const float lo0 = even ? acc[0] : r0, hi0 = even ? r0 : acc[2];
-          const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
+          const float x0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
+          const float x1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
+          const float lo0 = even ? acc[0] : x0, hi0 = even ? x0 : acc[2];
+          const float lo1 = even ? acc[1] : x1, hi1 = even ? x1 : acc[3];
           const int t = tau + pos0;
           if (t >= 0 && t < p.T) *reinterpret_cast<uint32_t*>(yrow + t) = pack2_relu6<DT>(lo0, hi0);
           if (t + 16 >= 0 && t + 16 < p.T) *reinterpret_cast<uint32_t*>(yrow + t + 16) = pack2_relu6<DT>(lo1, hi1);
@@ -260,33 +285,41 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
         } else {                                        // end of the unit: leave a zero left halo for the next one
           if (lane < kHalo * 2 / 16) *reinterpret_cast<uint4*>(rp + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncwarp();
       }
+      __syncwarp();
     };
 
     int iter = 0;
+    const bool tail = p.T > p.t_tiles * kN - p.p - p.e1;       // outputs [256 nT - p - e1, T) need a flush pass
+    if (unit0 < p.num_units) {                                 // tables of the first pass's first two channels
+      const int ch0 = ((unit0 % p.m_tiles) * 2 + int(cta_rank)) * kM;
+      request_table(ch0 + r0, 0);
+      request_table(ch0 + r0 + 1, 1);
+    }
     for (int unit = unit0; unit < p.num_units; unit += unit_step) {
       const int m_tile = unit % p.m_tiles, b = unit / p.m_tiles;
       const int ch0 = (m_tile * 2 + int(cta_rank)) * kM;
+      const int unit_next = unit + unit_step;
+      const int ch0_next = unit_next < p.num_units ? ((unit_next % p.m_tiles) * 2 + int(cta_rank)) * kM : -1;
       const float sc1 = p.scale1 ? __ldg(p.scale1 + ch0 + row) : 1.0f;
       const float sh1 = __ldg(p.shift1 + ch0 + row);
       for (int tt = 0; tt < p.t_tiles; ++tt, ++iter) {
         const int accbuf = iter & 1;
         mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
         tc_fence_after();
-        // ---- drain this warp's 128 columns of its quadrant's 32 channels into the window ----
+        // ---- drain this warp's 64 columns of its quadrant's 32 channels into the window ----
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
           uint32_t v[32];
-          tmem_ld32(lane_addr + accbuf * kN + g * 128 + cc * 32, v);
+          tmem_ld32(lane_addr + accbuf * kN + g * 64 + cc * 32, v);
           tmem_ld_wait();
-          if (cc == 3) {   // this warp is done reading the accumulator buffer
+          if (cc == 1) {   // this warp is done reading the accumulator buffer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
           }
-          const int t0 = tt * kN + g * 128 + cc * 32;   // time of v[0]; columns at t >= T are the conv's zero padding
-          uint4* dst = reinterpret_cast<uint4*>(my_row + (kHalo + g * 128 + cc * 32) * 2);
+          const int t0 = tt * kN + g * 64 + cc * 32;    // time of v[0]; columns at t >= T are the conv's zero padding
+          uint4* dst = reinterpret_cast<uint4*>(my_row + (kHalo + g * 64 + cc * 32) * 2);
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) {
             uint32_t w[4];
@@ -301,26 +334,25 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             dst[k16] = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
-        named_bar_sync(1 + qd, 64);      // both column halves of these 32 channels are in the window
-        filter_rows(ch0, b, tt * kN - p.p - p.e1, 2, true);
-        named_bar_sync(1 + qd, 64);      // both warps are done reading: the next drain may overwrite columns [88, 344)
+        named_bar_sync(1 + qd, 128);     // all four column slices of these 32 channels are in the window
+        const bool last_pass = tt == p.t_tiles - 1 && !tail;
+        filter_rows(ch0, b, tt * kN - p.p - p.e1, 2, true, last_pass ? ch0_next : ch0);
+        named_bar_sync(1 + qd, 128);     // all four warps are done reading: the next drain may overwrite columns [88, 344)
       }
       // ---- flush: outputs whose taps reach past the last tile (zero data), and a zero halo for the next unit ----
-      {
-        const bool tail = p.T > p.t_tiles * kN - p.p - p.e1;     // outputs [256 nT - p - e1, T) are still missing
-        for (int i = 0; i < 16; ++i) {
-          uint8_t* rp = win + (qd * 32 + g * 16 + i) * kWinPitch;
-          if (tail) {
-            if (lane < 8) *reinterpret_cast<uint4*>(rp + kHalo * 2 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);   // 64 zero columns >= p
-          } else if (lane < kHalo * 2 / 16) {
-            *reinterpret_cast<uint4*>(rp + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
-          }
+      for (int i = 0; i < kRows; ++i) {
+        uint8_t* rp = win + (r0 + i) * kWinPitch;
+        if (tail) {
+          if (lane < 8) *reinterpret_cast<uint4*>(rp + kHalo * 2 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);   // 64 zero columns >= p
+        } else if (lane < kHalo * 2 / 16) {
+          *reinterpret_cast<uint4*>(rp + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncwarp();
-        if (tail) filter_rows(ch0, b, p.t_tiles * kN - p.p - p.e1, 1, false);
-        named_bar_sync(1 + qd, 64);
       }
+      __syncwarp();
+      if (tail) filter_rows(ch0, b, p.t_tiles * kN - p.p - p.e1, 1, false, ch0_next);
+      named_bar_sync(1 + qd, 128);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -355,13 +387,7 @@ int dw_pack_pairs(const void* w, uint32_t* pairs, int C, int k, cudaStream_t str
 template <int Q>
 static int launch_expand_dw(const CUtensorMap& tw, const CUtensorMap& tx, const FusedParams& p, cudaStream_t stream) {
   auto launch = [&](auto kern) -> int {
-    static thread_local int configured_dev = -1;     // (one static per kernel instantiation: the lambda is generic)
-    int dev = 0;
-    V100_CUDA(cudaGetDevice(&dev));
-    if (configured_dev != dev) {
-      V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      configured_dev = dev;
-    }
+    V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));   // (not a stream operation)
     int pairs = num_sms() / 2;
     if (p.num_units < pairs) pairs = p.num_units;
     V100_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kThreads), kSmem, stream, tw, tx, p));
