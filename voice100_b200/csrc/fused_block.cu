@@ -76,6 +76,31 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
   }
 }
 
+// explicit shared-window accesses: the dynamic shared memory base is re-aligned through integer arithmetic, after which
+// the compiler no longer knows the address space and would emit generic loads (measured: 172 M generic LD per launch,
+// every fragment and data word of the FIR) -- these keep them LDS / STS
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool B>
+struct BoolC { static constexpr bool value = B; };
+
 }  // namespace
 
 template <int Q, int DT>
@@ -200,91 +225,101 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     const bool even = (gq & 1) == 0;
     const int pos0 = 32 * tg + (even ? gq : gq + 7);      // after the pair exchange: outputs (pos0, pos0+1), (pos0+16, +17)
     const int cb = kHalo - 2 * p.p - 2 * p.e1;            // window column where a tile's data window starts (multiple of 4)
-    const int tpair = 16 + 4 * tg - gq;                   // pair-table index of this lane's first fragment word
-    uint8_t* my_row = win + row * kWinPitch;
-    uint32_t* my_tabs = tabs + (warp - 4) * kTabBufs * kPairTab;
     constexpr int kRows = kM / kEpiWarps;                 // 8 channels per warp
     const int r0 = qd * 32 + g * kRows;                   // this warp's first channel row
+    const uint32_t win_s = smem_u32(win);
+    const uint32_t my_row_s = win_s + row * kWinPitch + kHalo * 2;             // where this thread drains to
+    const uint32_t rows_s = win_s + r0 * kWinPitch;                            // first of the 8 rows this warp filters
+    const uint32_t tabs_s = smem_u32(tabs) + (warp - 4) * kTabBufs * kPairTab * 4;
+    const uint32_t frag_off = (16 + 4 * tg - gq) * 4;     // byte offset of this lane's first fragment word in a table
+    const uint32_t data_off = cb * 2 + lane * 8;          // byte offset of this lane's first data word in a row
 
     // Pair tables are staged two channels ahead with cp.async (16 bytes per lane = one 512-byte table per warp-wide
-    // copy) so that their L2 latency is never on the critical path; the sequence number `seq` counts the tables this
-    // warp has requested, table n lives in ring slot n % 3.  One commit group per request, empty when there is none.
+    // copy) so that their L2 latency is never on the critical path.  Table n of this warp lives in ring slot n % 3;
+    // one commit group per request, empty when there is nothing left to request.
     auto request_table = [&](int ch, int slot) {
       if (ch >= 0)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_tabs + slot * kPairTab + lane * 4)),
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tabs_s + slot * (kPairTab * 4) + lane * 16),
                      "l"(p.pairs + static_cast<long long>(ch) * kPairTab + lane * 4) : "memory");
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    // filter this warp's 8 channels: n_mma x 128 outputs starting at time tau0.  `next_ch0` = first channel of the CTA
-    // in the pass that follows (this unit's next tile / flush, or the next unit), -1 if there is none.
-    int seq = 0;                                          // tables consumed so far by this warp
-    auto filter_rows = [&](int ch0, int b, int tau0, int n_mma, bool move_halo, int next_ch0) {
+    // Filter this warp's 8 channels: N_MMA x 128 outputs per channel starting at time tau0.  `next_first` = the first
+    // channel this warp filters in the pass that follows (the unit's next tile / flush, or the next unit), -1 if none.
+    // INTERIOR: every output of the pass lies in [0, T) -- no store predicates.
+    int slot = 0;                                         // ring slot of the table the next channel uses
+    auto filter_rows = [&](auto two_tiles, auto interior, int first_ch, int b, int tau0, bool move_halo, int next_first) {
+      constexpr bool kTwo = decltype(two_tiles)::value, kInterior = decltype(interior)::value;
+      uint32_t rp = rows_s;
+      unsigned short* yrow = p.y + (static_cast<long long>(b) * p.H + first_ch) * p.y_pitch + tau0 + pos0;
+      const int t_lane = tau0 + pos0;
 #pragma unroll 1
-      for (int i = 0; i < kRows; ++i, ++seq) {
-        const int r = r0 + i;
-        const int ch = ch0 + r;
-        uint8_t* rp = win + r * kWinPitch;
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // table `seq` has landed (seq + 1 may be in flight)
-        __syncwarp();                                           // ... for every lane; and slot (seq + 2) % 3 is no longer read
+      for (int i = 0; i < kRows; ++i) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this channel's table has landed (the next may be in flight)
+        __syncwarp();                                           // ... for every lane; and the slot two ahead is no longer read
         {
           const int i2 = i + 2;
-          const int nch = i2 < kRows ? ch0 + r0 + i2 : (next_ch0 >= 0 ? next_ch0 + r0 + (i2 - kRows) : -1);
-          request_table(nch, (seq + 2) % kTabBufs);
+          const int nch = i2 < kRows ? first_ch + i2 : (next_first >= 0 ? next_first + (i2 - kRows) : -1);
+          request_table(nch, slot >= 1 ? slot - 1 : kTabBufs - 1);      // (slot + 2) % 3
         }
-        const uint32_t* pt = my_tabs + (seq % kTabBufs) * kPairTab + tpair;
+        const uint32_t pt = tabs_s + slot * (kPairTab * 4) + frag_off;
+        slot = slot == kTabBufs - 1 ? 0 : slot + 1;
         uint32_t af[Q][4];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-          af[q][0] = pt[16 * q];          // (m = g    , kk = 4tg, 4tg+1)
-          af[q][1] = pt[16 * q - 8];      // (m = g + 8, kk = 4tg, 4tg+1)
-          af[q][2] = pt[16 * q + 2];      // (m = g    , kk = 4tg+2, 4tg+3)
-          af[q][3] = pt[16 * q - 6];      // (m = g + 8, kk = 4tg+2, 4tg+3)
+          af[q][0] = lds32(pt + 64 * q);          // (m = g    , kk = 4tg, 4tg+1)
+          af[q][1] = lds32(pt + 64 * q - 32);     // (m = g + 8, kk = 4tg, 4tg+1)
+          af[q][2] = lds32(pt + 64 * q + 8);      // (m = g    , kk = 4tg+2, 4tg+3)
+          af[q][3] = lds32(pt + 64 * q - 24);     // (m = g + 8, kk = 4tg+2, 4tg+3)
         }
+        const int ch = first_ch + i;
         const float sc = p.scale2 ? __ldg(p.scale2 + ch) : 1.0f;
         const float sh = __ldg(p.shift2 + ch);
-        const uint2* xw = reinterpret_cast<const uint2*>(rp + cb * 2) + lane;
-        unsigned short* yrow = p.y + (static_cast<long long>(b) * p.H + ch) * p.y_pitch;
-        auto finish = [&](float (&acc)[4], int tau) {
+        const uint32_t xw = rp + data_off;
+        auto finish = [&](float (&acc)[4], int dt) {       // dt = 0 / 128: which of the pass's tiles
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[j] = fmaf(acc[j], sc, sh);
           const float x0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
           const float x1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
-          const float lo0 = even ? acc[0] : x0, hi0 = even ? x0 : acc[2];
-          const float lo1 = even ? acc[1] : x1, hi1 = even ? x1 : acc[3];
-          const int t = tau + pos0;
-          if (t >= 0 && t < p.T) *reinterpret_cast<uint32_t*>(yrow + t) = pack2_relu6<DT>(lo0, hi0);
-          if (t + 16 >= 0 && t + 16 < p.T) *reinterpret_cast<uint32_t*>(yrow + t + 16) = pack2_relu6<DT>(lo1, hi1);
+          const uint32_t o0 = even ? pack2_relu6<DT>(acc[0], x0) : pack2_relu6<DT>(x0, acc[2]);
+          const uint32_t o1 = even ? pack2_relu6<DT>(acc[1], x1) : pack2_relu6<DT>(x1, acc[3]);
+          if constexpr (kInterior) {
+            *reinterpret_cast<uint32_t*>(yrow + dt) = o0;
+            *reinterpret_cast<uint32_t*>(yrow + dt + 16) = o1;
+          } else {
+            const int t = t_lane + dt;
+            if (t >= 0 && t < p.T) *reinterpret_cast<uint32_t*>(yrow + dt) = o0;
+            if (t + 16 >= 0 && t + 16 < p.T) *reinterpret_cast<uint32_t*>(yrow + dt + 16) = o1;
+          }
         };
-        if (n_mma == 2) {
+        if constexpr (kTwo) {
           float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            const uint2 b0 = xw[4 * q];
-            const uint2 b1 = xw[32 + 4 * q];
+            const uint2 b0 = lds64(xw + 32 * q);
+            const uint2 b1 = lds64(xw + 256 + 32 * q);
             mma_16816<DT>(acc0, af[q], b0.x, b0.y);
             mma_16816<DT>(acc1, af[q], b1.x, b1.y);
           }
-          finish(acc0, tau0);
-          finish(acc1, tau0 + 128);
+          finish(acc0, 0);
+          finish(acc1, 128);
         } else {
           float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            const uint2 bq = xw[4 * q];
+            const uint2 bq = lds64(xw + 32 * q);
             mma_16816<DT>(acc, af[q], bq.x, bq.y);
           }
-          finish(acc, tau0);
+          finish(acc, 0);
         }
         __syncwarp();                                   // every lane is past its reads of this row
-        if (move_halo) {                                // columns [256, 344) become the next tile's [0, 88)
-          if (lane < kHalo * 2 / 16) {
-            const uint4 h = *reinterpret_cast<const uint4*>(rp + kN * 2 + lane * 16);
-            *reinterpret_cast<uint4*>(rp + lane * 16) = h;
-          }
-        } else {                                        // end of the unit: leave a zero left halo for the next one
-          if (lane < kHalo * 2 / 16) *reinterpret_cast<uint4*>(rp + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < kHalo * 2 / 16) {
+          // columns [256, 344) become the next tile's [0, 88); at the end of a unit the next one gets a zero halo
+          const uint4 h = move_halo ? lds128(rp + kN * 2 + lane * 16) : make_uint4(0u, 0u, 0u, 0u);
+          sts128(rp + lane * 16, h);
         }
+        rp += kWinPitch;
+        yrow += p.y_pitch;
       }
       __syncwarp();
     };
@@ -292,15 +327,16 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
     int iter = 0;
     const bool tail = p.T > p.t_tiles * kN - p.p - p.e1;       // outputs [256 nT - p - e1, T) need a flush pass
     if (unit0 < p.num_units) {                                 // tables of the first pass's first two channels
-      const int ch0 = ((unit0 % p.m_tiles) * 2 + int(cta_rank)) * kM;
-      request_table(ch0 + r0, 0);
-      request_table(ch0 + r0 + 1, 1);
+      const int first = ((unit0 % p.m_tiles) * 2 + int(cta_rank)) * kM + r0;
+      request_table(first, 0);
+      request_table(first + 1, 1);
     }
     for (int unit = unit0; unit < p.num_units; unit += unit_step) {
       const int m_tile = unit % p.m_tiles, b = unit / p.m_tiles;
       const int ch0 = (m_tile * 2 + int(cta_rank)) * kM;
+      const int first = ch0 + r0;
       const int unit_next = unit + unit_step;
-      const int ch0_next = unit_next < p.num_units ? ((unit_next % p.m_tiles) * 2 + int(cta_rank)) * kM : -1;
+      const int first_next = unit_next < p.num_units ? ((unit_next % p.m_tiles) * 2 + int(cta_rank)) * kM + r0 : -1;
       const float sc1 = p.scale1 ? __ldg(p.scale1 + ch0 + row) : 1.0f;
       const float sh1 = __ldg(p.shift1 + ch0 + row);
       for (int tt = 0; tt < p.t_tiles; ++tt, ++iter) {
@@ -319,38 +355,36 @@ expand_dw_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
             if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
           }
           const int t0 = tt * kN + g * 64 + cc * 32;    // time of v[0]; columns at t >= T are the conv's zero padding
-          uint4* dst = reinterpret_cast<uint4*>(my_row + (kHalo + g * 64 + cc * 32) * 2);
+          const uint32_t dst = my_row_s + (g * 64 + cc * 32) * 2;
+          uint32_t w[16];
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            uint32_t w[4];
+          for (int e = 0; e < 16; ++e)
+            w[e] = pack2_relu6<DT>(fmaf(__uint_as_float(v[2 * e]), sc1, sh1), fmaf(__uint_as_float(v[2 * e + 1]), sc1, sh1));
+          if (t0 + 32 > p.T) {                          // (warp-uniform) the tile straddles the end of the clip
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = k16 * 8 + 2 * e;
-              const float lo = fmaf(__uint_as_float(v[j]), sc1, sh1), hi = fmaf(__uint_as_float(v[j + 1]), sc1, sh1);
-              uint32_t pk = pack2_relu6<DT>(lo, hi);
-              if (t0 + j + 1 >= p.T) pk = (t0 + j >= p.T) ? 0u : (pk & 0xFFFFu);
-              w[e] = pk;
-            }
-            dst[k16] = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int e = 0; e < 16; ++e)
+              if (t0 + 2 * e + 1 >= p.T) w[e] = (t0 + 2 * e >= p.T) ? 0u : (w[e] & 0xFFFFu);
           }
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) sts128(dst + 16 * k16, make_uint4(w[4 * k16], w[4 * k16 + 1], w[4 * k16 + 2], w[4 * k16 + 3]));
         }
         named_bar_sync(1 + qd, 128);     // all four column slices of these 32 channels are in the window
         const bool last_pass = tt == p.t_tiles - 1 && !tail;
-        filter_rows(ch0, b, tt * kN - p.p - p.e1, 2, true, last_pass ? ch0_next : ch0);
+        const int tau0 = tt * kN - p.p - p.e1;
+        const int nxt = last_pass ? first_next : first;
+        if (tau0 >= 0 && tau0 + kN <= p.T) filter_rows(BoolC<true>{}, BoolC<true>{}, first, b, tau0, !last_pass, nxt);
+        else filter_rows(BoolC<true>{}, BoolC<false>{}, first, b, tau0, !last_pass, nxt);
         named_bar_sync(1 + qd, 128);     // all four warps are done reading: the next drain may overwrite columns [88, 344)
       }
-      // ---- flush: outputs whose taps reach past the last tile (zero data), and a zero halo for the next unit ----
-      for (int i = 0; i < kRows; ++i) {
-        uint8_t* rp = win + (r0 + i) * kWinPitch;
-        if (tail) {
-          if (lane < 8) *reinterpret_cast<uint4*>(rp + kHalo * 2 + lane * 16) = make_uint4(0u, 0u, 0u, 0u);   // 64 zero columns >= p
-        } else if (lane < kHalo * 2 / 16) {
-          *reinterpret_cast<uint4*>(rp + lane * 16) = make_uint4(0u, 0u, 0u, 0u);
-        }
+      // ---- flush: the outputs whose taps reach past the last tile see zero data there ----
+      if (tail) {
+        uint32_t rp = rows_s + kHalo * 2;
+        for (int i = 0; i < kRows; ++i, rp += kWinPitch)
+          if (lane < 8) sts128(rp + lane * 16, make_uint4(0u, 0u, 0u, 0u));     // 64 zero columns >= p
+        __syncwarp();
+        filter_rows(BoolC<false>{}, BoolC<false>{}, first, b, p.t_tiles * kN - p.p - p.e1, false, first_next);
+        named_bar_sync(1 + qd, 128);
       }
-      __syncwarp();
-      if (tail) filter_rows(ch0, b, p.t_tiles * kN - p.p - p.e1, 1, false, ch0_next);
-      named_bar_sync(1 + qd, 128);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
