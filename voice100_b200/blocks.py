@@ -61,8 +61,11 @@ class InvertedResidualParams(nn.Module):
             k=self.kernel_size, stride=self.stride, res=self.use_residual)
 
 
-# V100_FUSE=0 in the environment runs every block as three kernels (A/B measurements, cross-checks in the tests)
-FUSE_EXPAND_DW = os.environ.get("V100_FUSE", "1") != "0"
+# V100_FUSE=1 in the environment runs expand + depthwise of the stride-1 blocks as ONE kernel (v100_expand_dw).  It is
+# correct (tests/test_kernels_gpu.py) but OFF by default: measured on the B200 it is slower than the two kernels it
+# replaces (DESIGN.md section 7 -- the depthwise FIR is bound by shared-memory wavefronts, not by HBM, so keeping the
+# 4x-wide tensor on chip buys nothing while the per-tile reload of the Toeplitz fragments costs a second FIR's worth).
+FUSE_EXPAND_DW = os.environ.get("V100_FUSE", "0") == "1"
 
 
 def run_inverted_residual(x: K.Ncw, w: dict, fuse: Optional[bool] = None) -> K.Ncw:

@@ -5,9 +5,9 @@
 //    ConvVoiceEncoder costs 72 MFLOP per audio-second -- on fp32 CUDA cores that is ~2.5x MORE time
 //    than its HBM traffic, so the FIR is evaluated on the tensor cores instead, as Toeplitz blocks of the
 //    filter times 16-sample columns of the time series (mma.sync.m16n8k16, bf16 x bf16 -> fp32,
-//    Q = ceil((k+15+e1)/16) <= 7 per 128 outputs; geometry in the comment above the kernel).  The Toeplitz
-//    blocks live in registers while a warp walks 8 batch rows of its channel; rows are double-buffered in
-//    shared memory with cp.async.  8 channels per CTA.
+//    2 Q MMAs fed by Q + 1 shared-memory fragment loads per 256 outputs, Q = ceil((k+15+e1)/16) <= 7;
+//    geometry in the comment above the kernel).  The Toeplitz blocks live in registers while a warp walks 8
+//    batch rows of its channel; rows are double-buffered in shared memory with cp.async.  8 channels per CTA.
 //  * dw_s2_kernel: stride 2 (the first encoder block, 0.4 % of the depthwise FLOPs, HBM-bound): CUDA cores
 //    over a shared-memory staged row.
 //  * dw_simt_kernel: any stride / any k, plain CUDA cores; last resort and exported for cross-checking.
@@ -16,8 +16,9 @@
 
 namespace v100 {
 
-constexpr int kDwChunk = 1024;            // outputs per CTA along time (8 mma tiles)
-constexpr int kDwRow = kDwChunk + 256;    // staged inputs per row: 9 tiles of 128 + (Q+1)*16 halo
+constexpr int kDwChunk = 1024;            // outputs per CTA along time (4 double-tiles of 256)
+constexpr int kDwRow = kDwChunk + 384;    // staged inputs per row: up to 5 double-tiles of 16 blocks + Q blocks of halo
+constexpr int kDwHalf = kDwRow / 2;       // the staged row is kept as two arrays: even and odd 16-sample blocks
 constexpr int kDwWarps = 8;
 
 template <int DT>
@@ -48,14 +49,19 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one set of Toeplitz fragments
 
-// Stage x[b][c][tcA .. tcA + kDwRow) into `xs` with zeros outside [0, T).  16-byte chunks never straddle 0
-// (tcA % 8 == 0); a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
+// Staged-row layout: sample i of the staged row (i = 0 at x[tcA]) lives in 16-sample block i >> 4; even blocks are
+// packed into xs[0 .. kDwHalf), odd blocks into xs[kDwHalf .. kDwRow).  Eight blocks of ONE parity are then 256
+// contiguous bytes -- what one mma's data operand reads (see the kernel comment).
+__device__ __forceinline__ int dw_map(int i) { return ((i >> 4) & 1) * kDwHalf + ((i >> 5) << 4) + (i & 15); }
+
+// Stage x[b][c][tcA .. tcA + 8 n_chunks) with zeros outside [0, T).  16-byte chunks never straddle 0 (tcA % 8 == 0);
+// a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
 __device__ __forceinline__ void dw_stage_row(unsigned short* xs, const unsigned short* xrow, int tcA, int T, int lane,
                                              int n_chunks) {
   for (int v = lane; v < n_chunks; v += 32) {
     const int t = tcA + v * 8;
     const bool ok = t >= 0 && t < T;
-    cp_async_16(xs + v * 8, xrow + (ok ? t : 0), ok);
+    cp_async_16(xs + dw_map(v * 8), xrow + (ok ? t : 0), ok);
   }
   cp_async_commit();
 }
@@ -63,19 +69,23 @@ __device__ __forceinline__ void dw_fix_tail(unsigned short* xs, int tcA, int T, 
   const int i0 = T - tcA;               // first staged index that is past the end of the clip
   if ((T & 7) != 0 && i0 > 0 && i0 < kDwRow) {
     const int i = i0 + lane;
-    if (lane < 8 - (T & 7)) xs[i] = 0;
+    if (lane < 8 - (T & 7)) xs[dw_map(i)] = 0;
   }
 }
 
-// Toeplitz-on-tensor-cores depthwise FIR.  Per tile of 128 outputs of one (batch, channel) row:
-//   D[m][n] = out[tau + m + 16 n] = sum_q sum_kk  W_q[m][kk] * X_q[kk][n],        m < 16, n < 8, kk < 16
-//   X_q[kk][n] = xs[128 tile + 16 (n + q) + kk]      (the DATA is the small "B" operand: 256 contiguous bytes)
-//   W_q[m][kk] = wz[16 q + kk - m],  wz[i] = w[i - e1]   (Toeplitz blocks of the filter = "A", in registers)
-// The mma's kk axis is permuted (physical rows {2j, 2j+1, 2j+8, 2j+9} carry logical kk = 4j .. 4j+3), so a
-// thread's (b0, b1) pair is ONE aligned 64-bit shared load at uint2 index 32 tile + 4 q + lane: consecutive
-// lanes read consecutive 8-byte words (conflict-free, 2 wavefronts per mma -- the ldmatrix form of this kernel
-// needed 4 and was shared-memory bound at 88 % of L1 throughput).  The D fragment holds outputs 16 apart;
-// one xor-shuffle pair regroups them into bf16x2 pairs that are stored as full 32-byte sectors.
+// Toeplitz-on-tensor-cores depthwise FIR.  A "double tile" is 256 consecutive outputs of one (batch, channel) row, seen
+// as sixteen 16-sample blocks; accumulator A takes the even blocks, accumulator B the odd ones:
+//   A[m][n] = out[tau + m + 32 n],   B[m][n] = out[tau + 16 + m + 32 n],          m < 16, n < 8
+//   A = sum_c W_c     * X_c,   c = 0 .. Q-1
+//   B = sum_c W_(c-1) * X_c,   c = 1 .. Q          X_c[kk][n] = xs[16 (2 n + c) + kk]   (data block 2 n + c)
+//   W_q[m][kk] = wz[16 q + kk - m],  wz[i] = w[i - e1]   (Toeplitz blocks of the filter = the "A" operand, in registers)
+// Because the two accumulators are one block apart, data fragment X_c serves BOTH of them: Q + 1 shared-memory
+// fragment loads feed 2 Q MMAs (the round-1 kernel gave each of its two tiles private fragments: 2 Q loads, and ncu
+// showed it bound by exactly these wavefronts -- L1/shared 89 % busy at 50 % of DRAM bandwidth).  X_c is eight blocks
+// of one parity, which the staged layout keeps contiguous: with the mma's kk axis permuted (physical rows
+// {2j, 2j+1, 2j+8, 2j+9} carry logical kk = 4j .. 4j+3) a thread's (b0, b1) pair is ONE aligned 64-bit load at uint2
+// index 4 (c >> 1) + lane of the parity-(c & 1) array: consecutive lanes read consecutive 8-byte words, 2 wavefronts.
+// One xor-shuffle pair regroups an accumulator into bf16x2 pairs that are stored as full 32-byte sectors.
 // Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory); tiles start
 // s = e - (e & 1) outputs before tc0 (e = pl8 - p), leaving e1 = e & 1 to fold into the zero-extended filter;
 // Q = ceil((k + 15 + e1) / 16) <= 7 for k <= 83.
@@ -103,8 +113,8 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
   const long long xbstride = static_cast<long long>(C) * x_pitch;
 
   const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
-  const int n_tiles = (len + s + 127) / 128;
-  const int n_chunks = min(kDwRow / 8, 16 * n_tiles + 2 * Q);   // 16-byte chunks the tiles actually read
+  const int n_dt = (len + s + 255) / 256;            // double tiles
+  const int n_chunks = min(kDwRow / 8, 2 * (16 * n_dt + Q));   // 16-byte chunks the tiles actually read
   pdl_trigger();
   pdl_wait();        // (x is the previous kernel's output)
   dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane, n_chunks);   // first row in flight
@@ -131,8 +141,8 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
   const float sc = scale ? scale[c] : 1.0f;
   const float sh = shift[c];
   const bool even = (g & 1) == 0;
-  // after the pair exchange this lane stores outputs (t, t+1) and (t+16, t+17), t relative to tc0:
-  const int pos0 = 32 * tg + (even ? g : g + 7) - s;
+  // after the pair exchange this lane stores outputs (t, t+1) and (t+32, t+33) of an accumulator, t relative to tc0:
+  const int pos0 = 64 * tg + (even ? g : g + 7) - s;
 
   for (int r = 0; r < nb; ++r) {
     unsigned short* xs = xs_all[warp][r & 1];
@@ -145,13 +155,14 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
     __syncwarp();
     dw_fix_tail(xs, tcA, T, lane);
     __syncwarp();
-    const uint2* xw = reinterpret_cast<const uint2*>(xs) + lane;
+    const uint2* xe = reinterpret_cast<const uint2*>(xs) + lane;             // even blocks
+    const uint2* xo = reinterpret_cast<const uint2*>(xs + kDwHalf) + lane;   // odd blocks
     unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
     int pos = pos0;
-    auto finish_tile = [&](float (&acc)[4], unsigned short* yq, int posq) {
+    auto finish = [&](float (&acc)[4], unsigned short* yq, int posq) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
-      // acc = out[tau + g + 32tg + {0, 16}], out[tau + g + 8 + 32tg + {0, 16}]; trade with lane g^1 so that even
+      // acc = out[tau + g + 64 tg + {0, 32}], out[tau + g + 8 + 64 tg + {0, 32}]; trade with lane g^1 so that even
       // g holds (g, g+1) of the first pair of rows and odd g holds (g-1+8, g+8) of the second
       const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
       const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
@@ -166,33 +177,23 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
         o1 = pack2<DT>(lo1, hi1);
       }
       if (posq >= 0 && posq < len) *reinterpret_cast<uint32_t*>(yq) = o0;
-      if (posq + 16 >= 0 && posq + 16 < len) *reinterpret_cast<uint32_t*>(yq + 16) = o1;
+      if (posq + 32 >= 0 && posq + 32 < len) *reinterpret_cast<uint32_t*>(yq + 32) = o1;
     };
-    int tile = 0;
 #pragma unroll 1
-    for (; tile + 2 <= n_tiles; tile += 2) {   // two tiles per trip: two independent mma chains interleave
-      float acc0[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc1[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int d = 0; d < n_dt; ++d) {
+      float accA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint2 b0q = xw[4 * q];
-        const uint2 b1q = xw[32 + 4 * q];
-        mma_16816<DT>(acc0, af[q][0], af[q][1], af[q][2], af[q][3], b0q.x, b0q.y);
-        mma_16816<DT>(acc1, af[q][0], af[q][1], af[q][2], af[q][3], b1q.x, b1q.y);
+      for (int cq = 0; cq <= Q; ++cq) {
+        const uint2 f = (cq & 1) ? xo[4 * (cq >> 1)] : xe[4 * (cq >> 1)];
+        if (cq < Q) mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], f.x, f.y);
+        if (cq > 0) mma_16816<DT>(accB, af[cq - 1][0], af[cq - 1][1], af[cq - 1][2], af[cq - 1][3], f.x, f.y);
       }
-      finish_tile(acc0, yp, pos);
-      finish_tile(acc1, yp + 128, pos + 128);
-      xw += 64;
+      finish(accA, yp, pos);
+      finish(accB, yp + 16, pos + 16);
+      xe += 32;      // eight blocks of each parity per double tile
+      xo += 32;
       yp += 256;
       pos += 256;
-    }
-    if (tile < n_tiles) {
-      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const uint2 bq = xw[4 * q];
-        mma_16816<DT>(acc, af[q][0], af[q][1], af[q][2], af[q][3], bq.x, bq.y);
-      }
-      finish_tile(acc, yp, pos);
     }
     __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
