@@ -163,10 +163,16 @@ def test_bench_work_model_matches_survey():
     import sys
     sys.path.insert(0, ROOT)
     import bench
-    work = bench.asr_work_model(1, 101, 512, 512, 29)   # ~ one audio-second (100 in-frames -> ~50 out)
+    work = bench.asr_work_model(1, 101, 512, 512, 29, fused=False)   # ~ one audio-second (100 in-frames -> ~50 out)
     gemm = sum(w["flops"] for w in work if w["kind"] == "gemm") / 1e6
     dw = sum(w["flops"] for w in work if w["kind"] == "dwconv") / 1e6
     assert abs(gemm - 1084.6 - 1.48) / 1086 < 0.03 and abs(dw - 72.0) / 72.0 < 0.03, (gemm, dw)
+    assert len(work) == 30                                            # log-mel + 9 x 3 + head + CTC tail
+    # the fused form (opt-in) charges the same FLOPs, minus the hidden tensor's round trip through HBM
+    fused = bench.asr_work_model(1, 101, 512, 512, 29, fused=True)
+    assert len(fused) == 22 and abs(sum(w["flops"] for w in fused) - sum(w["flops"] for w in work)) < 1.0
+    big = [sum(w["bytes"] for w in bench.asr_work_model(256, 1501, 512, 512, 29, fused=f)) for f in (False, True)]
+    assert 22e9 < big[0] < 25e9 and big[1] < 0.65 * big[0]           # ~23.5 GB per 256 x 15 s step, ~14 GB fused
 
 
 def test_load_checkpoint_roundtrip(tmp_path):
