@@ -21,6 +21,8 @@ def short(name):
 
 
 def kind_of(name):
+    if "expand_dw" in name:
+        return "expand_dw"
     if "conv_gemm" in name:
         return "gemm"
     if "dw_" in name:
@@ -60,7 +62,7 @@ def step(src, dst):
     open(dst, "w").write("\n".join(out) + "\n")
     traffic = {k: dict(dram_bytes_per_step=v["bytes"], launches=v["launches"], dram_bytes_per_launch=v["bytes"] / v["launches"],
                        share_of_step=v["us"] / tot) for k, v in agg.items()}
-    tj = os.path.join(os.path.dirname(dst), os.path.basename(dst).split("_")[0] + "_traffic.json")
+    tj = os.path.join(os.path.dirname(dst), os.path.basename(dst).split("_")[0] + "_traffic.json")   # r02_traffic.json
     json.dump({"source": os.path.basename(dst), "per_kernel_class": traffic}, open(tj, "w"), indent=1)
     print(out[-1])
 

@@ -34,6 +34,9 @@ if MODE == "nogemm":
     wav = 0.1 * torch.randn(3, 16000 * 2 + 123, device=dev)
     ln = torch.tensor([32123, 9000, 20001], dtype=torch.int32, device=dev)
     tr.logmel_batch(wav, ln); tr.logmel_batch(wav, ln, ncw_dtype=torch.float16); tr.melspec(wav[0])
+    pcm = (wav * 32767).to(torch.int16)
+    tr.logmel_batch(pcm, ln, ncw_dtype=torch.bfloat16); tr.logmel_batch(pcm[:, :32001].contiguous(), ln.clamp(max=32001))
+    tr.logmel_batch(wav, torch.tensor([0, 1, 10 ** 6], dtype=torch.int32, device=dev))      # empty / too short / over-long
     for dtype in (torch.bfloat16, torch.float16):
         x = K.empty_ncw(2, 72, 333, dev, dtype); x.data.normal_()
         for k in (5, 11, 35, 83):
@@ -49,8 +52,11 @@ if MODE == "nogemm":
     K.ctc_collapse(tok, torch.tensor([51, 20], device=dev))
     K.ncw_f32_to_ntc(lg)
     K.world_finalize(K.Ncw(torch.randn(2, 260, 56, device=dev), 53), torch.zeros(259, device=dev), torch.ones(259, device=dev), True)
+    K.world_finalize(K.Ncw(torch.randn(2, 33, 56, device=dev), 53), torch.zeros(29, device=dev), torch.ones(29, device=dev), True, 25, 3, 2)
+    _, _, ol = K.ctc_finalize(lg, False, torch.tensor([51, 20], dtype=torch.int32, device=dev))
     lp = torch.log_softmax(torch.randn(3, 50, 29, device=dev), -1)
     v.ctc_best_path_batch(lp, torch.tensor([50, 30, 4]), torch.randint(1, 29, (3, 9), device=dev), torch.tensor([9, 5, 9]))
+    v.ctc_best_path_batch(lp * 3, torch.tensor([50, 9, 4]), torch.randint(1, 29, (3, 9), device=dev), torch.tensor([9, 9, 0]), normalize=True)
     torch.cuda.synchronize()
     print("sanitize_small (nogemm) done")
     sys.exit(0)
@@ -81,6 +87,13 @@ for dtype in (torch.bfloat16, torch.float16):
     for simt in (False, True):
         K.dwconv(x, w, None, torch.zeros(72, device=dev), 83, 1, 1, simt=simt)
     K.dwconv(x, w[:, :11].contiguous(), None, torch.zeros(72, device=dev), 11, 2, 1)
+    # the fused expand + depthwise kernel (opt-in path): ragged T, K not a multiple of 64, more units than CTA pairs
+    for (Bf, Ci, Hf, Tf, kf) in ((2, 72, 512, 333, 67), (3, 64, 256, 257, 11), (90, 64, 256, 70, 33)):
+        xf = K.empty_ncw(Bf, Ci, Tf, dev, dtype); xf.data.normal_()
+        W1 = torch.randn(Hf, Ci, device=dev).to(dtype)
+        wd = torch.randn(Hf, kf, device=dev).to(dtype)
+        z, o = torch.zeros(Hf, device=dev), torch.ones(Hf, device=dev)
+        K.expand_dw(xf, W1, o, z, K.dw_pack_pairs(wd), o, z, kf)
 lp = torch.log_softmax(torch.randn(3, 50, 29, device=dev), -1)
 v.ctc_best_path_batch(lp, torch.tensor([50, 30, 4]), torch.randint(1, 29, (3, 9), device=dev), torch.tensor([9, 5, 9]))
 torch.cuda.synchronize()

@@ -17,8 +17,13 @@
 namespace v100 {
 
 constexpr int kDwChunk = 1024;            // outputs per CTA along time (4 double-tiles of 256)
-constexpr int kDwRow = kDwChunk + 384;    // staged inputs per row: up to 5 double-tiles of 16 blocks + Q blocks of halo
-constexpr int kDwHalf = kDwRow / 2;       // the staged row is kept as two arrays: even and odd 16-sample blocks
+// The staged row is kept as two arrays, even and odd 16-sample blocks: up to 5 double tiles of 16 blocks + Q blocks of
+// halo = 87 blocks (44 even, 43 odd).  The odd array starts 736 samples = 1472 B = 64 (mod 128) bytes in, so that the
+// 16-byte cp.async chunks of one quarter-warp (two even-block halves, two odd-block halves, ...) fall into distinct
+// banks: with the arrays a multiple of 128 bytes apart ncu showed the staging copies costing 2.3x the wavefronts of the
+// FIR's own data reads.
+constexpr int kDwHalf = 736;
+constexpr int kDwRow = kDwHalf + 43 * 16; // 1424 samples staged per row
 constexpr int kDwWarps = 8;
 
 template <int DT>
@@ -50,7 +55,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one set of Toeplitz fragments
 
 // Staged-row layout: sample i of the staged row (i = 0 at x[tcA]) lives in 16-sample block i >> 4; even blocks are
-// packed into xs[0 .. kDwHalf), odd blocks into xs[kDwHalf .. kDwRow).  Eight blocks of ONE parity are then 256
+// packed into xs[0 .. 704), odd blocks into xs[kDwHalf .. kDwRow).  Eight blocks of ONE parity are then 256
 // contiguous bytes -- what one mma's data operand reads (see the kernel comment).
 __device__ __forceinline__ int dw_map(int i) { return ((i >> 4) & 1) * kDwHalf + ((i >> 5) << 4) + (i & 15); }
 
@@ -67,7 +72,7 @@ __device__ __forceinline__ void dw_stage_row(unsigned short* xs, const unsigned 
 }
 __device__ __forceinline__ void dw_fix_tail(unsigned short* xs, int tcA, int T, int lane) {
   const int i0 = T - tcA;               // first staged index that is past the end of the clip
-  if ((T & 7) != 0 && i0 > 0 && i0 < kDwRow) {
+  if ((T & 7) != 0 && i0 > 0 && i0 < 87 * 16) {
     const int i = i0 + lane;
     if (lane < 8 - (T & 7)) xs[dw_map(i)] = 0;
   }
@@ -114,7 +119,7 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
 
   const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
   const int n_dt = (len + s + 255) / 256;            // double tiles
-  const int n_chunks = min(kDwRow / 8, 2 * (16 * n_dt + Q));   // 16-byte chunks the tiles actually read
+  const int n_chunks = min(2 * 87, 2 * (16 * n_dt + Q));       // 16-byte chunks the tiles actually read
   pdl_trigger();
   pdl_wait();        // (x is the previous kernel's output)
   dw_stage_row(xs_all[warp][0], xbase + b0 * xbstride, tcA, T, lane, n_chunks);   // first row in flight
