@@ -18,6 +18,6 @@ timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_small.py > $
 SAN_MODE=nogemm timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_small.py > $O/r2e_san_racecheck.log 2>&1; tail -2 $O/r2e_san_racecheck.log
 SAN_MODE=nogemm timeout 600 compute-sanitizer --tool synccheck python tools/sanitize_small.py > $O/r2e_san_synccheck.log 2>&1; tail -2 $O/r2e_san_synccheck.log
 SAN_MODE=nogemm timeout 600 compute-sanitizer --tool initcheck python tools/sanitize_small.py > $O/r2e_san_initcheck.log 2>&1; tail -2 $O/r2e_san_initcheck.log
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv --log-file $O/r2e_step_metrics.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager --sustain-seconds 0 > $O/r2e_ncu_bench.log 2>&1; echo "ncu step rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"logmel|conv_gemm|dw_|ctc_finalize|expand_dw" -c 150 --csv --log-file $O/r2e_step_metrics.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-eager --sustain-seconds 0 > $O/r2e_ncu_bench.log 2>&1; echo "ncu step rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"dw_mma|dw_s2|conv_gemm|logmel" -f -o $O/r2e_prof_full python tools/profile_kernels.py > $O/r2e_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la $O | grep r2e
