@@ -283,6 +283,29 @@ def gen_tokenizer(seed=81):
     print("tokenizer", {k: len(v["cases"]) for k, v in out.items()})
 
 
+def gen_align_edges(seed=91):
+    """TextToAlignTextModel.align (voice100/models/tts.py:89-110) on alignments with negative gaps / durations: frame
+    indices that wrap around from the end of the tensor, non-monotone starts, and the IndexError cases."""
+    import json
+    model = TextToAlignTextModel(vocab_size=29, hidden_size=64, learning_rate=1e-3)
+    rng = np.random.default_rng(seed)
+    cases = []
+    for trial in range(60):
+        L = int(rng.integers(1, 12))
+        text = rng.integers(1, 29, L)
+        al = rng.normal(1.0, 2.0, (L, 2)).astype(np.float32)
+        if trial % 3 == 0:
+            al = np.abs(al)
+        try:
+            out = model.align(torch.from_numpy(text), torch.from_numpy(al)).tolist()
+        except (IndexError, RuntimeError, ValueError) as exc:
+            out = type(exc).__name__
+        cases.append(dict(text=text.tolist(), align=[[float(x) for x in row] for row in al], out=out))
+    with open(os.path.join(OUT, "align_edges.json"), "w") as f:
+        json.dump(cases, f)
+    print("align_edges", len(cases), "errors", sum(isinstance(c["out"], str) for c in cases))
+
+
 def viterbi_case(T, L, seed):
     from voice100_b200.synth import viterbi_inputs
     return viterbi_inputs(T, L, 29, seed)
@@ -305,3 +328,4 @@ if __name__ == "__main__":
     gen_mcep()
     gen_tts_v1_mcep()
     gen_tokenizer()
+    gen_align_edges()

@@ -124,6 +124,34 @@ def test_tokenizers_match_reference():
         BasicTokenizer("fr")
 
 
+def test_align_edge_cases_match_reference():
+    """TextToAlignTextModel.align / align_batch on alignments with negative entries: wrap-around frame indices,
+    non-monotone starts and the IndexError cases, against the reference's outputs (oracle/gen_golden.py:gen_align_edges).
+    Pure host code: no GPU involved."""
+    import json
+    import os
+    from helpers import GOLDEN
+    import voice100_b200 as v
+    with open(os.path.join(GOLDEN, "align_edges.json")) as f:
+        cases = json.load(f)
+    model = v.TextToAlignTextModel(29, 64)
+    n_err = 0
+    for c in cases:
+        text = torch.tensor(c["text"], dtype=torch.int64)
+        al = torch.tensor(c["align"], dtype=torch.float32)
+        if isinstance(c["out"], str):
+            n_err += 1
+            with pytest.raises((IndexError, RuntimeError, ValueError)):
+                model.align(text, al)
+            with pytest.raises((IndexError, RuntimeError, ValueError)):
+                v.align_batch(text[None], al[None])
+            continue
+        assert model.align(text, al).tolist() == c["out"]
+        got, n = v.align_batch(text[None], al[None])
+        assert got[0, : int(n[0])].tolist() == c["out"]
+    assert 0 < n_err < len(cases)
+
+
 def test_tts_matches_reference():
     sd_a, sd_v, text, align, g = tts_case()
     with torch.no_grad():

@@ -50,22 +50,28 @@ class TextToAlignTextModel(StorageDtypeMixin, nn.Module):
         """Host-side expansion of one utterance's tokens to 20 ms frames (tts.py:89-110): token i fills
         frames [round(t + gap_i), round(t + gap_i + dur_i)), at least one; python round() semantics."""
         assert text.dim() == 1 and align.dim() == 2
-        gaps = align.detach().cpu().tolist()
-        toks = text.detach().cpu().tolist()
-        total = head + int(torch.sum(align)) + tail
-        out = [0] * total
-        t = head
-        for (gap, dur), tok in zip(gaps, toks):
-            t += gap
-            s = round(t)
-            t += dur
-            e = round(t)
-            if s == e:
-                e = max(0, e + 1)
-            if e > total or s < 0:
-                raise IndexError("alignment runs past the aligned text (same failure as the reference)")
-            out[s:e] = [tok] * (e - s)
-        return torch.tensor(out, dtype=text.dtype)
+        return torch.tensor(_align_one(text.detach().cpu().tolist(), align.detach().cpu().tolist(),
+                                       head + int(torch.sum(align)) + tail, head), dtype=text.dtype)
+
+
+def _align_one(toks, gaps, total: int, head: int):
+    """The reference loop verbatim in its index behaviour (tts.py:100-110): `aligntext[j] = text[i]` on a tensor of
+    `total` frames, so a NEGATIVE frame index wraps around from the end (a negative gap early in the text) and an
+    index outside [-total, total) raises IndexError."""
+    out = [0] * total
+    t = head
+    for (gap, dur), tok in zip(gaps, toks):
+        t += gap
+        s = round(t)
+        t += dur
+        e = round(t)
+        if s == e:
+            e = max(0, e + 1)
+        for j in range(s, e):
+            if j < -total or j >= total:
+                raise IndexError(f"index {j} is out of bounds for dimension 0 with size {total}")
+            out[j] = tok
+    return out
 
 
 def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_value: int = 0):
@@ -89,8 +95,13 @@ def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_va
         e = np.rint(t[1::2]).astype(np.int64)
         e = np.where(s == e, np.maximum(0, e + 1), e)
         total = head + int(torch.sum(align[b, :n])) + tail    # the reference sums in float32 (torch.sum)
-        if n and (s.min() < 0 or e.max() > total):
+        if n and a.min() >= 0 and e.max() > total:
             raise IndexError("alignment runs past the aligned text (same failure as the reference)")
+        if n and (s.min() < 0 or a.min() < 0):
+            # negative frame indices wrap around in the reference, and negative gaps / durations make the start frames
+            # non-monotone: take the reference's own loop for this utterance
+            outs.append(np.asarray(_align_one(text_np[b, :n].tolist(), a.tolist(), total, head), np.int64))
+            continue
         # frame f belongs to the LAST token i with s_i <= f < e_i (later tokens overwrite earlier ones in the
         # reference loop); s is non-decreasing, so that is one searchsorted per utterance
         out = np.zeros((total,), np.int64)
