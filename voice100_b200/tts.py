@@ -58,6 +58,8 @@ def _align_one(toks, gaps, total: int, head: int):
     """The reference loop verbatim in its index behaviour (tts.py:100-110): `aligntext[j] = text[i]` on a tensor of
     `total` frames, so a NEGATIVE frame index wraps around from the end (a negative gap early in the text) and an
     index outside [-total, total) raises IndexError."""
+    if total < 0:
+        raise RuntimeError(f"Trying to create tensor with negative dimension {total}")   # torch.zeros(total) in the reference
     out = [0] * total
     t = head
     for (gap, dur), tok in zip(gaps, toks):
@@ -97,6 +99,8 @@ def align_batch(text, align, text_len=None, head: int = 5, tail: int = 5, pad_va
         total = head + int(torch.sum(align[b, :n])) + tail    # the reference sums in float32 (torch.sum)
         if n and a.min() >= 0 and e.max() > total:
             raise IndexError("alignment runs past the aligned text (same failure as the reference)")
+        if total < 0:
+            raise RuntimeError(f"Trying to create tensor with negative dimension {total}")
         if n and (s.min() < 0 or a.min() < 0):
             # negative frame indices wrap around in the reference, and negative gaps / durations make the start frames
             # non-monotone: take the reference's own loop for this utterance
