@@ -179,6 +179,30 @@ def test_dwconv_long_rows_and_stride2(dtype):
         assert rel_err(y2.valid().float(), ref) < OUT_TOL[dtype]
 
 
+@pytest.mark.parametrize("k", [3, 5, 11, 19, 31, 59, 61])
+@pytest.mark.parametrize("T", [1501, 100, 2600, 1])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_stride2_polyphase_matches_torch(k, T, dtype):
+    """Stride 2 as two polyphase stride-1 FIRs on the tensor cores (k <= 59; 61 takes the CUDA-core kernel), vs fp32
+    F.conv1d(stride=2) on the same operands and vs the any-shape kernel: odd/even T, rows longer than one 1024-output
+    chunk, a ragged channel count, more batch rows than one warp walks."""
+    B, C = 11, 20
+    x = rnd(B, C, T, seed=51)
+    w = rnd(C, k, seed=52, scale=1.0 / math.sqrt(k)).to(dtype)
+    scale, shift = torch.rand(C, device=DEV) + 0.5, rnd(C, seed=53)
+    xn = ncw(x, dtype)
+    ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], stride=2, padding=(k - 1) // 2, groups=C)
+    ref = (ref * scale[None, :, None] + shift[None, :, None]).clamp(0, 6)
+    y = K.dwconv(xn, w, scale, shift, k, 2, K.ACT_RELU6)
+    assert y.T == (T - 1) // 2 + 1 == ref.shape[2]
+    assert rel_err(y.valid().float(), ref) < OUT_TOL[dtype]
+    y2 = K.dwconv(xn, w, scale, shift, k, 2, K.ACT_RELU6, simt=True)
+    assert rel_err(y2.valid().float(), ref) < OUT_TOL[dtype]
+    y3 = K.dwconv(xn, w, None, shift, k, 2, K.ACT_NONE)                  # no scale, no activation
+    ref3 = F.conv1d(xn.valid().float(), w.float()[:, None, :], stride=2, padding=(k - 1) // 2, groups=C) + shift[None, :, None]
+    assert rel_err(y3.valid().float(), ref3) < OUT_TOL[dtype]
+
+
 # ------------------------------------------------------------------------------------------------
 # fused expand + depthwise (tcgen05 GEMM whose epilogue runs the depthwise FIR on a shared-memory sliding window)
 # ------------------------------------------------------------------------------------------------

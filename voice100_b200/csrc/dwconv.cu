@@ -204,6 +204,141 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
   }
 }
 
+// Stride-2 depthwise conv on the same tensor-core FIR (the first encoder block, asr.py:68), as two polyphase
+// stride-1 filters:   out[o] = sum_j w[j] x[2 o + j - p]
+//                            = sum_a w_e[a] x_e[o + a - p_e]  +  sum_a w_o[a] x_o[o + a - p_o],
+// x_e[i] = x[2 i], x_o[i] = x[2 i + 1];  w_e = the taps j = p (mod 2) (they meet even samples), w_o = the others;
+// p_e = floor(p / 2), p_o = ceil(p / 2).  The row is staged de-interleaved twice over -- by sample parity (a PRMT pair
+// per 32-bit word on the way from the 16-byte global loads to shared memory) and by 16-sample block parity (the
+// layout of dw_mma_kernel) -- and both filters accumulate into the same two accumulators of a 256-output double tile.
+// Their zero extensions z_e = z + (p & 1), z_o = z give both the same delay D = z_o + p_o (even), so the tile geometry
+// and the store pattern are those of dw_mma_kernel with s = P / 2 - D.
+// The CUDA-core version of this kernel (dw_s2_kernel below, kept for long filters) ran at 0.30 of the HBM roofline with
+// the issue slots 88 % busy on fp32 FMAs and bf16 unpacking.
+template <int Q, int DT>
+__global__ void __launch_bounds__(kDwWarps * 32)
+dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
+                 const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
+                 long long y_pitch, int B, int C, int T_in, int T_out, int k, int act) {
+  __shared__ __align__(128) unsigned short xs_all[kDwWarps][2][kDwRow];     // [phase e / o][block-parity layout]
+  __shared__ __align__(16) unsigned short ws_all[kDwWarps][2][16 * Q + 16];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * kDwWarps + warp;
+  const int b0 = blockIdx.z * kDwRowsPerWarp;
+  const int nb = min(kDwRowsPerWarp, B - b0);
+  const int oc0 = blockIdx.x * kDwChunk;          // first output of this CTA
+  const int p = (k - 1) >> 1;
+  const int p_o = (p + 1) >> 1;                   // taps of the odd-phase filter before its centre
+  const int z = p_o & 1;                          // makes the common delay D even
+  const int D = z + p_o;
+  const int P2 = (D + 7) & ~7;                    // the staged phase arrays start at x_e / x_o index oc0 - P2
+  const int s = P2 - D;                           // tiles start s outputs before oc0 (even)
+  const int iA = oc0 - P2;                        // phase index of staged sample 0 (x index 2 iA, a multiple of 16)
+  pdl_trigger();
+  if (c >= C) return;
+
+  const int len = min(kDwChunk, T_out - oc0);
+  const int n_dt = (len + s + 255) / 256;
+  const int n_vec = min(4 * 87, 4 * (16 * n_dt + Q));   // 16-byte global loads per row: 8 samples = 4 per phase each
+
+  // zero-extended polyphase filters: ws[ph][16 + z_ph + a] = w_ph[a]
+  for (int i = lane; i < 2 * (16 * Q + 16); i += 32) {
+    const int ph = i / (16 * Q + 16), ii = i - ph * (16 * Q + 16);
+    const int first = ph == 0 ? (p & 1) : 1 - (p & 1);           // w_e takes taps j = p (mod 2)
+    const int a = ii - 16 - (ph == 0 ? z + (p & 1) : z);
+    const int j = first + 2 * a;
+    ws_all[warp][ph][ii] = (a >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : static_cast<unsigned short>(0);
+  }
+  __syncwarp();
+  const int g = lane >> 2, tg = lane & 3;
+  uint32_t af[2][Q][4];
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+    const unsigned short* wsu = ws_all[warp][ph];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int i0 = 16 + 16 * q + 4 * tg - g;
+      af[ph][q][0] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);
+      af[ph][q][1] = uint32_t(wsu[i0 - 8]) | (uint32_t(wsu[i0 - 7]) << 16);
+      af[ph][q][2] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);
+      af[ph][q][3] = uint32_t(wsu[i0 - 6]) | (uint32_t(wsu[i0 - 5]) << 16);
+    }
+  }
+  const float sc = scale ? scale[c] : 1.0f;
+  const float sh = shift[c];
+  const bool even = (g & 1) == 0;
+  const int pos0 = 64 * tg + (even ? g : g + 7) - s;
+  const bool relu6 = act == V100_ACT_RELU6;
+  unsigned short* xs_e = xs_all[warp][0];
+  unsigned short* xs_o = xs_all[warp][1];
+  pdl_wait();
+
+  for (int r = 0; r < nb; ++r) {
+    const unsigned short* xrow = x + (static_cast<long long>(b0 + r) * C + c) * x_pitch;
+    // ---- stage: 8 consecutive samples -> 4 even-phase + 4 odd-phase samples ----
+    for (int v = lane; v < n_vec; v += 32) {
+      const int t = 2 * iA + 8 * v;                               // x index of the first sample (a multiple of 8)
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (t >= 0 && t < T_in) {
+        val = *reinterpret_cast<const uint4*>(xrow + t);
+        if (t + 8 > T_in) {
+          uint32_t* u = reinterpret_cast<uint32_t*>(&val);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (t + i >= T_in) u[i >> 1] &= (i & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+        }
+      }
+      const uint2 ev = make_uint2(__byte_perm(val.x, val.y, 0x5410), __byte_perm(val.z, val.w, 0x5410));
+      const uint2 od = make_uint2(__byte_perm(val.x, val.y, 0x7632), __byte_perm(val.z, val.w, 0x7632));
+      const int d = dw_map(4 * v);                                // phase samples 4v .. 4v+3: one 8-byte word
+      *reinterpret_cast<uint2*>(xs_e + d) = ev;
+      *reinterpret_cast<uint2*>(xs_o + d) = od;
+    }
+    __syncwarp();
+    unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + oc0 + pos0;
+    int pos = pos0;
+    auto finish = [&](float (&acc)[4], unsigned short* yq, int posq) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
+      const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
+      const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
+      const float lo0 = even ? acc[0] : r0, hi0 = even ? r0 : acc[2];
+      const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
+      const uint32_t o0 = relu6 ? pack2_relu6<DT>(lo0, hi0) : pack2<DT>(lo0, hi0);
+      const uint32_t o1 = relu6 ? pack2_relu6<DT>(lo1, hi1) : pack2<DT>(lo1, hi1);
+      if (posq >= 0 && posq < len) {
+        if (posq + 1 < len) *reinterpret_cast<uint32_t*>(yq) = o0;
+        else *yq = static_cast<unsigned short>(o0 & 0xFFFFu);     // (the row may end on an even column inside the pitch)
+      }
+      if (posq + 32 >= 0 && posq + 32 < len) {
+        if (posq + 33 < len) *reinterpret_cast<uint32_t*>(yq + 32) = o1;
+        else yq[32] = static_cast<unsigned short>(o1 & 0xFFFFu);
+      }
+    };
+#pragma unroll 1
+    for (int d = 0; d < n_dt; ++d) {
+      float accA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const uint2* xe = reinterpret_cast<const uint2*>(ph == 0 ? xs_e : xs_o) + 32 * d + lane;
+        const uint2* xo = reinterpret_cast<const uint2*>((ph == 0 ? xs_e : xs_o) + kDwHalf) + 32 * d + lane;
+#pragma unroll
+        for (int cq = 0; cq <= Q; ++cq) {
+          const uint2 f = (cq & 1) ? xo[4 * (cq >> 1)] : xe[4 * (cq >> 1)];
+          if (cq < Q) mma_16816<DT>(accA, af[ph][cq][0], af[ph][cq][1], af[ph][cq][2], af[ph][cq][3], f.x, f.y);
+          if (cq > 0) mma_16816<DT>(accB, af[ph][cq - 1][0], af[ph][cq - 1][1], af[ph][cq - 1][2], af[ph][cq - 1][3], f.x, f.y);
+        }
+      }
+      finish(accA, yp, pos);
+      finish(accB, yp + 16, pos + 16);
+      yp += 256;
+      pos += 256;
+    }
+    __syncwarp();   // everyone is done reading the staged row before the next one overwrites it
+  }
+}
+
 // Stride-2 depthwise conv (the first encoder block, asr.py:68): one warp per (batch, channel) row,
 // the row segment staged in shared memory with coalesced 16-byte loads, each lane producing outputs
 // o = oc0 + 32 r + lane so that the 32-bit input words (x[2o+2m], x[2o+2m+1]) are consecutive across lanes.
@@ -363,6 +498,23 @@ int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, 
       case 6: launch_dw_mma<6>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
       default: launch_dw_mma<7>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
     }
+  } else if (!force_simt && stride == 2 && k <= 59) {
+    // polyphase tensor-core kernel: each phase filter has <= 30 taps -> Q <= 3
+    const int pp = (k - 1) / 2, p_o = (pp + 1) / 2, zz = p_o & 1;
+    const int ke = (k - (pp & 1) + 1) / 2, ko = (k - (1 - (pp & 1)) + 1) / 2;
+    const int q_e = (ke + 15 + zz + (pp & 1) + 15) / 16, q_o = (ko + 15 + zz + 15) / 16;
+    const int Qs = q_e > q_o ? q_e : q_o;
+    dim3 grid((T_out + kDwChunk - 1) / kDwChunk, (C + kDwWarps - 1) / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
+    const long long xpl = x_pitch, ypl = y_pitch;
+#define V100_S2(QQ)                                                                                                         \
+    do {                                                                                                                    \
+      if (dtype == DT_F16)                                                                                                  \
+        launch_pdl(dw_s2_mma_kernel<QQ, DT_F16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
+      else                                                                                                                  \
+        launch_pdl(dw_s2_mma_kernel<QQ, DT_BF16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
+    } while (0)
+    if (Qs <= 2) V100_S2(2); else V100_S2(3);
+#undef V100_S2
   } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
     dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
     const long long xpl = x_pitch, ypl = y_pitch;
