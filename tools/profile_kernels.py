@@ -24,7 +24,7 @@ def ncw(C, T):
 
 
 if "dw" in which:
-    for C, k in ((2048, 83), (2048, 59), (1024, 35)):
+    for C, k in ((2048, 83), (2048, 67), (2048, 59), (1024, 35)):
         x = ncw(C, T)
         w = (torch.randn(C, k, device=DEV) / k ** 0.5).to(torch.bfloat16)
         s, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)

@@ -21,7 +21,7 @@ int fail(int code, const char* fmt, ...) {
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("V100_PDL");
-    return e == nullptr || e[0] != '0';
+    return e != nullptr && e[0] == '1';
   }();
   return on;
 }

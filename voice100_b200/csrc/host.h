@@ -23,7 +23,9 @@ int num_sms();
 
 // Launch with programmatic stream serialization (see pdl_wait / pdl_trigger in common.cuh): the kernel may start
 // while the previous kernel of the stream is still draining.  ONLY for kernels that call pdl_wait() before touching
-// data of the chain.  V100_PDL=0 in the environment turns the attribute off (plain stream order) for A/B runs.
+// data of the chain.  Opt-in: V100_PDL=1 in the environment sets the attribute; the default is plain stream order,
+// because three alternating same-box A/B runs of the 30-kernel step showed no gain (6.59-6.77 ms with, 6.62-6.64 ms
+// without: the CUDA-graph step already equals the sum of its kernels, profiles/r02_history.md).
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
