@@ -12,9 +12,9 @@ def run(C, B=256, T=751, k=83, reps=20):
     for _ in range(reps): y = K.dwconv(x, w, s, b, k, 1, K.ACT_RELU6)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    tiles = C * ((B + 127) // 128) * ((T + 63) // 64)
     gb = 2 * B * C * T * 2 / 1e9
-    print(f"C={C} B={B} T={T} k={k}: {ms*1e3:.1f} us, {gb/ms*1e3/1e3:.2f} TB/s, {ms*1e3*148/tiles:.3f} us per tile per SM")
-for C in (64, 128, 512, 2048):
-    run(C)
-run(2048, k=19); run(1024, k=35); run(2048, B=128)
+    print(f"{os.environ.get('V100_LIB', 'default')}: C={C} B={B} T={T} k={k}: {ms*1e3:.1f} us, {gb/ms*1e3/1e3:.2f} TB/s")
+for k in (83, 75, 67, 59):
+    run(2048, k=k)
+for k in (51, 35, 27, 19):
+    run(1024, k=k)

@@ -53,6 +53,14 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one set of Toeplitz fragments
+// The staged row starts (p rounded up to V100_DW_PAD + 1) samples before the chunk.  16 samples = 32 bytes: the warp-wide
+// cp.async footprint then starts on a 32-byte SECTOR boundary.  With 8-sample (16-byte) rounding the filters whose
+// (p rounded up to 8) is an odd multiple of 8 (k = 35, 67, 75) staged from a half-sector offset and ran 16-22 % slower
+// (same-box A/B: k = 67/75 372 -> 313 us, k = 35 194 -> 152 us; the others unchanged).
+#ifndef V100_DW_PAD
+#define V100_DW_PAD 15
+#endif
+constexpr int kDwPad = V100_DW_PAD;
 
 // Staged-row layout: sample i of the staged row (i = 0 at x[tcA]) lives in 16-sample block i >> 4; even blocks are
 // packed into xs[0 .. 704), odd blocks into xs[kDwHalf .. kDwRow).  Eight blocks of ONE parity are then 256
@@ -91,8 +99,8 @@ __device__ __forceinline__ void dw_fix_tail(unsigned short* xs, int tcA, int T, 
 // {2j, 2j+1, 2j+8, 2j+9} carry logical kk = 4j .. 4j+3) a thread's (b0, b1) pair is ONE aligned 64-bit load at uint2
 // index 4 (c >> 1) + lane of the parity-(c & 1) array: consecutive lanes read consecutive 8-byte words, 2 wavefronts.
 // One xor-shuffle pair regroups an accumulator into bf16x2 pairs that are stored as full 32-byte sectors.
-// Alignment: the staged row starts at x[tc0 - pl8] (16-byte aligned in global memory); tiles start
-// s = e - (e & 1) outputs before tc0 (e = pl8 - p), leaving e1 = e & 1 to fold into the zero-extended filter;
+// Alignment: the staged row starts at x[tc0 - pl8] (32-byte aligned in global memory); tiles start
+// s = e - (e & 1) outputs before tc0 (e = pl8 - p <= 15), leaving e1 = e & 1 to fold into the zero-extended filter;
 // Q = ceil((k + 15 + e1) / 16) <= 7 for k <= 83.
 template <int Q, bool RELU6, int DT>
 __global__ void __launch_bounds__(kDwWarps * 32)
@@ -108,7 +116,7 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
   const int nb = min(kDwRowsPerWarp, B - b0);
   const int tc0 = blockIdx.x * kDwChunk;
   const int p = (k - 1) >> 1;
-  const int pl8 = (p + 7) & ~7;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
+  const int pl8 = (p + kDwPad) & ~kDwPad;   // staged row starts at x[tc0 - pl8] so global 16-byte chunks stay aligned
   const int e = pl8 - p;
   const int e1 = e & 1;           // folded into the zero-extended filter
   const int s = e - e1;           // tiles start s outputs before tc0
@@ -483,7 +491,7 @@ int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, 
     return fail(V100_E_INVALID, "dwconv: pitches must be multiples of 8 and >= T, bases 16-byte aligned");
   if (B > 65535 || C > 65535 * kDwWarps) return fail(V100_E_UNSUPPORTED, "dwconv: B or C too large for the grid");
   const int p = (k - 1) / 2;
-  const int e1 = (((p + 7) & ~7) - p) & 1;
+  const int e1 = (((p + kDwPad) & ~kDwPad) - p) & 1;
   const int Q = (k + 15 + e1 + 15) / 16;
   auto xp = static_cast<const unsigned short*>(x);
   auto wp = static_cast<const unsigned short*>(w);
