@@ -53,6 +53,11 @@ def rnd(*shape, seed=0, scale=1.0):
     (5, 256, 256, 100, 0, True),       # BLOCK_N=128 path
     (2, 72, 200, 333, 1, False),       # K not a multiple of 64, C_out not a multiple of 128
     (40, 128, 384, 520, 0, True),      # > 148 tiles: persistent loop + both TMEM buffers reused
+    (4, 2048, 512, 751, 0, True),      # pair kernel at the project shape, K = 2048
+    (40, 256, 1024, 751, 1, False),    # weights resident in tensor memory (WRES): K = 256, 4 channel blocks
+    (48, 512, 2048, 300, 1, False),    # WRES: K = 512 (all 512 TMEM columns), 8 channel blocks
+    (128, 128, 512, 300, 0, True),     # WRES: one ring stage per tile, residual
+    (64, 384, 768, 130, 1, True),      # WRES: K = 384, 3 channel blocks, ReLU6 + residual
 ])
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_conv1x1_matches_torch(B, C_in, C_out, T, act, res, dtype):
@@ -81,7 +86,8 @@ def test_conv_gemm_stress_is_deterministic():
     than SMs so both TMEM buffers and every smem stage are recycled), alternating with a different-shaped launch on the
     same stream; every result must be bit-identical to the first, which itself matches fp32 PyTorch."""
     shapes = [(2, 72, 200, 333, 1, False), (3, 1024, 256, 751, 0, True), (40, 128, 384, 520, 0, True),
-              (2, 512, 2048, 300, 1, False), (7, 264, 136, 77, 1, True)]
+              (2, 512, 2048, 300, 1, False), (7, 264, 136, 77, 1, True), (48, 512, 2048, 300, 1, False),
+              (64, 384, 768, 130, 1, True)]
     other_x = ncw(rnd(1, 64, 97, seed=33))
     other_w = rnd(128, 64, seed=34, scale=0.1).to(torch.bfloat16)
     other_b = torch.zeros(128, device=DEV)

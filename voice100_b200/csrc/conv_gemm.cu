@@ -15,6 +15,14 @@
 // 1.5x fewer operand bytes from L2 to shared memory than the single-CTA tile -- the first working
 // version of this kernel measured ~10.7 TB/s of L2->SM operand traffic, i.e. it was L2-bound.
 //
+// WRES (weights resident): for C_in <= 512 a CTA pair keeps its 256 x C_in weight block in TENSOR MEMORY for the whole
+// kernel (tcgen05.mma with the A operand from TMEM, 16-bit elements packed two per column) and works only on tiles of
+// that channel block; the ring then carries activations only.  ncu on the plain pair kernel (profiles/r02_gemm_stalls.md):
+// the MMA warp spends 55 % of its time waiting for operand bytes while the producer waits for free slots -- the tile
+// needs 64 B/clk/SM of operands (32 KB per 512 clk k-block) and L2 delivers ~10 TB/s chip-wide.  Without the weights
+// a k-block needs half the bytes, so the same ring covers twice the MMA time.  Tiles are 256 channels x 128 steps
+// (two 128-column accumulators + C_in/2 weight columns = 512 TMEM columns at C_in = 512).
+//
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warp 3 = idle, warps 4..11 = epilogue (two groups of four warps; warp%4 selects the TMEM
 // lane quadrant it is allowed to read).
@@ -58,30 +66,41 @@ struct GemmParams {
   int dtype;                // DT_BF16 / DT_F16: storage type of x, W, y, res
   float* y32;
   long long y32_pitch;
+  const unsigned short* w_raw;  // WRES: the row-major [C_out][C_in] weights themselves
 };
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG = 1>
+// epilogue variant bits (compile time: the generic epilogue was ~2000 SASS instructions of run-time branches and the
+// epilogue warps spent 28 % of their samples on instruction fetch)
+enum { EPI_RELU6 = 1, EPI_RES = 2, EPI_F16 = 4 };
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG = 1, bool WRES = false>
 struct GemmCfg {
   static constexpr int kBCols = BLOCK_N / CG;  // time columns this CTA stages per k-block
-  static constexpr int kStageBytes = kATileBytes + (kBCols / 64) * kBAtomBytes;
+  static constexpr int kStageK = WRES ? 128 : kBlockK;  // K extent of one ring stage
+  static constexpr int kStageBytes = WRES ? kStageK * 64 * 2 * (kBCols / 64) : kATileBytes + (kBCols / 64) * kBAtomBytes;
+  static constexpr int kWCol0 = 2 * N_ACC * BLOCK_N;  // WRES: first TMEM column of the resident weights
   static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? 4 * kChunkBytes : 0;
   static constexpr int kBarBytes = 256;
   static constexpr int kSmemBytes = 1024 + STAGES * kStageBytes + kStagingBytes + kBarBytes;
-  static constexpr int kTmemCols = 2 * N_ACC * BLOCK_N;
+  static constexpr int kTmemCols = WRES ? 512 : 2 * N_ACC * BLOCK_N;
+  static_assert(!WRES || (CG == 2 && BLOCK_N == 128 && N_ACC == 1), "WRES: CTA pairs, 128-column tiles");
   static constexpr int kOutCols = N_ACC * BLOCK_N;       // output time steps per tile
   static constexpr int kChunksPerGroup = kOutCols / 128;  // 64-column chunks per epilogue group per tile
   static_assert(kTmemCols == 512 || kTmemCols == 256, "TMEM allocation must be a power of two");
   static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG>
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int CG, int EPI, bool WRES>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CUtensorMap& tm_x,
                                                const CUtensorMap& tm_y, const CUtensorMap& tm_res,
                                                const GemmParams& p) {
-  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES, CG>;
+  using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES, CG, WRES>;
   static_assert(CG == 1 || (N_ACC == 1 && OUT_MODE == OUT_BF16), "the CTA-pair path serves the plain bf16 conv");
+  constexpr bool kRelu6 = (EPI & EPI_RELU6) != 0, kRes = (EPI & EPI_RES) != 0;
+  constexpr int DT = (EPI & EPI_F16) ? DT_F16 : DT_BF16;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
+  // WRES: gridDim.x / CG is a multiple of m_tiles, so `tile % m_tiles` is the same for every tile of this CTA
   const int tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,11 +118,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
 
   pdl_trigger();   // persistent grid: every CTA is resident, the next kernel may queue up behind our tail
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_w);
+    if (!WRES) tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_x);
     if (OUT_MODE == OUT_BF16) {
       tma_prefetch_desc(&tm_y);
-      if (p.has_res) tma_prefetch_desc(&tm_res);
+      if (kRes) tma_prefetch_desc(&tm_res);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -131,6 +150,31 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  if constexpr (WRES) {
+    // This CTA's 128 weight rows -> tensor memory, straight from global memory (weights are not produced by the
+    // preceding kernel, so this runs in front of pdl_wait): TMEM lane = output channel, and a row-major 16-bit row
+    // already is "two K elements per 32-bit column".  The two epilogue warps of a lane quadrant alternate
+    // 32-column blocks.
+    if (warp >= 4) {
+      const int q = warp & 3, g = (warp - 4) >> 2;
+      const int ch = ((tile0 % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32 + lane;
+      const uint4* wrow = reinterpret_cast<const uint4*>(p.w_raw + static_cast<long long>(ch) * p.C_in);
+      for (int c0 = g * 32; c0 < p.C_in / 2; c0 += 64) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 v = __ldg(wrow + (c0 >> 2) + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tmem_st32(tmem_base + (uint32_t(q * 32) << 16) + Cfg::kWCol0 + c0, r);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    cluster_sync_all();   // the leader's MMAs read both CTAs' halves
+    tc_fence_after();
+  }
   pdl_wait();      // everything above overlapped the previous kernel's tail; from here on we read its output
 
   if (warp == 0) {
@@ -154,9 +198,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
-            uint8_t* sb = sa + kATileBytes;
             if (issuer) {
-              if constexpr (CG == 2) {
+              if constexpr (WRES) {
+                // activations only: one [128 k rows x 64 steps] box per CTA, credited to the leader's barrier
+                if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                tma_load_3d_cg2(sa, &tm_x, fb, t_in0, xrow0 + kb * Cfg::kStageK, b);
+              } else if constexpr (CG == 2) {
+                uint8_t* sb = sa + kATileBytes;
                 // both CTAs' bytes are credited to the LEADER's full barrier (the MMA issuer waits there)
                 if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
                 const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -165,6 +214,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
                 for (int a = 0; a < Cfg::kBCols / 64; ++a)
                   tma_load_3d_cg2(sb + a * kBAtomBytes, &tm_x, fb, t_in0 + a * 64, xrow0 + kb * kBlockK, b);
               } else {
+                uint8_t* sb = sa + kATileBytes;
                 mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                 tma_load_2d(sa, &tm_w, &full_bar[stage], tap * p.C_in + kb * kBlockK, m0);
 #pragma unroll
@@ -203,17 +253,27 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t b_addr = a_addr + kATileBytes;
+            if constexpr (WRES) {
+              // A from tensor memory: 8 columns per K = 16 step; B: MN-major SW128, 16 k rows = 2048 B per K step
+              const uint32_t a_tmem = tmem_base + Cfg::kWCol0 + kb * (Cfg::kStageK / 2);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // A: K-major SW128 (8-row groups 1024 B apart; +32 B per 16-element K step inside the atom)
-              const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024);
-              // B: MN-major SW128 (64-time atoms 8 KB apart = LBO; 8-k-row groups 1024 B apart = SBO;
-              //    16 k rows = 2048 B per K step)
-              const uint64_t db = umma_desc(b_addr + k * 2048, kBAtomBytes, 1024);
-              if (issuer) {
-                if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
-                else umma_bf16(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+              for (int k = 0; k < Cfg::kStageK / 16; ++k) {
+                const uint64_t db = umma_desc(a_addr + k * 2048, kBAtomBytes, 1024);
+                if (issuer) umma_ts_cg2(d_tmem, a_tmem + k * 8, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+              }
+            } else {
+              const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // A: K-major SW128 (8-row groups 1024 B apart; +32 B per 16-element K step inside the atom)
+                const uint64_t da = umma_desc(a_addr + k * 32, 16, 1024);
+                // B: MN-major SW128 (64-time atoms 8 KB apart = LBO; 8-k-row groups 1024 B apart = SBO;
+                //    16 k rows = 2048 B per K step)
+                const uint64_t db = umma_desc(b_addr + k * 2048, kBAtomBytes, 1024);
+                if (issuer) {
+                  if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+                  else umma_bf16(d_tmem, da, db, idesc, ((used >> acc) & 1u) | (k > 0 ? 1u : 0u));
+                }
               }
             }
             used |= 1u << acc;
@@ -249,13 +309,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
       const uint32_t swz = uint32_t(lane & 7);
       uint8_t* my_row = stg + lane * 128;
       const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
-      const bool relu6 = p.act == V100_ACT_RELU6;
-      const bool f16 = p.dtype == DT_F16;
 
       // one elected lane of the (converged) warp issues every TMA operation of this warp; bulk async-groups are
       // per thread, so the same lane also commits and waits
       const bool issuer = elect_one();
-      if (p.has_res && issuer && tile0 < p.num_tiles) {
+      if (kRes && issuer && tile0 < p.num_tiles) {
         const int r = tile0 / p.m_tiles;
         mbar_expect_tx(&rbar[0], kWarpChunkBytes);
         tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + h * 64,
@@ -268,6 +326,35 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
         const bool live = tile < p.num_tiles && ch_t < p.C_out;
         sc_o = (live && p.scale != nullptr) ? __ldg(p.scale + ch_t) : 1.0f;
         sh_o = live ? __ldg(p.shift + ch_t) : 0.0f;
+      };
+      // eight accumulator columns -> one 16-byte piece of this lane's staged row
+      auto emit8 = [&](const float (&a)[8], uint4* dst) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = a[e];
+        uint4 w;
+        if constexpr (!kRes) {
+          if constexpr (kRelu6) {
+            w.x = pack2_relu6<DT>(o[0], o[1]); w.y = pack2_relu6<DT>(o[2], o[3]);
+            w.z = pack2_relu6<DT>(o[4], o[5]); w.w = pack2_relu6<DT>(o[6], o[7]);
+          } else {
+            w.x = pack2<DT>(o[0], o[1]); w.y = pack2<DT>(o[2], o[3]);
+            w.z = pack2<DT>(o[4], o[5]); w.w = pack2<DT>(o[6], o[7]);
+          }
+        } else {
+          if constexpr (kRelu6) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
+          }
+          const uint4 rr = *dst;
+          o[0] += unpack_lo<DT>(rr.x); o[1] += unpack_hi<DT>(rr.x);
+          o[2] += unpack_lo<DT>(rr.y); o[3] += unpack_hi<DT>(rr.y);
+          o[4] += unpack_lo<DT>(rr.z); o[5] += unpack_hi<DT>(rr.z);
+          o[6] += unpack_lo<DT>(rr.w); o[7] += unpack_hi<DT>(rr.w);
+          w.x = pack2<DT>(o[0], o[1]); w.y = pack2<DT>(o[2], o[3]);
+          w.z = pack2<DT>(o[4], o[5]); w.w = pack2<DT>(o[6], o[7]);
+        }
+        *dst = w;
       };
       float sc, sh;
       load_scalars(tile0, sc, sh);
@@ -290,82 +377,59 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           const int buf = n & 1;
           uint32_t v0[32], v1[32];
           const uint32_t col0 = accbuf * (N_ACC * BLOCK_N);
+          uint8_t* rowp = my_row + buf * kWarpChunkBytes;
+          auto release_acc = [&]() {
+            if (i == CPG - 1) {  // this warp is done reading the accumulator buffer
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
+                else mbar_arrive(&tmem_empty[accbuf]);
+              }
+            }
+          };
           if constexpr (N_ACC == 1) {
+            // the second half of the chunk is in flight while the first half is converted and staged
             tmem_ld32(lane_addr + col0 + c * 64, v0);
+            tmem_ld_wait();
+            tmem_ld_fence(v0);
             tmem_ld32(lane_addr + col0 + c * 64 + 32, v1);
+            // slot `buf` is free: lane 0 waited for its previous TMA store before the __syncwarp that ended
+            // the previous chunk.  With a residual it now holds this chunk's residual sub-tile.
+            if constexpr (kRes) mbar_wait(&rbar[buf], (n >> 1) & 1);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = fmaf(__uint_as_float(v0[k16 * 8 + e]), sc, sh);
+              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
+            }
+            tmem_ld_wait();
+            tmem_ld_fence(v1);
+            release_acc();
+#pragma unroll
+            for (int k16 = 4; k16 < 8; ++k16) {
+              float a[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a[e] = fmaf(__uint_as_float(v1[(k16 - 4) * 8 + e]), sc, sh);
+              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
+            }
           } else {
             tmem_ld32(lane_addr + col0 + c * 32, v0);            // even output phase
             tmem_ld32(lane_addr + col0 + BLOCK_N + c * 32, v1);  // odd output phase
-          }
-          tmem_ld_wait();
-          if (i == CPG - 1) {  // this warp is done reading the accumulator buffer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CG == 2) mbar_arrive_cluster(tmem_empty_leader + accbuf * 8);
-              else mbar_arrive(&tmem_empty[accbuf]);
-            }
-          }
-          // slot `buf` is free: lane 0 waited for its previous TMA store before the __syncwarp that ended
-          // the previous chunk.  With a residual it now holds this chunk's residual sub-tile.
-          if (p.has_res) mbar_wait(&rbar[buf], (n >> 1) & 1);
-          uint8_t* rowp = my_row + buf * kWarpChunkBytes;
+            tmem_ld_wait();
+            release_acc();
+            if constexpr (kRes) mbar_wait(&rbar[buf], (n >> 1) & 1);
 #pragma unroll
-          for (int k16 = 0; k16 < 8; ++k16) {
-            uint4* dst = reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4));
-            float o[8];
+            for (int k16 = 0; k16 < 8; ++k16) {
+              float a[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float a;
-              if constexpr (N_ACC == 1) {
-                const int j = k16 * 8 + e;
-                a = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
-              } else {
+              for (int e = 0; e < 8; ++e) {
                 const int j = k16 * 4 + (e >> 1);
-                a = __uint_as_float((e & 1) ? v1[j] : v0[j]);
+                a[e] = fmaf(__uint_as_float((e & 1) ? v1[j] : v0[j]), sc, sh);
               }
-              o[e] = fmaf(a, sc, sh);
+              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
             }
-            uint4 w;
-            if (!p.has_res) {
-              if (relu6) {
-                if (f16) {
-                  w.x = pack_f16x2_relu6(o[0], o[1]); w.y = pack_f16x2_relu6(o[2], o[3]);
-                  w.z = pack_f16x2_relu6(o[4], o[5]); w.w = pack_f16x2_relu6(o[6], o[7]);
-                } else {
-                  w.x = pack_bf16x2_relu6(o[0], o[1]); w.y = pack_bf16x2_relu6(o[2], o[3]);
-                  w.z = pack_bf16x2_relu6(o[4], o[5]); w.w = pack_bf16x2_relu6(o[6], o[7]);
-                }
-              } else if (f16) {
-                w.x = pack_f16x2(o[0], o[1]); w.y = pack_f16x2(o[2], o[3]);
-                w.z = pack_f16x2(o[4], o[5]); w.w = pack_f16x2(o[6], o[7]);
-              } else {
-                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-                w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-              }
-            } else {
-              if (relu6) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
-              }
-              const uint4 rr = *dst;
-              if (f16) {
-                o[0] += f16_lo(rr.x); o[1] += f16_hi(rr.x);
-                o[2] += f16_lo(rr.y); o[3] += f16_hi(rr.y);
-                o[4] += f16_lo(rr.z); o[5] += f16_hi(rr.z);
-                o[6] += f16_lo(rr.w); o[7] += f16_hi(rr.w);
-                w.x = pack_f16x2(o[0], o[1]); w.y = pack_f16x2(o[2], o[3]);
-                w.z = pack_f16x2(o[4], o[5]); w.w = pack_f16x2(o[6], o[7]);
-              } else {
-                o[0] += bf16_lo(rr.x); o[1] += bf16_hi(rr.x);
-                o[2] += bf16_lo(rr.y); o[3] += bf16_hi(rr.y);
-                o[4] += bf16_lo(rr.z); o[5] += bf16_hi(rr.z);
-                o[6] += bf16_lo(rr.w); o[7] += bf16_hi(rr.w);
-                w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-                w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
-              }
-            }
-            *dst = w;
           }
           fence_proxy_async();
           __syncwarp();
@@ -373,7 +437,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
             tma_store_3d(&tm_y, stg + buf * kWarpChunkBytes, t_tile * Cfg::kOutCols + c * 64, m0, b);
             tma_store_commit();
             tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
-            if (p.has_res) {
+            if constexpr (kRes) {
               int ntile = tile, nc = c + 2;
               if (i == CPG - 1) { ntile = tile + tile_step; nc = h; }
               if (ntile < p.num_tiles) {
@@ -444,32 +508,44 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
   }
 }
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                  const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
                  const GemmParams p) {
-  conv_gemm_body<BLOCK_N, N_ACC, OUT_MODE, STAGES, 1>(tm_w, tm_x, tm_y, tm_res, p);
+  conv_gemm_body<BLOCK_N, N_ACC, OUT_MODE, STAGES, 1, EPI, false>(tm_w, tm_x, tm_y, tm_res, p);
 }
 
 // CTA-pair variant: 256 output channels x 256 time steps per cluster of two CTAs
-template <int STAGES>
+template <int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                       const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
                       const GemmParams p) {
-  conv_gemm_body<256, 1, OUT_BF16, STAGES, 2>(tm_w, tm_x, tm_y, tm_res, p);
+  conv_gemm_body<256, 1, OUT_BF16, STAGES, 2, EPI, false>(tm_w, tm_x, tm_y, tm_res, p);
+}
+
+// CTA-pair variant with the pair's weight block resident in tensor memory: 256 channels x 128 steps per tile
+template <int STAGES, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+conv_gemm_wres_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_y,
+                      const __grid_constant__ CUtensorMap tm_res, const GemmParams p) {
+  conv_gemm_body<128, 1, OUT_BF16, STAGES, 2, EPI, true>(tm_x, tm_x, tm_y, tm_res, p);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 
-template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
-static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
-                       const GemmParams& p, cudaStream_t stream) {
+static int epi_of(const GemmParams& p) {
+  return (p.act == V100_ACT_RELU6 ? EPI_RELU6 : 0) | (p.has_res ? EPI_RES : 0) | (p.dtype == DT_F16 ? EPI_F16 : 0);
+}
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES, int EPI>
+static int launch_gemm_e(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
+                         const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
-  auto kern = conv_gemm_kernel<BLOCK_N, N_ACC, OUT_MODE, STAGES>;
+  auto kern = conv_gemm_kernel<BLOCK_N, N_ACC, OUT_MODE, STAGES, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V100_CUDA(cudaGetDevice(&dev));
@@ -482,12 +558,42 @@ static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUten
   return 0;
 }
 
+// run-time epilogue flags -> the compile-time variant
+#define V100_EPI_DISPATCH(FN, ...)                      \
+  switch (epi_of(p)) {                                  \
+    case 0: return FN<__VA_ARGS__, 0>(V100_EPI_ARGS);   \
+    case 1: return FN<__VA_ARGS__, 1>(V100_EPI_ARGS);   \
+    case 2: return FN<__VA_ARGS__, 2>(V100_EPI_ARGS);   \
+    case 3: return FN<__VA_ARGS__, 3>(V100_EPI_ARGS);   \
+    case 4: return FN<__VA_ARGS__, 4>(V100_EPI_ARGS);   \
+    case 5: return FN<__VA_ARGS__, 5>(V100_EPI_ARGS);   \
+    case 6: return FN<__VA_ARGS__, 6>(V100_EPI_ARGS);   \
+    default: return FN<__VA_ARGS__, 7>(V100_EPI_ARGS);  \
+  }
+
+template <int BLOCK_N, int N_ACC, int OUT_MODE, int STAGES>
+static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
+                       const GemmParams& p, cudaStream_t stream) {
+#define V100_EPI_ARGS tw, tx, ty, tr, p, stream
+  if constexpr (OUT_MODE == OUT_F32) {
+    return launch_gemm_e<BLOCK_N, N_ACC, OUT_MODE, STAGES, 0>(V100_EPI_ARGS);
+  } else if constexpr (N_ACC == 2) {  // transposed conv: bias only
+    if (p.act != V100_ACT_NONE || p.has_res) return fail(V100_E_UNSUPPORTED, "two-phase GEMM: bias-only epilogue");
+    if (p.dtype == DT_F16) return launch_gemm_e<BLOCK_N, N_ACC, OUT_MODE, STAGES, EPI_F16>(V100_EPI_ARGS);
+    return launch_gemm_e<BLOCK_N, N_ACC, OUT_MODE, STAGES, 0>(V100_EPI_ARGS);
+  } else {
+    V100_EPI_DISPATCH(launch_gemm_e, BLOCK_N, N_ACC, OUT_MODE, STAGES)
+  }
+#undef V100_EPI_ARGS
+}
+
 constexpr int kPairStages = 5;
 
-static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
-                            const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<256, 1, OUT_BF16, kPairStages, 2>;
-  auto kern = conv_gemm_pair_kernel<kPairStages>;
+template <int STAGES, int EPI>
+static int launch_gemm_pair_e(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty,
+                              const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<256, 1, OUT_BF16, STAGES, 2>;
+  auto kern = conv_gemm_pair_kernel<STAGES, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V100_CUDA(cudaGetDevice(&dev));
@@ -499,6 +605,53 @@ static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const 
   if (p.num_tiles < pairs) pairs = p.num_tiles;
   V100_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tw, tx, ty, tr, p));
   return 0;
+}
+
+static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
+                            const GemmParams& p, cudaStream_t stream) {
+#define V100_EPI_ARGS tw, tx, ty, tr, p, stream
+  V100_EPI_DISPATCH(launch_gemm_pair_e, kPairStages)
+#undef V100_EPI_ARGS
+}
+
+// Weights-resident pair kernel (WRES).  Each pair serves ONE 256-channel block for the whole launch, so the number of
+// pairs is rounded down to a multiple of the number of channel blocks (72 of 74 pairs for 4 or 8 blocks).
+constexpr int kWresStages = 9;
+
+template <int STAGES, int EPI>
+static int launch_gemm_wres_e(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr, const GemmParams& p,
+                              int pairs, cudaStream_t stream) {
+  using Cfg = GemmCfg<128, 1, OUT_BF16, STAGES, 2, true>;
+  auto kern = conv_gemm_wres_kernel<STAGES, EPI>;
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  V100_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured_dev = dev;
+  }
+  V100_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tx, ty, tr, p));
+  return 0;
+}
+
+static int launch_gemm_wres(const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr, const GemmParams& p,
+                            int pairs, cudaStream_t stream) {
+#define V100_EPI_ARGS tx, ty, tr, p, pairs, stream
+  V100_EPI_DISPATCH(launch_gemm_wres_e, kWresStages)
+#undef V100_EPI_ARGS
+}
+
+// WRES applies when the pair's weight block fits in tensor memory next to two 128-column accumulators and the
+// channel blocks divide the device's pairs without leaving more than ~5 % of them idle.
+static int wres_pairs(int C_in, int C_out, int B, int T) {
+  static const int enabled = getenv("V100_GEMM_WRES") ? atoi(getenv("V100_GEMM_WRES")) : 1;  // A/B runs
+  if (!enabled || C_in > 512 || C_in % 128 != 0 || C_out % (2 * kBlockM) != 0) return 0;
+  const int m_tiles = C_out / (2 * kBlockM), all = num_sms() / 2;
+  const int slots = all / m_tiles;
+  if (slots < 1 || slots * m_tiles * 20 < all * 19) return 0;
+  const long long units = static_cast<long long>((T + 127) / 128) * B;
+  if (units < 4LL * slots) return 0;   // too little work per pair to pay for loading the weights
+  return slots * m_tiles;
 }
 
 static int pick_block_n(int T) {
@@ -545,6 +698,16 @@ int conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, c
   p.scale = scale; p.shift = shift; p.act = act; p.has_res = res != nullptr; p.dtype = dtype;
   p.t_tiles = (T + bn - 1) / bn;
   static const int force_cg = getenv("V100_GEMM_CG") ? atoi(getenv("V100_GEMM_CG")) : 0;  // debugging / A-B runs
+  if (const int pairs = force_cg != 1 ? wres_pairs(C_in, C_out, B, T) : 0) {
+    CUtensorMap txw;   // [64 steps x 128 k rows] boxes: one per ring stage and CTA
+    if (int e = make_tmap_3d(&txw, tmap_type(dtype), x, T, C_in, B, x_pitch * 2, int64_t(C_in) * x_pitch * 2, 64, 128)) return e;
+    p.w_raw = static_cast<const unsigned short*>(W);
+    p.k_blocks = C_in / 128;
+    p.t_tiles = (T + 127) / 128;
+    p.m_tiles = C_out / (2 * kBlockM);
+    p.num_tiles = p.m_tiles * p.t_tiles * B;
+    return launch_gemm_wres(txw, ty, tr, p, pairs, stream);
+  }
   if (bn == 256 && C_out % (2 * kBlockM) == 0 && force_cg != 1) {
     p.m_tiles = C_out / (2 * kBlockM);
     p.num_tiles = p.m_tiles * p.t_tiles * B;

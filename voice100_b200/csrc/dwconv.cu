@@ -42,16 +42,6 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a
   }
 }
 
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, bool valid) {
-  // 16-byte global->shared copy that bypasses registers; src-size 0 zero-fills the destination
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
-               "r"(valid ? 16 : 0)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int kDwRowsPerWarp = 8;   // batch rows a warp walks through with one set of Toeplitz fragments
 // The staged row starts (p rounded up to V100_DW_PAD + 1) samples before the chunk.  16 samples = 32 bytes: the warp-wide
 // cp.async footprint then starts on a 32-byte SECTOR boundary.  With 8-sample (16-byte) rounding the filters whose
