@@ -213,8 +213,8 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
 // and the store pattern are those of dw_mma_kernel with s = P / 2 - D.
 // The CUDA-core version of this kernel (dw_s2_kernel below, kept for long filters) ran at 0.30 of the HBM roofline with
 // the issue slots 88 % busy on fp32 FMAs and bf16 unpacking.
-template <int Q, int DT>
-__global__ void __launch_bounds__(kDwWarps * 32)
+template <int Q, int DT, int NV>
+__global__ void __launch_bounds__(kDwWarps * 32, NV <= 7 ? 3 : 2)
 dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
                  const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
                  long long y_pitch, int B, int C, int T_in, int T_out, int k, int act) {
@@ -272,28 +272,45 @@ dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const 
   unsigned short* xs_o = xs_all[warp][1];
   pdl_wait();
 
-  for (int r = 0; r < nb; ++r) {
+  // The row passes through registers on its way to shared memory (cp.async cannot split 16-bit samples by parity), so
+  // the NEXT row's 16-byte loads are issued before this row's MMAs and are in flight while they run: with the loads
+  // issued and consumed back to back the kernel sat at 0.44 of the HBM roofline waiting on them.
+  constexpr int kS2Vec = NV;   // 16-byte loads per lane and row: 11 covers a full 1024-output chunk, 7 three double tiles
+  uint4 pre[kS2Vec];
+  auto load_row = [&](int r) {
     const unsigned short* xrow = x + (static_cast<long long>(b0 + r) * C + c) * x_pitch;
+#pragma unroll
+    for (int i = 0; i < kS2Vec; ++i) {
+      const int v = i * 32 + lane;
+      const int t = 2 * iA + 8 * v;                                 // x index of the first sample (a multiple of 8)
+      pre[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (v < n_vec && t >= 0 && t < T_in) pre[i] = __ldg(reinterpret_cast<const uint4*>(xrow + t));
+    }
+  };
+  load_row(0);
+  for (int r = 0; r < nb; ++r) {
     // ---- stage: 8 consecutive samples -> 4 even-phase + 4 odd-phase samples ----
-    for (int v = lane; v < n_vec; v += 32) {
-      const int t = 2 * iA + 8 * v;                               // x index of the first sample (a multiple of 8)
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (t >= 0 && t < T_in) {
-        val = *reinterpret_cast<const uint4*>(xrow + t);
-        if (t + 8 > T_in) {
+#pragma unroll
+    for (int i = 0; i < kS2Vec; ++i) {
+      const int v = i * 32 + lane;
+      if (v < n_vec) {
+        const int t = 2 * iA + 8 * v;
+        uint4 val = pre[i];
+        if (t < T_in && t + 8 > T_in) {
           uint32_t* u = reinterpret_cast<uint32_t*>(&val);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (t + i >= T_in) u[i >> 1] &= (i & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+          for (int j = 0; j < 8; ++j)
+            if (t + j >= T_in) u[j >> 1] &= (j & 1) ? 0x0000FFFFu : 0xFFFF0000u;
         }
+        const uint2 ev = make_uint2(__byte_perm(val.x, val.y, 0x5410), __byte_perm(val.z, val.w, 0x5410));
+        const uint2 od = make_uint2(__byte_perm(val.x, val.y, 0x7632), __byte_perm(val.z, val.w, 0x7632));
+        const int d = dw_map(4 * v);                                // phase samples 4v .. 4v+3: one 8-byte word
+        *reinterpret_cast<uint2*>(xs_e + d) = ev;
+        *reinterpret_cast<uint2*>(xs_o + d) = od;
       }
-      const uint2 ev = make_uint2(__byte_perm(val.x, val.y, 0x5410), __byte_perm(val.z, val.w, 0x5410));
-      const uint2 od = make_uint2(__byte_perm(val.x, val.y, 0x7632), __byte_perm(val.z, val.w, 0x7632));
-      const int d = dw_map(4 * v);                                // phase samples 4v .. 4v+3: one 8-byte word
-      *reinterpret_cast<uint2*>(xs_e + d) = ev;
-      *reinterpret_cast<uint2*>(xs_o + d) = od;
     }
     __syncwarp();
+    if (r + 1 < nb) load_row(r + 1);
     unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + oc0 + pos0;
     int pos = pos0;
     auto finish = [&](float (&acc)[4], unsigned short* yq, int posq) {
@@ -504,14 +521,18 @@ int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, 
     const int Qs = q_e > q_o ? q_e : q_o;
     dim3 grid((T_out + kDwChunk - 1) / kDwChunk, (C + kDwWarps - 1) / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
     const long long xpl = x_pitch, ypl = y_pitch;
-#define V100_S2(QQ)                                                                                                         \
+    // 16-byte loads per row of the longest chunk (the kernel's n_vec), which sizes the register prefetch
+    const int len0 = T_out < kDwChunk ? T_out : kDwChunk;
+    const bool small = 4 * (16 * ((len0 + 14 + 255) / 256) + 3) <= 7 * 32;
+#define V100_S2(QQ, NV)                                                                                                     \
     do {                                                                                                                    \
       if (dtype == DT_F16)                                                                                                  \
-        launch_pdl(dw_s2_mma_kernel<QQ, DT_F16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
+        launch_pdl(dw_s2_mma_kernel<QQ, DT_F16, NV>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
       else                                                                                                                  \
-        launch_pdl(dw_s2_mma_kernel<QQ, DT_BF16>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
+        launch_pdl(dw_s2_mma_kernel<QQ, DT_BF16, NV>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T_in, T_out, k, act); \
     } while (0)
-    if (Qs <= 2) V100_S2(2); else V100_S2(3);
+    if (Qs <= 2) { if (small) V100_S2(2, 7); else V100_S2(2, 11); }
+    else { if (small) V100_S2(3, 7); else V100_S2(3, 11); }
 #undef V100_S2
   } else if (!force_simt && stride == 2 && k <= 2 * kS2MaxWords - 3) {
     dim3 grid((T_out + kS2Chunk - 1) / kS2Chunk, (C + kDwWarps - 1) / kDwWarps, B);
