@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "host.h"
 
+#include <cstdlib>
+
 namespace v100 {
 
 constexpr int kDwChunk = 1024;            // outputs per CTA along time (4 double-tiles of 256)
@@ -198,6 +200,163 @@ dw_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const uns
       yp += 256;
       pos += 256;
     }
+    __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dw_bulk_kernel: the same Toeplitz FIR with the row staged by ONE bulk copy (cp.async.bulk global -> shared, mbarrier
+// completion) instead of ~110 16-byte cp.async chunks per row.  ncu on dw_mma_kernel (k = 83): the L1 data pipe is 84 %
+// busy, and 37 % of its wavefronts are the staging copies (LDGSTS: 30 per row into shared memory + 19 on the global side),
+// which a bulk copy does not send through the LSU at all.  A bulk copy cannot de-interleave the row by block parity,
+// so the staged row is contiguous and the two accumulators of a double tile are the two HALVES of its 256 outputs:
+//   A[m][n] = out[tau + m + 16 n],   B[m][n] = out[tau + 128 + m + 16 n],          m < 16, n < 8
+//   A = sum_c W_c * X_c,  X_c[kk][n] = xs[16 (n + c) + kk]:  a lane's (b0, b1) is the aligned 64-bit word lane + 4 c
+// (consecutive lanes, consecutive words: conflict-free), 2 Q fragment loads per double tile (dw_mma_kernel: Q + 1, plus
+// the staging).  Everything outside the copied span is zeroed once per buffer -- every row of a CTA has the same span.
+// The copy moves whole 16-byte groups up to T & ~7; the last T & 7 samples of a clip come by plain loads one row ahead
+// (generic-proxy stores into bytes no bulk copy ever writes, so the row loop needs no proxy fence).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int Q, bool RELU6, int DT>
+__global__ void __launch_bounds__(kDwWarps * 32, 4)
+dw_bulk_kernel(const unsigned short* __restrict__ x, long long x_pitch, const unsigned short* __restrict__ w,
+               const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
+               long long y_pitch, int B, int C, int T, int k) {
+  __shared__ __align__(128) unsigned short xs_all[kDwWarps][2][kDwRow];
+  __shared__ __align__(16) unsigned short ws_all[kDwWarps][16 * Q + 16];
+  __shared__ __align__(8) uint64_t bars[kDwWarps][2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * kDwWarps + warp;
+  const int b0 = blockIdx.z * kDwRowsPerWarp;
+  const int nb = min(kDwRowsPerWarp, B - b0);
+  const int tc0 = blockIdx.x * kDwChunk;
+  const int p = (k - 1) >> 1;
+  const int pl8 = (p + kDwPad) & ~kDwPad;   // the staged row starts at x[tc0 - pl8], a multiple of 16 samples
+  const int e = pl8 - p;
+  const int e1 = e & 1;           // folded into the zero-extended filter
+  const int s = e - e1;           // tiles start s outputs before tc0
+  const int tcA = tc0 - pl8;
+  unsigned short* ws = ws_all[warp];
+  const unsigned short* xbase = x + static_cast<long long>(c) * x_pitch;
+  const long long xbstride = static_cast<long long>(C) * x_pitch;
+
+  const int len = min(kDwChunk, T - tc0);            // outputs this CTA owns: [tc0, tc0 + len)
+  const int n_dt = (len + s + 255) / 256;            // double tiles
+  const int need = 16 * (16 * n_dt + Q - 1);         // staged samples the tiles read
+  const int T8 = T & ~7;                             // rows are copied in whole 16-byte groups
+  const int cs = max(tcA, 0), ce = max(min(tcA + need, T8), cs);
+  const uint32_t bytes = uint32_t(ce - cs) * 2u;
+  const int dst_off = cs - tcA;
+  pdl_trigger();
+
+  // zero both buffers once (halo left of the clip, everything right of the copied span), barriers
+  for (int i = lane; i < 2 * kDwRow / 8; i += 32)
+    reinterpret_cast<uint4*>(xs_all[warp][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (lane == 0) {
+    mbar_init(&bars[warp][0], 1);
+    mbar_init(&bars[warp][1], 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async();     // the zeros (generic proxy) are ordered before the bulk copies (async proxy) into the same rows
+  __syncwarp();
+  pdl_wait();              // (x is the previous kernel's output)
+  // the clip's last T & 7 samples (staged index tail0 + lane), when the tiles read them
+  const int tail0 = T8 - tcA;
+  const bool has_tail = lane < (T & 7) && tail0 >= 0 && tail0 + lane < need;
+  if (lane == 0 && bytes > 0) {
+    mbar_expect_tx(&bars[warp][0], bytes);
+    bulk_load(xs_all[warp][0] + dst_off, xbase + b0 * xbstride + cs, bytes, &bars[warp][0]);
+  }
+  if (has_tail) xs_all[warp][0][tail0 + lane] = xbase[b0 * xbstride + T8 + lane];
+
+  // zero-extended filter: ws[16 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
+  for (int i = lane; i < 16 * Q + 16; i += 32) {
+    const int j = i - 16 - e1;
+    ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : static_cast<unsigned short>(0);
+  }
+  __syncwarp();
+  const int g = lane >> 2, tg = lane & 3;
+  uint32_t af[Q][4];
+  {
+    const unsigned short* wsu = ws;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int i0 = 16 + 16 * q + 4 * tg - g;   // wz[16q + kk - m] at m = g, kk = 4 tg
+      af[q][0] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);          // (m = g    , kk = 4tg, 4tg+1)
+      af[q][1] = uint32_t(wsu[i0 - 8]) | (uint32_t(wsu[i0 - 7]) << 16);      // (m = g + 8, kk = 4tg, 4tg+1)
+      af[q][2] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);      // (m = g    , kk = 4tg+2, 4tg+3)
+      af[q][3] = uint32_t(wsu[i0 - 6]) | (uint32_t(wsu[i0 - 5]) << 16);      // (m = g + 8, kk = 4tg+2, 4tg+3)
+    }
+  }
+  const float sc = scale ? scale[c] : 1.0f;
+  const float sh = shift[c];
+  const bool even = (g & 1) == 0;
+  // after the pair exchange this lane stores outputs (t, t+1) and (t+16, t+17) of an accumulator, t relative to tc0:
+  const int pos0 = 32 * tg + (even ? g : g + 7) - s;
+
+  for (int r = 0; r < nb; ++r) {
+    unsigned short* xs = xs_all[warp][r & 1];
+    unsigned short tail_next = 0;
+    if (r + 1 < nb) {   // the other buffer was last read in iteration r - 1, which ended with __syncwarp
+      if (lane == 0 && bytes > 0) {
+        mbar_expect_tx(&bars[warp][(r + 1) & 1], bytes);
+        bulk_load(xs_all[warp][(r + 1) & 1] + dst_off, xbase + (b0 + r + 1) * xbstride + cs, bytes, &bars[warp][(r + 1) & 1]);
+      }
+      if (has_tail) tail_next = xbase[(b0 + r + 1) * xbstride + T8 + lane];   // stored after this row's tiles
+    }
+    if (bytes > 0) {
+      const uint32_t parity = (r >> 1) & 1;
+      int spins = 0;
+      while (!mbar_try_wait(&bars[warp][r & 1], parity))
+        if (++spins > (1 << 28)) __trap();   // a protocol bug must fail the launch, not hang the GPU
+    }
+    __syncwarp();
+    const uint2* x2 = reinterpret_cast<const uint2*>(xs) + lane;
+    unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + tc0 + pos0;
+    int pos = pos0;
+    auto finish = [&](float (&acc)[4], unsigned short* yq, int posq) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
+      // acc = out[tau + g + 32 tg + {0, 16}], out[tau + g + 8 + 32 tg + {0, 16}]; trade with lane g^1 so that even
+      // g holds (g, g+1) of the first pair of rows and odd g holds (g-1+8, g+8) of the second
+      const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
+      const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
+      const float lo0 = even ? acc[0] : r0, hi0 = even ? r0 : acc[2];
+      const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
+      uint32_t o0, o1;
+      if (RELU6) {
+        o0 = pack2_relu6<DT>(lo0, hi0);
+        o1 = pack2_relu6<DT>(lo1, hi1);
+      } else {
+        o0 = pack2<DT>(lo0, hi0);
+        o1 = pack2<DT>(lo1, hi1);
+      }
+      if (posq >= 0 && posq < len) *reinterpret_cast<uint32_t*>(yq) = o0;
+      if (posq + 16 >= 0 && posq + 16 < len) *reinterpret_cast<uint32_t*>(yq + 16) = o1;
+    };
+#pragma unroll 1
+    for (int d = 0; d < n_dt; ++d) {
+      float accA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+      for (int cq = 0; cq < Q; ++cq) {
+        const uint2 fa = x2[4 * cq], fb = x2[4 * cq + 32];
+        mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
+        mma_16816<DT>(accB, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fb.x, fb.y);
+      }
+      finish(accA, yp, pos);
+      finish(accB, yp + 128, pos + 128);
+      x2 += 64;      // sixteen blocks per double tile
+      yp += 256;
+      pos += 256;
+    }
+    if (has_tail && r + 1 < nb) xs_all[warp][(r + 1) & 1][tail0 + lane] = tail_next;
     __syncwarp();   // everyone is done reading xs before it is refilled two rows from now
   }
 }
@@ -472,6 +631,18 @@ static void launch_dw_mma_dt(const void* x, int64_t x_pitch, const void* w, cons
   auto wp = static_cast<const unsigned short*>(w);
   auto yp = static_cast<unsigned short*>(y);
   const long long xpl = x_pitch, ypl = y_pitch;
+  // Same-box A/B (tools/dw_time.py, B = 256, T = 751): the bulk-staged kernel wins where staging is a large share of the
+  // row's shared-memory traffic -- k = 19/27 155/146 -> 131-137 us, k = 35 152 -> 140, k = 51 156 -> 152, k = 59 303 -> 295 --
+  // and loses where its 2 Q fragment loads (3 wavefronts each unless 128-byte aligned) dominate: k = 67/75 314 -> 324,
+  // k = 83 339 -> 348.  V100_DW_BULK: 0 = never, 2 = always (A/B runs).
+  static const int bulk = getenv("V100_DW_BULK") ? atoi(getenv("V100_DW_BULK")) : 1;
+  if (bulk == 2 || (bulk == 1 && Q <= 5)) {
+    if (act == V100_ACT_RELU6)
+      launch_pdl(dw_bulk_kernel<Q, true, DT>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T, k);
+    else
+      launch_pdl(dw_bulk_kernel<Q, false, DT>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T, k);
+    return;
+  }
   if (act == V100_ACT_RELU6)
     launch_pdl(dw_mma_kernel<Q, true, DT>, grid, dim3(kDwWarps * 32), 0, stream, xp, xpl, wp, scale, shift, yp, ypl, B, C, T, k);
   else
