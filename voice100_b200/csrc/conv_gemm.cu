@@ -69,6 +69,26 @@ struct GemmParams {
   const unsigned short* w_raw;  // WRES: the row-major [C_out][C_in] weights themselves
 };
 
+// Walks this CTA's tiles (tile, tile + step, ...) keeping tile = (b * t_tiles + t) * m_tiles + m decomposed, so the
+// per-tile divisions (two in the producer, three per epilogue chunk: ~50 SASS instructions each time) are done once.
+struct TileWalk {
+  int m, t, b;      // current tile
+  int sm, st, sb;   // the step in the mixed radix (m_tiles, t_tiles)
+  __device__ __forceinline__ void init(int tile, int step, int m_tiles, int t_tiles) {
+    m = tile % m_tiles; int r = tile / m_tiles; t = r % t_tiles; b = r / t_tiles;
+    sm = step % m_tiles; r = step / m_tiles; st = r % t_tiles; sb = r / t_tiles;
+  }
+  __device__ __forceinline__ void next(int m_tiles, int t_tiles) {
+    m += sm;
+    int c = m >= m_tiles ? 1 : 0;
+    m -= c ? m_tiles : 0;
+    t += st + c;
+    c = t >= t_tiles ? 1 : 0;
+    t -= c ? t_tiles : 0;
+    b += sb + c;
+  }
+};
+
 // epilogue variant bits (compile time: the generic epilogue was ~2000 SASS instructions of run-time branches and the
 // epilogue warps spent 28 % of their samples on instruction fetch)
 enum { EPI_RELU6 = 1, EPI_RES = 2, EPI_F16 = 4 };
@@ -186,12 +206,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        const int m_tile = tile % p.m_tiles;
-        const int r = tile / p.m_tiles;
-        const int t_tile = r % p.t_tiles;
-        const int b = r / p.t_tiles;
-        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM;
+      TileWalk tw;
+      tw.init(tile0, tile_step, p.m_tiles, p.t_tiles);
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, tw.next(p.m_tiles, p.t_tiles)) {
+        const int t_tile = tw.t, b = tw.b;
+        const int m0 = (tw.m * CG + int(cta_rank)) * kBlockM;
         for (int tap = 0; tap < p.n_taps; ++tap) {
           const int t_in0 = t_tile * BLOCK_N + int(cta_rank) * Cfg::kBCols + p.tap_col[tap];
           const int xrow0 = p.tap_xrow[tap];
@@ -306,29 +325,31 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
       const int h = g;                                   // which half of the tile's chunks
       uint8_t* stg = staging + (warp - 4) * 2 * kWarpChunkBytes;
       uint64_t* rbar = res_bar + (warp - 4) * 2;
-      const uint32_t swz = uint32_t(lane & 7);
-      uint8_t* my_row = stg + lane * 128;
+      // this lane's staged row (128 bytes) with the 128B-swizzle term folded in: 16-byte piece k16 lives at row ^ (k16 << 4)
+      const uint32_t row_s = smem_u32(stg) + uint32_t(lane) * 128u + (uint32_t(lane & 7) << 4);
       const uint32_t tmem_empty_leader = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
 
       // one elected lane of the (converged) warp issues every TMA operation of this warp; bulk async-groups are
       // per thread, so the same lane also commits and waits
       const bool issuer = elect_one();
+      TileWalk tw;
+      tw.init(tile0, tile_step, p.m_tiles, p.t_tiles);
       if (kRes && issuer && tile0 < p.num_tiles) {
-        const int r = tile0 / p.m_tiles;
         mbar_expect_tx(&rbar[0], kWarpChunkBytes);
-        tma_load_3d(stg, &tm_res, &rbar[0], (r % p.t_tiles) * Cfg::kOutCols + h * 64,
-                    ((tile0 % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, r / p.t_tiles);
+        tma_load_3d(stg, &tm_res, &rbar[0], tw.t * Cfg::kOutCols + h * 64,
+                    (tw.m * CG + int(cta_rank)) * kBlockM + q * 32, tw.b);
       }
       // per-channel BN scalars of a tile; loaded one tile ahead so their L2 latency is off the critical
       // path (ncu: the wait for these two loads was 16 % of the kernel's stall samples on the expand layers)
-      auto load_scalars = [&](int tile, float& sc_o, float& sh_o) {
-        const int ch_t = ((tile % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32 + lane;
-        const bool live = tile < p.num_tiles && ch_t < p.C_out;
+      auto load_scalars = [&](bool in_range, int m_tile, float& sc_o, float& sh_o) {
+        const int ch_t = (m_tile * CG + int(cta_rank)) * kBlockM + q * 32 + lane;
+        const bool live = in_range && ch_t < p.C_out;
         sc_o = (live && p.scale != nullptr) ? __ldg(p.scale + ch_t) : 1.0f;
         sh_o = live ? __ldg(p.shift + ch_t) : 0.0f;
       };
-      // eight accumulator columns -> one 16-byte piece of this lane's staged row
-      auto emit8 = [&](const float (&a)[8], uint4* dst) {
+      // eight accumulator columns -> one 16-byte piece of this lane's staged row (shared-space accesses: the generic
+      // form cost a 64-bit address and an address-space check per store)
+      auto emit8 = [&](const float (&a)[8], uint32_t dst) {
         float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = a[e];
@@ -346,7 +367,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = fminf(fmaxf(o[e], 0.0f), 6.0f);
           }
-          const uint4 rr = *dst;
+          uint4 rr;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w) : "r"(dst) : "memory");
           o[0] += unpack_lo<DT>(rr.x); o[1] += unpack_hi<DT>(rr.x);
           o[2] += unpack_lo<DT>(rr.y); o[3] += unpack_hi<DT>(rr.y);
           o[4] += unpack_lo<DT>(rr.z); o[5] += unpack_hi<DT>(rr.z);
@@ -354,21 +376,19 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           w.x = pack2<DT>(o[0], o[1]); w.y = pack2<DT>(o[2], o[3]);
           w.z = pack2<DT>(o[4], o[5]); w.w = pack2<DT>(o[6], o[7]);
         }
-        *dst = w;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
       };
       float sc, sh;
-      load_scalars(tile0, sc, sh);
+      load_scalars(tile0 < p.num_tiles, tw.m, sc, sh);
       int iter = 0;
       uint32_t n = 0;  // chunk sequence number of this warp
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++iter) {
-        const int m_tile = tile % p.m_tiles;
-        const int r = tile / p.m_tiles;
-        const int t_tile = r % p.t_tiles;
-        const int b = r / p.t_tiles;
+        const int t_tile = tw.t, b = tw.b;
         const int accbuf = iter & 1;
-        const int m0 = (m_tile * CG + int(cta_rank)) * kBlockM + q * 32;
+        const int m0 = (tw.m * CG + int(cta_rank)) * kBlockM + q * 32;
+        tw.next(p.m_tiles, p.t_tiles);               // tw now describes the NEXT tile of this CTA
         float sc_next, sh_next;
-        load_scalars(tile + tile_step, sc_next, sh_next);
+        load_scalars(tile + tile_step < p.num_tiles, tw.m, sc_next, sh_next);
         mbar_wait(&tmem_full[accbuf], (iter >> 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -377,7 +397,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
           const int buf = n & 1;
           uint32_t v0[32], v1[32];
           const uint32_t col0 = accbuf * (N_ACC * BLOCK_N);
-          uint8_t* rowp = my_row + buf * kWarpChunkBytes;
+          const uint32_t rowp = row_s + uint32_t(buf) * kWarpChunkBytes;
           auto release_acc = [&]() {
             if (i == CPG - 1) {  // this warp is done reading the accumulator buffer
               tc_fence_before();
@@ -402,7 +422,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
               float a[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) a[e] = fmaf(__uint_as_float(v0[k16 * 8 + e]), sc, sh);
-              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
+              emit8(a, rowp ^ (uint32_t(k16) << 4));
             }
             tmem_ld_wait();
             tmem_ld_fence(v1);
@@ -412,7 +432,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
               float a[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) a[e] = fmaf(__uint_as_float(v1[(k16 - 4) * 8 + e]), sc, sh);
-              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
+              emit8(a, rowp ^ (uint32_t(k16) << 4));
             }
           } else {
             tmem_ld32(lane_addr + col0 + c * 32, v0);            // even output phase
@@ -428,7 +448,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
                 const int j = k16 * 4 + (e >> 1);
                 a[e] = fmaf(__uint_as_float((e & 1) ? v1[j] : v0[j]), sc, sh);
               }
-              emit8(a, reinterpret_cast<uint4*>(rowp + ((uint32_t(k16) ^ swz) << 4)));
+              emit8(a, rowp ^ (uint32_t(k16) << 4));
             }
           }
           fence_proxy_async();
@@ -438,14 +458,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& tm_w, const CU
             tma_store_commit();
             tma_store_wait_read<1>();  // every store but the newest has finished reading smem: buf^1 is free
             if constexpr (kRes) {
-              int ntile = tile, nc = c + 2;
-              if (i == CPG - 1) { ntile = tile + tile_step; nc = h; }
-              if (ntile < p.num_tiles) {
-                const int nr = ntile / p.m_tiles;
+              if (i < CPG - 1) {                      // next chunk of this tile
                 mbar_expect_tx(&rbar[buf ^ 1], kWarpChunkBytes);
                 tma_load_3d(stg + (buf ^ 1) * kWarpChunkBytes, &tm_res, &rbar[buf ^ 1],
-                            (nr % p.t_tiles) * Cfg::kOutCols + nc * 64,
-                            ((ntile % p.m_tiles) * CG + int(cta_rank)) * kBlockM + q * 32, nr / p.t_tiles);
+                            t_tile * Cfg::kOutCols + (c + 2) * 64, m0, b);
+              } else if (tile + tile_step < p.num_tiles) {   // first chunk of the next tile (tw already points at it)
+                mbar_expect_tx(&rbar[buf ^ 1], kWarpChunkBytes);
+                tma_load_3d(stg + (buf ^ 1) * kWarpChunkBytes, &tm_res, &rbar[buf ^ 1],
+                            tw.t * Cfg::kOutCols + h * 64, (tw.m * CG + int(cta_rank)) * kBlockM + q * 32, tw.b);
               }
             }
           }
