@@ -622,6 +622,8 @@ static int launch_gemm_pair_e(const CUtensorMap& tw, const CUtensorMap& tx, cons
     configured_dev = dev;
   }
   int pairs = num_sms() / 2;
+  static const int cap = getenv("V100_GEMM_PAIRS") ? atoi(getenv("V100_GEMM_PAIRS")) : 0;   // experiments: fewer SMs
+  if (cap > 0 && cap < pairs) pairs = cap;
   if (p.num_tiles < pairs) pairs = p.num_tiles;
   V100_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tw, tx, ty, tr, p));
   return 0;
