@@ -38,6 +38,24 @@ def test_library_loads_and_exports_header_symbols():
     assert _lib.lib().v100_abi_version() == _lib.ABI_VERSION == 6
 
 
+def test_plain_c_consumer_compiles_links_and_fails_loudly(tmp_path):
+    """include/v100.h is a C header: a C99 translation unit (what a cgo / JNI / FFI binding compiles) must build against it
+    with no CUDA or C++ headers, link to libv100.so, see the header's ABI version, and get an ERROR (not a host fallback)
+    from a compute entry point on a box without a GPU."""
+    from voice100_b200 import build
+    build.build()
+    exe = str(tmp_path / "consumer")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "consumer.c"), "-o", exe, "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "conv1x1(NULL...) -> -1" in r.stdout, r.stdout
+
+
 def test_ctypes_table_matches_header():
     funcs = header_functions()
     for name, argtypes in _lib.SIGNATURES.items():
