@@ -163,6 +163,39 @@ def test_dwconv_mma_matches_torch(k, T, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_bulk_staging_edges(dtype):
+    """dw_bulk_kernel (filters of up to 59 taps): the row is staged by ONE cp.async.bulk + mbarrier per row.  Covered here:
+    every clip-length residue mod 8 (the bulk copy moves whole 16-byte groups, the last T & 7 samples come by plain loads
+    one row ahead), clips shorter than one group (no copy at all), rows of several 1024-output chunks with a partial last
+    one, batches that are not a multiple of the 8 rows a warp walks (both buffers and both barrier phases reused), garbage
+    in the pitch padding, and 300 repeats that must be bit-identical (the mbarrier protocol is not visible to racecheck)."""
+    shapes = [(3, 16, 1027, 35), (11, 8, 2049, 59), (2, 8, 5, 19), (2, 8, 1, 5), (9, 24, 3001, 27), (2, 16, 1024, 51),
+              (17, 8, 1029, 11), (2, 16, 1030, 51), (2, 8, 9, 59), (5, 8, 756, 19), (3, 8, 748, 43)]
+    for B, C, T, k in shapes:
+        x = rnd(B, C, T, seed=T + k)
+        w = rnd(C, k, seed=k, scale=1.0 / math.sqrt(k)).to(dtype)
+        scale, shift = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+        xn = ncw(x, dtype)
+        xn.data[:, :, T:] = float("nan")             # pitch padding is never data: it must not leak into the outputs
+        ref = F.conv1d(xn.valid().float(), w.float()[:, None, :], padding=(k - 1) // 2, groups=C)
+        ref = (ref * scale[None, :, None] + shift[None, :, None]).clamp(0, 6)
+        y = K.dwconv(xn, w, scale, shift, k, 1, K.ACT_RELU6)
+        torch.cuda.synchronize()
+        got = y.valid().float()
+        assert torch.isfinite(got).all(), (B, C, T, k)
+        assert rel_err(got, ref) < OUT_TOL[dtype], (B, C, T, k, rel_err(got, ref))
+    B, C, T, k = 11, 8, 2049, 59
+    xn = ncw(rnd(B, C, T, seed=5), dtype)
+    w = rnd(C, k, seed=6, scale=0.2).to(dtype)
+    shift = torch.zeros(C, device=DEV)
+    first = K.dwconv(xn, w, None, shift, k, 1, K.ACT_NONE)
+    n_bad = torch.zeros((), device=DEV, dtype=torch.int64)
+    for _ in range(300):
+        n_bad += (K.dwconv(xn, w, None, shift, k, 1, K.ACT_NONE).valid() != first.valid()).sum()
+    assert int(n_bad) == 0
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_dwconv_long_rows_and_stride2(dtype):
     B, C, T, k = 2, 16, 3001, 83                       # 60 s clip: three 1024-output chunks per row
     x = rnd(B, C, T, seed=9)

@@ -87,6 +87,15 @@ for dtype in (torch.bfloat16, torch.float16):
     for simt in (False, True):
         K.dwconv(x, w, None, torch.zeros(72, device=dev), 83, 1, 1, simt=simt)
     K.dwconv(x, w[:, :11].contiguous(), None, torch.zeros(72, device=dev), 11, 2, 1)
+    # weights-resident pair GEMM (needs >= 4 units per pair slot: 40 utterances x 2 time tiles, 4 channel blocks), with and
+    # without a residual; bulk-staged depthwise at odd lengths (T & 7 != 0, several chunks, fewer than 8 samples)
+    xw = K.empty_ncw(40, 256, 140, dev, dtype); xw.data.normal_()
+    Ww = torch.randn(1024, 256, device=dev).to(dtype) / 16
+    yw = K.conv1x1(xw, Ww, torch.rand(1024, device=dev), torch.zeros(1024, device=dev), 1)
+    K.conv1x1(yw, torch.randn(256, 1024, device=dev).to(dtype) / 32, None, torch.zeros(256, device=dev), 0, xw)
+    for (Tb, kb) in ((1027, 35), (5, 19), (2049, 59)):
+        xb = K.empty_ncw(3, 16, Tb, dev, dtype); xb.data.normal_()
+        K.dwconv(xb, torch.randn(16, kb, device=dev).to(dtype), None, torch.zeros(16, device=dev), kb, 1, 1)
     # the fused expand + depthwise kernel (opt-in path): ragged T, K not a multiple of 64, more units than CTA pairs
     for (Bf, Ci, Hf, Tf, kf) in ((2, 72, 512, 333, 67), (3, 64, 256, 257, 11), (90, 64, 256, 70, 33)):
         xf = K.empty_ncw(Bf, Ci, Tf, dev, dtype); xf.data.normal_()
