@@ -18,10 +18,11 @@
 // WRES (weights resident): for C_in <= 512 a CTA pair keeps its 256 x C_in weight block in TENSOR MEMORY for the whole
 // kernel (tcgen05.mma with the A operand from TMEM, 16-bit elements packed two per column) and works only on tiles of
 // that channel block; the ring then carries activations only.  ncu on the plain pair kernel (profiles/r02_gemm_stalls.md):
-// the MMA warp spends 55 % of its time waiting for operand bytes while the producer waits for free slots -- the tile
-// needs 64 B/clk/SM of operands (32 KB per 512 clk k-block) and L2 delivers ~10 TB/s chip-wide.  Without the weights
-// a k-block needs half the bytes, so the same ring covers twice the MMA time.  Tiles are 256 channels x 128 steps
-// (two 128-column accumulators + C_in/2 weight columns = 512 TMEM columns at C_in = 512).
+// the MMA warp spends 55 % of its time waiting for operand bytes while the producer waits for free slots -- a 256 x 256
+// tile needs 64 B/clk/SM of operands (32 KB per 512 clk k-block) and gets 52-58.  Without the weights a k-block moves
+// half the bytes through L2, the TMA unit and shared memory, so the same ring covers twice the MMA time (ncu: -23 %
+// cycles, tensor pipe 91 % busy; the wall-clock gain is 10 % because the full chip is then held back by the power limit).
+// Tiles are 256 channels x 128 steps (two 128-column accumulators + C_in/2 weight columns = 512 TMEM columns at C_in = 512).
 //
 // Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM
 // allocator, warp 3 = idle, warps 4..11 = epilogue (two groups of four warps; warp%4 selects the TMEM
