@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 6
+#define V100_ABI_VERSION 7
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
@@ -218,6 +218,15 @@ int v100_world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, 
 
 /* fp32 NCW [B][C][pitch] -> fp32 [B][T][C] (align head output [B][L][2]). */
 int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, void* stream);
+
+/*
+ * Feature masking of a padded batch: out[b][t][c] = log(max(exp(audio[b][t][c]) * (t < audio_len[b]), log_offset)),
+ * i.e. frames at or past an utterance's own length become log(log_offset) = BLANK_AUDIO and valid frames are floored
+ * there.  audio / out fp32 [B][T][C] contiguous (out may alias audio), audio_len int32 [B].
+ * Replaces BatchSpectrogramAugumentation.maskaudio (voice100/audio.py:106-108).
+ */
+int v100_maskaudio(const float* audio, const int32_t* audio_len, float* out, int B, int T, int C, float log_offset,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * v2 models: ConvLayerBlock / ConvTransposeLayerBlock (voice100/models/_layers_v2.py:29-88) and the

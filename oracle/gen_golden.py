@@ -308,6 +308,23 @@ def gen_align_edges(seed=91):
     print("align_edges", len(cases), "errors", sum(isinstance(c["out"], str) for c in cases))
 
 
+def gen_maskaudio(seed=101):
+    """BatchSpectrogramAugumentation.maskaudio (voice100/audio.py:106-108) on a ragged log-mel-like batch: values over the
+    whole range the front end produces (BLANK_AUDIO .. +12), lengths 0 / 1 / interior / full."""
+    from voice100.audio import BatchSpectrogramAugumentation
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B, T, C = 5, 37, 64
+    audio = rng.uniform(BLANK_AUDIO - 1.0, 12.0, size=(B, T, C)).astype(np.float32)
+    audio[0, :3] = BLANK_AUDIO
+    audio_len = np.asarray([37, 0, 1, 20, 36], dtype=np.int32)
+    aug = BatchSpectrogramAugumentation()
+    with torch.no_grad():
+        out = aug.maskaudio(torch.from_numpy(audio), torch.from_numpy(audio_len))
+    np.savez_compressed(os.path.join(OUT, "maskaudio.npz"), cfg=np.asarray([B, T, C, seed]), audio_len=audio_len,
+                        out=out.numpy())
+    print("maskaudio", out.shape, float(out.min()), float(out.max()))
+
+
 def viterbi_case(T, L, seed):
     from voice100_b200.synth import viterbi_inputs
     return viterbi_inputs(T, L, 29, seed)
@@ -331,3 +348,4 @@ if __name__ == "__main__":
     gen_tts_v1_mcep()
     gen_tokenizer()
     gen_align_edges()
+    gen_maskaudio()

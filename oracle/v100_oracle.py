@@ -126,6 +126,13 @@ def logmel_batch(waveform: torch.Tensor, lengths: Sequence[int], **kw) -> Tuple[
     return audio, audio_len
 
 
+def maskaudio(audio: torch.Tensor, audio_len: torch.Tensor, log_offset=LOG_OFFSET) -> torch.Tensor:
+    """voice100/audio.py:106-108 (BatchSpectrogramAugumentation.maskaudio): frames at or past an utterance's own length
+    become log(log_offset) = BLANK_AUDIO; valid frames are floored there.  audio fp32 [B, T, C], audio_len [B]."""
+    mask = (torch.arange(audio.shape[1])[None, :, None] < audio_len[:, None, None]).float()
+    return torch.log(torch.clamp(torch.exp(audio) * mask, min=log_offset))
+
+
 def logmel_numpy(waveform: np.ndarray, sample_rate=16000, n_fft=512, win_length=400, hop_length=160,
                  n_mels=MELSPEC_DIM, log_offset=LOG_OFFSET) -> np.ndarray:
     """Independent numpy restatement of the same front end for ONE clip -> [T, n_mels] fp32.

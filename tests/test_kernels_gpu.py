@@ -541,6 +541,33 @@ def test_ctc_best_path_matches_oracle_bit_exact():
     assert torch.isnan(s4[1]) and (h4[1] == -1).all() and float(s4[0]) == float(score[0]) and torch.equal(h4[0], hist[0])
 
 
+def test_maskaudio_matches_reference_golden_and_oracle():
+    """v100_maskaudio vs the reference method's own output (tests/golden/maskaudio.npz) and vs the oracle on a larger ragged
+    batch.  Tolerance 2e-6 absolute on valid frames (expf -> logf round trip, values in [-14.8, 12]); padded frames and
+    floored values are BLANK_AUDIO exactly."""
+    import voice100_b200 as v
+    from helpers import golden
+    g = golden("maskaudio")
+    B, T, C, seed = [int(x) for x in g["cfg"]]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    audio = rng.uniform(v.BLANK_AUDIO - 1.0, 12.0, size=(B, T, C)).astype(np.float32)
+    audio[0, :3] = v.BLANK_AUDIO
+    lens = torch.from_numpy(g["audio_len"])
+    out = v.maskaudio(torch.from_numpy(audio).to(DEV), lens.to(DEV)).cpu().numpy()
+    assert np.abs(out - g["out"]).max() < 2e-6
+    for b, n in enumerate(g["audio_len"]):
+        assert np.all(out[b, int(n):] == np.float32(v.BLANK_AUDIO))
+    B, T = 67, 1501
+    a = torch.from_numpy(rng.uniform(-16.0, 12.0, size=(B, T, 64)).astype(np.float32))
+    ln = torch.from_numpy(rng.integers(0, T + 1, size=B).astype(np.int64))     # host lengths, int64: converted by the wrapper
+    got = v.maskaudio(a.to(DEV), ln).cpu()
+    ref = orc.maskaudio(a, ln)
+    assert float((got - ref).abs().max()) < 2e-6
+    assert torch.equal(got == v.BLANK_AUDIO, ref == v.BLANK_AUDIO)
+    with pytest.raises(v.V100Error):
+        v.maskaudio(a[0].to(DEV), ln[:1])                                      # not [B, T, C]
+
+
 def test_errors_are_loud():
     from voice100_b200 import V100Error
     x = K.empty_ncw(1, 60, 16, DEV)     # C_in not a multiple of 8

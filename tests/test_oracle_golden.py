@@ -284,3 +284,17 @@ def test_mc2sp_matches_reference():
     np.testing.assert_allclose(mcep.numpy(), g["mcep"], rtol=0, atol=2e-4)
     logspc = mcep.double().numpy() @ orc.mc2sp_matrix(512, 24, 0.410)
     np.testing.assert_allclose(logspc, g["logspc"], rtol=0, atol=5e-3)  # |logspc| ~ 1e2: fp32 matmul round-off
+
+
+def test_maskaudio_matches_reference_golden():
+    """oracle.maskaudio restates BatchSpectrogramAugumentation.maskaudio (voice100/audio.py:106-108); the fixture is the
+    reference method's own output (oracle/gen_golden.py:gen_maskaudio)."""
+    g = golden("maskaudio")
+    B, T, C, seed = [int(x) for x in g["cfg"]]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    audio = rng.uniform(orc.BLANK_AUDIO - 1.0, 12.0, size=(B, T, C)).astype(np.float32)
+    audio[0, :3] = orc.BLANK_AUDIO
+    out = orc.maskaudio(torch.from_numpy(audio), torch.from_numpy(g["audio_len"]))
+    assert np.array_equal(out.numpy(), g["out"])                      # same ATen ops in the same order: bit-identical
+    for b, n in enumerate(g["audio_len"]):
+        assert np.all(g["out"][b, int(n):] == np.float32(orc.BLANK_AUDIO))

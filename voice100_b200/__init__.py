@@ -15,6 +15,7 @@ from .tts import TextToAlignTextModel, AlignTextToAudioModel, VoiceDecoder, WORL
 from .text import BasicTokenizer, CharTokenizer  # noqa: F401
 from .checkpoint import load_checkpoint  # noqa: F401
 from .align import ctc_best_path_batch  # noqa: F401
+from .audio import maskaudio  # noqa: F401
 from .v2 import (AudioToAlignText, TextToAlignText, AlignTextToAudio, AsrV2Pipeline,  # noqa: F401
                  ConvLayerBlock, ConvTransposeLayerBlock, get_conv_layers, align_batch_v2)
 from .vocoder import AlignTextToAudioPredict, create_mc2sp_matrix  # noqa: F401

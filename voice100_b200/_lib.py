@@ -32,6 +32,7 @@ SIGNATURES = {
     "v100_ctc_best_path": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "v100_world_finalize": [_p, _l, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "v100_ncw_f32_to_ntc": [_p, _l, _p, _i, _i, _i, _p],
+    "v100_maskaudio": [_p, _p, _p, _i, _i, _i, _f, _p],
     "v100_conv1d": [_p, _l, _p, _p, _p, _p, _l, _i, _i, _i, _i, _i, _i, _i, _i, _p],
     "v100_conv1d_tm": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "v100_layernorm_gelu": [_p, _l, _p, _p, _f, _p, _l, _i, _i, _i, _i, _p],
@@ -40,7 +41,7 @@ SIGNATURES = {
     "v100_lstm_layer": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 _lib = None
 
 

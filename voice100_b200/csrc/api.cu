@@ -188,6 +188,11 @@ int v100_ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, 
   return ncw_f32_to_ntc(y_ncw, y_pitch, out, B, C, T, STREAM(stream));
 }
 
+int v100_maskaudio(const float* audio, const int32_t* audio_len, float* out, int B, int T, int C, float log_offset,
+                   void* stream) {
+  return maskaudio(audio, audio_len, out, B, T, C, log_offset, STREAM(stream));
+}
+
 int v100_conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,
                 int64_t y_pitch, int B, int C_in, int C_out, int T_in, int k, int stride, int pad, int dtype,
                 void* stream) {

@@ -81,6 +81,8 @@ int world_finalize(const float* y_ncw, int64_t y_pitch, const float* mean, const
                    float* logspc, float* hascodeap, float* codeap, int B, int T, int logspc_size, int codeap_size,
                    int layout, int unnormalize, cudaStream_t stream);
 int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C, int T, cudaStream_t stream);
+int maskaudio(const float* audio, const int32_t* audio_len, float* out, int B, int T, int C, float log_offset,
+              cudaStream_t stream);
 
 // v2 models (seq.cu)
 int conv1d(const void* x, int64_t x_pitch, const void* Wp, const float* bias, void* workspace, void* y,

@@ -353,6 +353,37 @@ int ncw_f32_to_ntc(const float* y_ncw, int64_t y_pitch, float* out, int B, int C
   return 0;
 }
 
+// BatchSpectrogramAugumentation.maskaudio (voice100/audio.py:106-108): log(clamp(exp(audio) * mask, min = log_offset)) with
+// mask = t < audio_len[b].  One thread per element; expf / logf (not the fast intrinsics) so that valid frames come back
+// within an ulp or two of the reference's exp -> log round trip.
+__global__ void __launch_bounds__(256)
+maskaudio_kernel(const float* __restrict__ audio, const int32_t* __restrict__ audio_len, float* __restrict__ out,
+                 long long n, int T, int C, float log_offset) {
+  pdl_trigger();
+  pdl_wait();
+  const long long tc = static_cast<long long>(T) * C;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const long long b = i / tc;
+    const int t = int((i - b * tc) / C);
+    const float m = t < __ldg(audio_len + b) ? 1.0f : 0.0f;
+    out[i] = logf(fmaxf(expf(audio[i]) * m, log_offset));
+  }
+}
+
+int maskaudio(const float* audio, const int32_t* audio_len, float* out, int B, int T, int C, float log_offset,
+              cudaStream_t stream) {
+  if (audio == nullptr || audio_len == nullptr || out == nullptr) return fail(V100_E_INVALID, "maskaudio: null pointer");
+  if (B <= 0 || T <= 0 || C <= 0) return fail(V100_E_INVALID, "maskaudio: non-positive size");
+  if (!(log_offset > 0.0f)) return fail(V100_E_INVALID, "maskaudio: log_offset must be positive");
+  const long long n = static_cast<long long>(B) * T * C;
+  long long blocks = (n + 255) / 256;
+  const long long cap = 32LL * num_sms();
+  if (blocks > cap) blocks = cap;
+  V100_CUDA(launch_pdl(maskaudio_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, audio, audio_len, out, n, T, C,
+                       log_offset));
+  return 0;
+}
+
 // WORLD head tail: split the decoder output into its parameter groups, un-normalise (WORLDNorm.unnormalize,
 // _layers_v1.py:131-138) and apply the presence gates, transposing NCW -> [B][T][.] on the way.
 //   layout 1 (AlignTextToAudioModel, tts.py:160-167,181-190):  [hasf0 | f0 | logspc(S) | codeap(A)]

@@ -304,6 +304,22 @@ def ncw_f32_to_ntc(y: Ncw) -> torch.Tensor:
     return out
 
 
+def maskaudio(audio: torch.Tensor, audio_len: torch.Tensor, log_offset: float) -> torch.Tensor:
+    """audio fp32 [B, T, C], audio_len [B] -> log(clamp(exp(audio) * (t < len), min=log_offset)) (voice100/audio.py:106-108)."""
+    if audio.dim() != 3 or audio.dtype != torch.float32:
+        raise _lib.V100Error("maskaudio: audio must be fp32 [B, T, C]")
+    audio = audio.contiguous()
+    if audio_len.is_cuda:
+        _same_device(audio, audio_len)
+    lens = audio_len.to(device=audio.device, dtype=torch.int32).contiguous()
+    if lens.shape != (audio.shape[0],):
+        raise _lib.V100Error("maskaudio: audio_len must be [B]")
+    out = torch.empty_like(audio)
+    _call(audio, "v100_maskaudio", audio.data_ptr(), lens.data_ptr(), out.data_ptr(), audio.shape[0], audio.shape[1],
+          audio.shape[2], float(log_offset))
+    return out
+
+
 # ---- v2 models: dense conv + LayerNorm/GELU, time-major layout, LSTM (include/v100.h, "v2 models") ----
 
 def conv1d(x: Ncw, Wp: torch.Tensor, bias: torch.Tensor, k: int, stride: int, pad: int) -> Ncw:
