@@ -537,13 +537,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant
   conv_gemm_body<BLOCK_N, N_ACC, OUT_MODE, STAGES, 1, EPI, false>(tm_w, tm_x, tm_y, tm_res, p);
 }
 
-// CTA-pair variant: 256 output channels x 256 time steps per cluster of two CTAs
-template <int STAGES, int EPI>
+// CTA-pair variant: 256 output channels x BLOCK_N (256, or 128 for short rows) time steps per cluster of two CTAs
+template <int BLOCK_N, int STAGES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x,
                       const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_res,
                       const GemmParams p) {
-  conv_gemm_body<256, 1, OUT_BF16, STAGES, 2, EPI, false>(tm_w, tm_x, tm_y, tm_res, p);
+  conv_gemm_body<BLOCK_N, 1, OUT_BF16, STAGES, 2, EPI, false>(tm_w, tm_x, tm_y, tm_res, p);
 }
 
 // CTA-pair variant with the pair's weight block resident in tensor memory: 256 channels x 128 steps per tile
@@ -608,13 +608,14 @@ static int launch_gemm(const CUtensorMap& tw, const CUtensorMap& tx, const CUten
 #undef V100_EPI_ARGS
 }
 
-constexpr int kPairStages = 5;
+constexpr int kPairStages = 5;      // 256-column tiles: 32 KB per stage
+constexpr int kPairStages128 = 6;   // 128-column tiles: 24 KB per stage
 
-template <int STAGES, int EPI>
+template <int BLOCK_N, int STAGES, int EPI>
 static int launch_gemm_pair_e(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty,
                               const CUtensorMap& tr, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<256, 1, OUT_BF16, STAGES, 2>;
-  auto kern = conv_gemm_pair_kernel<STAGES, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, 1, OUT_BF16, STAGES, 2>;
+  auto kern = conv_gemm_pair_kernel<BLOCK_N, STAGES, EPI>;
   static thread_local int configured_dev = -1;
   int dev = 0;
   V100_CUDA(cudaGetDevice(&dev));
@@ -631,9 +632,12 @@ static int launch_gemm_pair_e(const CUtensorMap& tw, const CUtensorMap& tx, cons
 }
 
 static int launch_gemm_pair(const CUtensorMap& tw, const CUtensorMap& tx, const CUtensorMap& ty, const CUtensorMap& tr,
-                            const GemmParams& p, cudaStream_t stream) {
+                            const GemmParams& p, int block_n, cudaStream_t stream) {
 #define V100_EPI_ARGS tw, tx, ty, tr, p, stream
-  V100_EPI_DISPATCH(launch_gemm_pair_e, kPairStages)
+  if (block_n == 128) {
+    V100_EPI_DISPATCH(launch_gemm_pair_e, 128, kPairStages128)
+  }
+  V100_EPI_DISPATCH(launch_gemm_pair_e, 256, kPairStages)
 #undef V100_EPI_ARGS
 }
 
@@ -731,10 +735,10 @@ int conv1x1(const void* x, int64_t x_pitch, const void* W, const float* scale, c
     p.num_tiles = p.m_tiles * p.t_tiles * B;
     return launch_gemm_wres(txw, ty, tr, p, pairs, stream);
   }
-  if (bn == 256 && C_out % (2 * kBlockM) == 0 && force_cg != 1) {
+  if (C_out % (2 * kBlockM) == 0 && force_cg != 1) {   // CTA pairs; 128-column tiles where they pad the row less
     p.m_tiles = C_out / (2 * kBlockM);
     p.num_tiles = p.m_tiles * p.t_tiles * B;
-    return launch_gemm_pair(tw, tx, ty, tr, p, stream);
+    return launch_gemm_pair(tw, tx, ty, tr, p, bn, stream);
   }
   p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
   p.num_tiles = p.m_tiles * p.t_tiles * B;
@@ -798,7 +802,7 @@ int conv1d_tm(const void* x, const void* Wp, const float* bias, void* y, int C_i
   if (bn == 256 && C_out % (2 * kBlockM) == 0) {
     p.m_tiles = C_out / (2 * kBlockM);
     p.num_tiles = p.m_tiles * p.t_tiles;
-    return launch_gemm_pair(tw, tx, ty, ty, p, stream);
+    return launch_gemm_pair(tw, tx, ty, ty, p, 256, stream);
   }
   p.m_tiles = (C_out + kBlockM - 1) / kBlockM;
   p.num_tiles = p.m_tiles * p.t_tiles;

@@ -344,14 +344,23 @@ dw_bulk_kernel(const unsigned short* __restrict__ x, long long x_pitch, const un
 #pragma unroll 1
     for (int d = 0; d < n_dt; ++d) {
       float accA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (256 * d + 128 - s < len) {
 #pragma unroll
-      for (int cq = 0; cq < Q; ++cq) {
-        const uint2 fa = x2[4 * cq], fb = x2[4 * cq + 32];
-        mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
-        mma_16816<DT>(accB, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fb.x, fb.y);
+        for (int cq = 0; cq < Q; ++cq) {
+          const uint2 fa = x2[4 * cq], fb = x2[4 * cq + 32];
+          mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
+          mma_16816<DT>(accB, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fb.x, fb.y);
+        }
+        finish(accA, yp, pos);
+        finish(accB, yp + 128, pos + 128);
+      } else {   // the row ends in the first half of this double tile (short rows: T = 100 text tokens, ...)
+#pragma unroll
+        for (int cq = 0; cq < Q; ++cq) {
+          const uint2 fa = x2[4 * cq];
+          mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
+        }
+        finish(accA, yp, pos);
       }
-      finish(accA, yp, pos);
-      finish(accB, yp + 128, pos + 128);
       x2 += 64;      // sixteen blocks per double tile
       yp += 256;
       pos += 256;
