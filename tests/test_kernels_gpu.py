@@ -403,6 +403,13 @@ def test_layout_and_head_kernels():
     table = rnd(29, 64, seed=22).to(torch.bfloat16)
     e = K.embedding_ncw(ids, table)
     assert torch.equal(e.valid(), F.embedding(ids, table).transpose(1, 2))
+    # the shared-memory gather at model shapes (8 channel blocks, ragged last group, partial channel block) and the
+    # global-memory fallback for a table too large to stage
+    for (Be, Te, Ve, Ce) in ((5, 292, 29, 512), (2, 100, 71, 24), (3, 7, 44, 72), (2, 33, 1000, 64)):
+        ids_e = torch.randint(0, Ve, (Be, Te), device=DEV)
+        for dtype in DTYPES:
+            tab_e = rnd(Ve, Ce, seed=Ve).to(dtype)
+            assert torch.equal(K.embedding_ncw(ids_e, tab_e).valid(), F.embedding(ids_e, tab_e).transpose(1, 2))
     lg = K.Ncw(torch.randn(4, 29, 104, device=DEV), 101)
     lg.data[0, 3, 7] = lg.data[0, 11, 7] = 50.0          # tie -> first maximal index
     logits, tokens = K.ctc_finalize(lg)
