@@ -170,7 +170,10 @@ def test_dwconv_bulk_staging_edges(dtype):
     one, batches that are not a multiple of the 8 rows a warp walks (both buffers and both barrier phases reused), garbage
     in the pitch padding, and 300 repeats that must be bit-identical (the mbarrier protocol is not visible to racecheck)."""
     shapes = [(3, 16, 1027, 35), (11, 8, 2049, 59), (2, 8, 5, 19), (2, 8, 1, 5), (9, 24, 3001, 27), (2, 16, 1024, 51),
-              (17, 8, 1029, 11), (2, 16, 1030, 51), (2, 8, 9, 59), (5, 8, 756, 19), (3, 8, 748, 43)]
+              (17, 8, 1029, 11), (2, 16, 1030, 51), (2, 8, 9, 59), (5, 8, 756, 19), (3, 8, 748, 43),
+              # short rows -> dw_rows_kernel (one TMA tensor load per channel and eight utterances): one and two boxes,
+              # fragments straddling the boxes, a batch that is not a multiple of eight, the longest filters
+              (256, 16, 100, 29), (11, 8, 292, 65), (9, 8, 292, 33), (3, 8, 383, 83), (13, 8, 250, 5), (2, 8, 129, 11)]
     for B, C, T, k in shapes:
         x = rnd(B, C, T, seed=T + k)
         w = rnd(C, k, seed=k, scale=1.0 / math.sqrt(k)).to(dtype)

@@ -56,12 +56,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int encode(CUtensorMap* m, CUtensorMapDataType type, const void* base, int rank, const cuuint64_t* dims,
-                  const cuuint64_t* strides, const cuuint32_t* box) {
+                  const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint32_t ones[3] = {1, 1, 1};
   CUresult r = fn(m, type, rank, const_cast<void*>(base), dims, strides, box, ones,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(V100_E_DRIVER, "cuTensorMapEncodeTiled failed (CUresult %d; rank %d dims %llu,%llu strides %llu)",
@@ -83,6 +83,16 @@ int make_tmap_3d(CUtensorMap* m, CUtensorMapDataType type, const void* base, int
   const cuuint64_t strides[2] = {cuuint64_t(stride1_bytes), cuuint64_t(stride2_bytes)};
   const cuuint32_t box[3] = {cuuint32_t(box0), cuuint32_t(box1), 1};
   return encode(m, type, base, 3, dims, strides, box);
+}
+
+// NCW activations as a (T, C, B) tensor with an UNSWIZZLED box of [box_t steps x 1 channel x box_b utterances]: the
+// staged rows of one channel for several utterances in one TMA instruction, zero-filled outside [0, T) and [0, B).
+int make_tmap_rows(CUtensorMap* m, CUtensorMapDataType type, const void* base, int64_t T, int64_t C, int64_t B,
+                   int64_t pitch_bytes, int box_t, int box_b) {
+  const cuuint64_t dims[3] = {cuuint64_t(T), cuuint64_t(C), cuuint64_t(B)};
+  const cuuint64_t strides[2] = {cuuint64_t(pitch_bytes), cuuint64_t(C) * cuuint64_t(pitch_bytes)};
+  const cuuint32_t box[3] = {cuuint32_t(box_t), 1, cuuint32_t(box_b)};
+  return encode(m, type, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace v100

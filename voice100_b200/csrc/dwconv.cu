@@ -370,6 +370,138 @@ dw_bulk_kernel(const unsigned short* __restrict__ x, long long x_pitch, const un
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// dw_rows_kernel: short rows (the TTS models: 100 text tokens, ~290 aligned frames).  A bulk copy costs the TMA unit a
+// fixed ~65 clk whatever its size, so with 200-600 byte rows dw_bulk_kernel is bound by the NUMBER of copies (120 us for a
+// 210 MB layer; eight copies in flight per warp instead of two changed nothing).  Here ONE TMA tensor load brings the
+// staged rows of a channel for all eight utterances of the warp: x seen as a (T, C, B) tensor, box = [256 steps x 1
+// channel x 8 utterances], unswizzled, out-of-bounds elements zero-filled -- which also supplies the filter halo left of
+// the clip and everything right of its end, so there is no zero-initialisation and no tail handling.  One or two boxes
+// per warp (staged span <= 512 samples); the tile arithmetic is dw_bulk_kernel's, with the fragment address split into
+// (box, block in box) because a fragment's eight blocks may straddle the two boxes.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDwBoxT = 256;     // steps per TMA box
+template <int Q, bool RELU6, int DT>
+__global__ void __launch_bounds__(kDwWarps * 32)
+dw_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const unsigned short* __restrict__ w,
+               const float* __restrict__ scale, const float* __restrict__ shift, unsigned short* __restrict__ y,
+               long long y_pitch, int B, int C, int T, int k, int n_boxes) {
+  extern __shared__ __align__(128) unsigned char rows_smem[];
+  __shared__ __align__(16) unsigned short ws_all[kDwWarps][16 * Q + 16];
+  __shared__ __align__(8) uint64_t bars[kDwWarps];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * kDwWarps + warp;
+  const int b0 = blockIdx.z * kDwRowsPerWarp;
+  const int nb = min(kDwRowsPerWarp, B - b0);
+  const int p = (k - 1) >> 1;
+  const int pl8 = (p + kDwPad) & ~kDwPad;   // the staged rows start at x[-pl8] (a multiple of 16 samples; zeros by OOB fill)
+  const int e = pl8 - p;
+  const int e1 = e & 1;           // folded into the zero-extended filter
+  const int s = e - e1;           // tiles start s outputs before 0
+  unsigned short* ws = ws_all[warp];
+  const int len = T;                                 // one chunk: the whole row
+  const int n_dt = (len + s + 255) / 256;            // double tiles
+  const uint32_t box_bytes = kDwRowsPerWarp * kDwBoxT * 2;   // 4 KB: [8 utterances][256 steps]
+  unsigned char* xs_w = rows_smem + size_t(warp) * n_boxes * box_bytes;
+  pdl_trigger();
+  if (lane == 0) {
+    mbar_init(&bars[warp], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_x);
+  }
+  __syncwarp();
+  pdl_wait();              // (x is the previous kernel's output)
+  if (lane == 0) {
+    mbar_expect_tx(&bars[warp], uint32_t(n_boxes) * box_bytes);   // out-of-bounds (zero-filled) elements count too
+    for (int j = 0; j < n_boxes; ++j)
+      tma_load_3d(xs_w + j * box_bytes, &tm_x, &bars[warp], -pl8 + j * kDwBoxT, c, b0);
+  }
+
+  // zero-extended filter: ws[16 + i] = w[i - e1] for 0 <= i - e1 < k; Toeplitz fragments stay in registers
+  for (int i = lane; i < 16 * Q + 16; i += 32) {
+    const int j = i - 16 - e1;
+    ws[i] = (j >= 0 && j < k) ? w[static_cast<long long>(c) * k + j] : static_cast<unsigned short>(0);
+  }
+  __syncwarp();
+  const int g = lane >> 2, tg = lane & 3;
+  uint32_t af[Q][4];
+  {
+    const unsigned short* wsu = ws;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int i0 = 16 + 16 * q + 4 * tg - g;   // wz[16q + kk - m] at m = g, kk = 4 tg
+      af[q][0] = uint32_t(wsu[i0]) | (uint32_t(wsu[i0 + 1]) << 16);          // (m = g    , kk = 4tg, 4tg+1)
+      af[q][1] = uint32_t(wsu[i0 - 8]) | (uint32_t(wsu[i0 - 7]) << 16);      // (m = g + 8, kk = 4tg, 4tg+1)
+      af[q][2] = uint32_t(wsu[i0 + 2]) | (uint32_t(wsu[i0 + 3]) << 16);      // (m = g    , kk = 4tg+2, 4tg+3)
+      af[q][3] = uint32_t(wsu[i0 - 6]) | (uint32_t(wsu[i0 - 5]) << 16);      // (m = g + 8, kk = 4tg+2, 4tg+3)
+    }
+  }
+  const float sc = scale ? scale[c] : 1.0f;
+  const float sh = shift[c];
+  const bool even = (g & 1) == 0;
+  // after the pair exchange this lane stores outputs (t, t+1) and (t+16, t+17) of an accumulator:
+  const int pos0 = 32 * tg + (even ? g : g + 7) - s;
+  {
+    int spins = 0;
+    while (!mbar_try_wait(&bars[warp], 0))
+      if (++spins > (1 << 28)) __trap();   // a protocol bug must fail the launch, not hang the GPU
+  }
+  __syncwarp();
+  // block `blk` of utterance r: uint2 index  (blk >> 4) * (8 rows * 64) + r * 64 + (blk & 15) * 4 + tg   (64 uint2 = 256 steps)
+  const uint2* xw = reinterpret_cast<const uint2*>(xs_w) + tg;
+  auto frag = [&](int r, int blk) -> uint2 {
+    return xw[(blk >> 4) * (kDwRowsPerWarp * 64) + r * 64 + ((blk & 15) << 2)];
+  };
+
+  for (int r = 0; r < nb; ++r) {
+    unsigned short* yp = y + (static_cast<long long>(b0 + r) * C + c) * y_pitch + pos0;
+    int pos = pos0;
+    auto finish = [&](float (&acc)[4], unsigned short* yq, int posq) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(acc[i], sc, sh);
+      const float r0 = __shfl_xor_sync(0xffffffffu, even ? acc[2] : acc[0], 4);
+      const float r1 = __shfl_xor_sync(0xffffffffu, even ? acc[3] : acc[1], 4);
+      const float lo0 = even ? acc[0] : r0, hi0 = even ? r0 : acc[2];
+      const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
+      uint32_t o0, o1;
+      if (RELU6) {
+        o0 = pack2_relu6<DT>(lo0, hi0);
+        o1 = pack2_relu6<DT>(lo1, hi1);
+      } else {
+        o0 = pack2<DT>(lo0, hi0);
+        o1 = pack2<DT>(lo1, hi1);
+      }
+      if (posq >= 0 && posq < len) *reinterpret_cast<uint32_t*>(yq) = o0;
+      if (posq + 16 >= 0 && posq + 16 < len) *reinterpret_cast<uint32_t*>(yq + 16) = o1;
+    };
+#pragma unroll 1
+    for (int d = 0; d < n_dt; ++d) {
+      float accA[4] = {0.0f, 0.0f, 0.0f, 0.0f}, accB[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const int blkA = 16 * d + g;             // this lane's first block: accumulator A column n = g
+      if (256 * d + 128 - s < len) {
+#pragma unroll
+        for (int cq = 0; cq < Q; ++cq) {
+          const uint2 fa = frag(r, blkA + cq), fb = frag(r, blkA + 8 + cq);
+          mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
+          mma_16816<DT>(accB, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fb.x, fb.y);
+        }
+        finish(accA, yp, pos);
+        finish(accB, yp + 128, pos + 128);
+      } else {   // the row ends in the first half of this double tile
+#pragma unroll
+        for (int cq = 0; cq < Q; ++cq) {
+          const uint2 fa = frag(r, blkA + cq);
+          mma_16816<DT>(accA, af[cq][0], af[cq][1], af[cq][2], af[cq][3], fa.x, fa.y);
+        }
+        finish(accA, yp, pos);
+      }
+      yp += 256;
+      pos += 256;
+    }
+  }
+}
+
 // Stride-2 depthwise conv on the same tensor-core FIR (the first encoder block, asr.py:68), as two polyphase
 // stride-1 filters:   out[o] = sum_j w[j] x[2 o + j - p]
 //                            = sum_a w_e[a] x_e[o + a - p_e]  +  sum_a w_o[a] x_o[o + a - p_o],
@@ -683,6 +815,46 @@ int dwconv1d(const void* x, int64_t x_pitch, const void* w, const float* scale, 
   auto xp = static_cast<const unsigned short*>(x);
   auto wp = static_cast<const unsigned short*>(w);
   auto yp = static_cast<unsigned short*>(y);
+  // short rows: one TMA tensor load per (channel, eight utterances) -- see dw_rows_kernel
+  {
+    static const int rows_on = getenv("V100_DW_ROWS") ? atoi(getenv("V100_DW_ROWS")) : 1;   // A/B runs
+    const int pl8 = (p + kDwPad) & ~kDwPad, s = (pl8 - p) - e1;
+    const int n_dt = (T_in + s + 255) / 256;
+    const bool last_half = 256 * (n_dt - 1) + 128 - s >= T_in;
+    const int need = 16 * (16 * n_dt - (last_half ? 8 : 0) + Q - 1);
+    if (rows_on && !force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7 && need <= 2 * kDwBoxT) {
+      const int n_boxes = need <= kDwBoxT ? 1 : 2;
+      CUtensorMap tm;
+      if (int e = make_tmap_rows(&tm, dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, x,
+                                 T_in, C, B, x_pitch * 2, kDwBoxT, kDwRowsPerWarp)) return e;
+      const size_t smem = size_t(kDwWarps) * n_boxes * kDwRowsPerWarp * kDwBoxT * 2;
+      dim3 grid(1, C / kDwWarps, (B + kDwRowsPerWarp - 1) / kDwRowsPerWarp);
+      const long long ypl = y_pitch;
+#define V100_ROWS(QQ, RL, DTT)                                                                                              \
+      do {                                                                                                                  \
+        auto kern = dw_rows_kernel<QQ, RL, DTT>;                                                                            \
+        V100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));                      \
+        V100_CUDA(launch_pdl(kern, grid, dim3(kDwWarps * 32), smem, stream, tm, wp, scale, shift, yp, ypl, B, C, T_in, k, n_boxes)); \
+      } while (0)
+#define V100_ROWS_Q(QQ)                                                                       \
+      do {                                                                                    \
+        if (dtype == DT_F16) { if (act == V100_ACT_RELU6) V100_ROWS(QQ, true, DT_F16); else V100_ROWS(QQ, false, DT_F16); } \
+        else { if (act == V100_ACT_RELU6) V100_ROWS(QQ, true, DT_BF16); else V100_ROWS(QQ, false, DT_BF16); }               \
+      } while (0)
+      switch (Q) {
+        case 1: V100_ROWS_Q(1); break;
+        case 2: V100_ROWS_Q(2); break;
+        case 3: V100_ROWS_Q(3); break;
+        case 4: V100_ROWS_Q(4); break;
+        case 5: V100_ROWS_Q(5); break;
+        case 6: V100_ROWS_Q(6); break;
+        default: V100_ROWS_Q(7); break;
+      }
+#undef V100_ROWS_Q
+#undef V100_ROWS
+      return 0;
+    }
+  }
   if (!force_simt && stride == 1 && (C % kDwWarps) == 0 && Q <= 7) {
     switch (Q) {
       case 1: launch_dw_mma<1>(x, x_pitch, w, scale, shift, y, y_pitch, B, C, T_in, k, act, dtype, stream); break;
