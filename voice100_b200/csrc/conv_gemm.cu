@@ -101,7 +101,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = WRES ? kStageK * 64 * 2 * (kBCols / 64) : kATileBytes + (kBCols / 64) * kBAtomBytes;
   static constexpr int kWCol0 = 2 * N_ACC * BLOCK_N;  // WRES: first TMEM column of the resident weights
   static constexpr int kStagingBytes = OUT_MODE == OUT_BF16 ? 4 * kChunkBytes : 0;
-  static constexpr int kBarBytes = 256;
+  // mbarriers: full/empty per stage, 2 + 2 for the accumulators, 2 per epilogue warp for the residual tiles, + the TMEM slot
+  static constexpr int kBarBytes = ((2 * STAGES + 4 + 2 * kEpiWarps) * 8 + 8 + 127) & ~127;
   static constexpr int kSmemBytes = 1024 + STAGES * kStageBytes + kStagingBytes + kBarBytes;
   static constexpr int kTmemCols = WRES ? 512 : 2 * N_ACC * BLOCK_N;
   static_assert(!WRES || (CG == 2 && BLOCK_N == 128 && N_ACC == 1), "WRES: CTA pairs, 128-column tiles");
