@@ -63,10 +63,13 @@ __device__ __forceinline__ int dw_map(int i) { return ((i >> 4) & 1) * kDwHalf +
 // a chunk straddling T is copied whole and its tail zeroed by `dw_fix_tail` afterwards.
 __device__ __forceinline__ void dw_stage_row(unsigned short* xs, const unsigned short* xrow, int tcA, int T, int lane,
                                              int n_chunks) {
-  for (int v = lane; v < n_chunks; v += 32) {
-    const int t = tcA + v * 8;
+  // chunk v = lane + 32 i: t = t_lane + 256 i and dw_map(8 v) = d_lane + 128 i (block parity = bit 1 of the lane, block
+  // pair = 8 i + lane / 4, half block = lane & 1), so the loop is two adds per copy instead of the full index arithmetic
+  int t = tcA + 8 * lane;
+  unsigned short* dst = xs + ((lane >> 1) & 1) * kDwHalf + ((lane >> 2) << 4) + 8 * (lane & 1);
+  for (int v = lane; v < n_chunks; v += 32, t += 256, dst += 128) {
     const bool ok = t >= 0 && t < T;
-    cp_async_16(xs + dw_map(v * 8), xrow + (ok ? t : 0), ok);
+    cp_async_16(dst, xrow + (ok ? t : 0), ok);
   }
   cp_async_commit();
 }
@@ -577,14 +580,18 @@ dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const 
   // issued and consumed back to back the kernel sat at 0.44 of the HBM roofline waiting on them.
   constexpr int kS2Vec = NV;   // 16-byte loads per lane and row: 11 covers a full 1024-output chunk, 7 three double tiles
   uint4 pre[kS2Vec];
+  // Load i of a lane is vector v = 32 i + lane: x index t = t_lane + 256 i, staged word d = d_lane + 64 i (dw_map(4 v) with
+  // the lane part taken out: block parity = bit 2 of the lane, block pair = 4 i + lane / 8, word in block = lane & 3), so the
+  // loop below is immediate offsets from two per-lane constants (the generic form cost ~25 integer instructions per load).
+  const int t_lane = 2 * iA + 8 * lane;
+  const int d_lane = ((lane >> 2) & 1) * kDwHalf + ((lane >> 3) << 4) + 4 * (lane & 3);
   auto load_row = [&](int r) {
-    const unsigned short* xrow = x + (static_cast<long long>(b0 + r) * C + c) * x_pitch;
+    const unsigned short* xrow = x + (static_cast<long long>(b0 + r) * C + c) * x_pitch + t_lane;
 #pragma unroll
     for (int i = 0; i < kS2Vec; ++i) {
-      const int v = i * 32 + lane;
-      const int t = 2 * iA + 8 * v;                                 // x index of the first sample (a multiple of 8)
+      const int t = t_lane + 256 * i;                               // x index of the first sample (a multiple of 8)
       pre[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (v < n_vec && t >= 0 && t < T_in) pre[i] = __ldg(reinterpret_cast<const uint4*>(xrow + t));
+      if (32 * i + lane < n_vec && t >= 0 && t < T_in) pre[i] = __ldg(reinterpret_cast<const uint4*>(xrow + 256 * i));
     }
   };
   load_row(0);
@@ -592,21 +599,21 @@ dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const 
     // ---- stage: 8 consecutive samples -> 4 even-phase + 4 odd-phase samples ----
 #pragma unroll
     for (int i = 0; i < kS2Vec; ++i) {
-      const int v = i * 32 + lane;
-      if (v < n_vec) {
-        const int t = 2 * iA + 8 * v;
+      if (32 * i + lane < n_vec) {
         uint4 val = pre[i];
-        if (t < T_in && t + 8 > T_in) {
+        const int nvalid = T_in - (t_lane + 256 * i);               // samples of this vector inside the clip
+        if (nvalid > 0 && nvalid < 8) {                             // the one vector that straddles the end of the clip
           uint32_t* u = reinterpret_cast<uint32_t*>(&val);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (t + j >= T_in) u[j >> 1] &= (j & 1) ? 0x0000FFFFu : 0xFFFF0000u;
+          for (int wd = 0; wd < 4; ++wd) {
+            const int cnt = nvalid - 2 * wd;
+            u[wd] &= cnt >= 2 ? 0xFFFFFFFFu : (cnt == 1 ? 0x0000FFFFu : 0u);
+          }
         }
         const uint2 ev = make_uint2(__byte_perm(val.x, val.y, 0x5410), __byte_perm(val.z, val.w, 0x5410));
         const uint2 od = make_uint2(__byte_perm(val.x, val.y, 0x7632), __byte_perm(val.z, val.w, 0x7632));
-        const int d = dw_map(4 * v);                                // phase samples 4v .. 4v+3: one 8-byte word
-        *reinterpret_cast<uint2*>(xs_e + d) = ev;
-        *reinterpret_cast<uint2*>(xs_o + d) = od;
+        *reinterpret_cast<uint2*>(xs_e + d_lane + 64 * i) = ev;     // phase samples 4v .. 4v+3: one 8-byte word
+        *reinterpret_cast<uint2*>(xs_o + d_lane + 64 * i) = od;
       }
     }
     __syncwarp();
@@ -622,14 +629,10 @@ dw_s2_mma_kernel(const unsigned short* __restrict__ x, long long x_pitch, const 
       const float lo1 = even ? acc[1] : r1, hi1 = even ? r1 : acc[3];
       const uint32_t o0 = relu6 ? pack2_relu6<DT>(lo0, hi0) : pack2<DT>(lo0, hi0);
       const uint32_t o1 = relu6 ? pack2_relu6<DT>(lo1, hi1) : pack2<DT>(lo1, hi1);
-      if (posq >= 0 && posq < len) {
-        if (posq + 1 < len) *reinterpret_cast<uint32_t*>(yq) = o0;
-        else *yq = static_cast<unsigned short>(o0 & 0xFFFFu);     // (the row may end on an even column inside the pitch)
-      }
-      if (posq + 32 >= 0 && posq + 32 < len) {
-        if (posq + 33 < len) *reinterpret_cast<uint32_t*>(yq + 32) = o1;
-        else yq[32] = static_cast<unsigned short>(o1 & 0xFFFFu);
-      }
+      // (a pair that starts on the row's last column also writes the pitch padding next to it: posq is even, so that
+      //  column exists whenever the row length is odd -- the pitch is a multiple of 8)
+      if (posq >= 0 && posq < len) *reinterpret_cast<uint32_t*>(yq) = o0;
+      if (posq + 32 >= 0 && posq + 32 < len) *reinterpret_cast<uint32_t*>(yq + 32) = o1;
     };
 #pragma unroll 1
     for (int d = 0; d < n_dt; ++d) {
