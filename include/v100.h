@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define V100_ABI_VERSION 7
+#define V100_ABI_VERSION 8
 
 #define V100_E_INVALID   (-1)   /* bad argument (null pointer, misaligned pitch, size <= 0)   */
 #define V100_E_UNSUPPORTED (-2) /* shape outside what the kernels implement                   */
@@ -76,6 +76,19 @@ int v100_logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64
                 const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off,
                 const float* fb_w, int fb_nnz, float log_offset,
                 void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out, void* stream);
+
+/*
+ * The same front end for any other MelSpectrogramAudioTransform configuration (the reference's constructor takes
+ * sample_rate, n_fft, win_length, hop_length, n_mels -- data_modules.py:263-281 -- although its code only ever builds
+ * 512 / 400 / 160 / 64, which v100_logmel serves): n_fft a power of two in [8, 2048], 0 < win_length <= n_fft,
+ * hop_length > 0, any sparse filter bank with n_mels filters.  Outputs as v100_logmel with 64 replaced by n_mels and
+ * 160 by hop_length; NCW pitches are not constrained.  A plain kernel (one CTA per frame), not a tuned one.
+ */
+int v100_logmel_generic(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
+                        int n_fft, int win_length, int hop_length, int n_mels,
+                        const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off, const float* fb_w,
+                        float log_offset, void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out,
+                        void* stream);
 
 /*
  * fp32 [B][T][C] features -> 16-bit NCW [B][C][pitch].  Replaces the transpose at the top of

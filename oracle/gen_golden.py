@@ -308,6 +308,25 @@ def gen_align_edges(seed=91):
     print("align_edges", len(cases), "errors", sum(isinstance(c["out"], str) for c in cases))
 
 
+GENERIC_MEL_CONFIGS = ((16000, 256, 200, 80, 40), (22050, 1024, 800, 256, 80), (8000, 64, 64, 16, 13), (16000, 512, 320, 100, 64))
+
+
+def gen_logmel_generic():
+    """MelSpectrogramAudioTransform with constructor arguments other than the 512 / 400 / 160 / 64 the reference's code
+    builds (voice100/data_modules.py:263-281 takes all of them): log-mel features of a noise and a harmonic clip."""
+    out = {}
+    w_noise = torch.from_numpy(synth.noise_waveform(1, 6000, seed=111))[0]
+    w_harm = torch.from_numpy(synth.harmonic_waveform(1, 4321, seed=112))[0]
+    for i, (sr, n_fft, win, hop, n_mels) in enumerate(GENERIC_MEL_CONFIGS):
+        tr = MelSpectrogramAudioTransform(sample_rate=sr, n_fft=n_fft, win_length=win, hop_length=hop, n_mels=n_mels)
+        with torch.no_grad():
+            for name, w in (("noise", w_noise), ("harm", w_harm)):
+                out[f"c{i}_{name}"] = torch.log(tr.melspec(w).T + tr.log_offset).numpy()
+        out[f"c{i}_cfg"] = np.asarray([sr, n_fft, win, hop, n_mels])
+    np.savez_compressed(os.path.join(OUT, "logmel_generic.npz"), **out)
+    print("logmel_generic", {k: v.shape for k, v in out.items() if not k.endswith("cfg")})
+
+
 def gen_maskaudio(seed=101):
     """BatchSpectrogramAugumentation.maskaudio (voice100/audio.py:106-108) on a ragged log-mel-like batch: values over the
     whole range the front end produces (BLANK_AUDIO .. +12), lengths 0 / 1 / interior / full."""
@@ -349,3 +368,4 @@ if __name__ == "__main__":
     gen_tokenizer()
     gen_align_edges()
     gen_maskaudio()
+    gen_logmel_generic()

@@ -35,7 +35,7 @@ def test_library_loads_and_exports_header_symbols():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (v100_\w+)", out))
     assert exported == set(funcs), exported ^ set(funcs)
-    assert _lib.lib().v100_abi_version() == _lib.ABI_VERSION == 7
+    assert _lib.lib().v100_abi_version() == _lib.ABI_VERSION == 8
 
 
 def test_plain_c_consumer_compiles_links_and_fails_loudly(tmp_path):

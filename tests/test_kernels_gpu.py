@@ -551,6 +551,49 @@ def test_ctc_best_path_matches_oracle_bit_exact():
     assert torch.isnan(s4[1]) and (h4[1] == -1).all() and float(s4[0]) == float(score[0]) and torch.equal(h4[0], hist[0])
 
 
+def test_logmel_generic_configs_match_reference_golden():
+    """MelSpectrogramAudioTransform with constructor arguments other than 512 / 400 / 160 / 64 (v100_logmel_generic) against
+    the reference class built with the same arguments (tests/golden/logmel_generic.npz), single clips and a ragged batch,
+    fp32 and int16 PCM input.  Same tolerances as the tuned kernel: 2e-4 absolute on the log-mel values of the noise clip,
+    3e-3 on the clean harmonic clip (fp32 FFT round-off in its near-silent bins)."""
+    import voice100_b200 as v
+    from helpers import golden
+    g = golden("logmel_generic")
+    clips = {"noise": synth.noise_waveform(1, 6000, seed=111)[0], "harm": synth.harmonic_waveform(1, 4321, seed=112)[0]}
+    i = 0
+    while f"c{i}_cfg" in g.files:
+        sr, n_fft, win, hop, n_mels = [int(x) for x in g[f"c{i}_cfg"]]
+        tr = v.MelSpectrogramAudioTransform(sr, n_fft, win, hop, n_mels).to(DEV)
+        assert tr.audio_size == n_mels
+        for name, w in clips.items():
+            ref = g[f"c{i}_{name}"]
+            got = tr(torch.from_numpy(w).to(DEV)).cpu().numpy()
+            assert got.shape == ref.shape
+            err = float(np.abs(got - ref).max())
+            # (fp32 FFT round-off only matters in the near-silent bins of the clean harmonic clip, as for the tuned kernel)
+            assert err < (2e-4 if name == "noise" else 3e-3), (i, name, err)
+        # ragged batch: [noise, harm padded], NTC fp32 and NCW bf16, frames past a clip's own length are BLANK_AUDIO
+        L = 6000
+        wav = np.zeros((2, L), np.float32)
+        wav[0] = clips["noise"]; wav[1, :4321] = clips["harm"]
+        lens = torch.tensor([6000, 4321], dtype=torch.int32)
+        audio, audio_len = tr.logmel_batch(torch.from_numpy(wav).to(DEV), lens.to(DEV))
+        assert audio_len.tolist() == [1 + 6000 // hop, 1 + 4321 // hop] and audio.shape == (2, 1 + L // hop, n_mels)
+        n1 = 1 + 4321 // hop
+        assert np.abs(audio[1, :n1].cpu().numpy() - g[f"c{i}_harm"]).max() < 3e-3
+        assert bool((audio[1, n1:] == v.BLANK_AUDIO).all())
+        ncw, _ = tr.logmel_batch(torch.from_numpy(wav).to(DEV), lens.to(DEV), ncw_dtype=torch.bfloat16)
+        assert ncw.C == n_mels and float((ncw.valid().float().transpose(1, 2) - audio).abs().max()) < 0.07   # bf16 rounding at |x| <= 16
+        pcm = torch.from_numpy(np.round(wav * 32767.0).astype(np.int16))
+        a16, _ = tr.logmel_batch(pcm.to(DEV), lens.to(DEV))
+        a32, _ = tr.logmel_batch((pcm.float() / 32768.0).to(DEV), lens.to(DEV))
+        assert float((a16 - a32).abs().max()) < 1e-4
+        i += 1
+    assert i == 4
+    with pytest.raises(v.V100Error):
+        v.MelSpectrogramAudioTransform(16000, 500, 400, 160, 64)      # n_fft must be a power of two
+
+
 def test_maskaudio_matches_reference_golden_and_oracle():
     """v100_maskaudio vs the reference method's own output (tests/golden/maskaudio.npz) and vs the oracle on a larger ragged
     batch.  Tolerance 2e-6 absolute on valid frames (expf -> logf round trip, values in [-14.8, 12]); padded frames and

@@ -298,3 +298,21 @@ def test_maskaudio_matches_reference_golden():
     assert np.array_equal(out.numpy(), g["out"])                      # same ATen ops in the same order: bit-identical
     for b, n in enumerate(g["audio_len"]):
         assert np.all(g["out"][b, int(n):] == np.float32(orc.BLANK_AUDIO))
+
+
+def test_logmel_generic_configs_match_reference():
+    """The oracle front end with constructor arguments other than 512 / 400 / 160 / 64, against the reference class built with
+    the same arguments (oracle/gen_golden.py:gen_logmel_generic)."""
+    g = golden("logmel_generic")
+    clips = {"noise": synth.noise_waveform(1, 6000, seed=111)[0], "harm": synth.harmonic_waveform(1, 4321, seed=112)[0]}
+    i = 0
+    while f"c{i}_cfg" in g.files:
+        sr, n_fft, win, hop, n_mels = [int(x) for x in g[f"c{i}_cfg"]]
+        for name, w in clips.items():
+            got = orc.logmel_clip(torch.from_numpy(w), sample_rate=sr, n_fft=n_fft, win_length=win, hop_length=hop,
+                                  n_mels=n_mels).numpy()
+            ref = g[f"c{i}_{name}"]
+            assert got.shape == ref.shape == (1 + len(w) // hop, n_mels)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5, err_msg=f"config {i} {name}")
+        i += 1
+    assert i == 4

@@ -16,6 +16,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "v100_abi_version": [],
     "v100_logmel": [_p, _i, _p, _i, _l, _i, _p, _p, _p, _p, _i, _f, _p, _i, _l, _i, _p, _p],
+    "v100_logmel_generic": [_p, _i, _p, _i, _l, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _i, _l, _i, _p, _p],
     "v100_ntc_f32_to_ncw16": [_p, _p, _i, _i, _i, _l, _i, _p],
     "v100_ncw_f32_to_16": [_p, _p, _l, _i, _i, _i, _i, _p],
     "v100_ncw_16_to_f32": [_p, _l, _p, _i, _i, _i, _i, _p],
@@ -41,7 +42,7 @@ SIGNATURES = {
     "v100_lstm_layer": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
 }
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 _lib = None
 
 

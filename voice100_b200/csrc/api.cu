@@ -113,6 +113,14 @@ int v100_logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64
                 out_pitch, out_mode, frames_out, STREAM(stream));
 }
 
+int v100_logmel_generic(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max,
+                        int n_fft, int win_length, int hop_length, int n_mels, const int32_t* fb_start,
+                        const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, float log_offset, void* out,
+                        int T, int64_t out_pitch, int out_mode, int32_t* frames_out, void* stream) {
+  return logmel_generic(wav, wav_dtype, len, B, wav_pitch, L_max, n_fft, win_length, hop_length, n_mels, fb_start, fb_count,
+                        fb_off, fb_w, log_offset, out, T, out_pitch, out_mode, frames_out, STREAM(stream));
+}
+
 int v100_ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, void* stream) {
   return ntc_f32_to_ncw16(x, y, B, T, C, y_pitch, dtype, STREAM(stream));
 }

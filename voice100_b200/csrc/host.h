@@ -68,6 +68,10 @@ int logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wa
            const int32_t* fb_start, const int32_t* fb_count, const int32_t* fb_off, const float* fb_w, int fb_nnz,
            float log_offset, void* out, int T, int64_t out_pitch, int out_mode, int32_t* frames_out,
            cudaStream_t stream);
+int logmel_generic(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max, int n_fft,
+                   int win_length, int hop_length, int n_mels, const int32_t* fb_start, const int32_t* fb_count,
+                   const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T, int64_t out_pitch,
+                   int out_mode, int32_t* frames_out, cudaStream_t stream);
 int ntc_f32_to_ncw16(const float* x, void* y, int B, int T, int C, int64_t y_pitch, int dtype, cudaStream_t stream);
 int ncw_f32_to_16(const float* x, void* y, int64_t y_pitch, int B, int C, int T, int dtype, cudaStream_t stream);
 int ncw_16_to_f32(const void* x, int64_t x_pitch, float* y, int B, int C, int T, int dtype, cudaStream_t stream);

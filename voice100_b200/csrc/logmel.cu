@@ -324,4 +324,127 @@ int logmel(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wa
   return wav_dtype == V100_WAV_I16 ? launch_logmel<16, true>(p, stream) : launch_logmel<16, false>(p, stream);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Any other MelSpectrogramAudioTransform configuration (the reference's constructor is general, data_modules.py:263-281,
+// although its code only ever builds 512 / 400 / 160 / 64): n_fft a power of two up to 2048, any win_length <= n_fft,
+// any hop, any filter bank.  Not a tuned kernel -- one CTA per frame, an in-place radix-2 FFT in shared memory --
+// but the same arithmetic contract as logmel_kernel: reflect padding at the clip's own ends, periodic Hann window
+// centred in the frame, |rFFT|^2, sparse mel filters, log(. + offset), BLANK_AUDIO past the clip's own frames.
+// ------------------------------------------------------------------------------------------------------------------
+struct MelGenParams {
+  const void* wav;
+  const int32_t* len;
+  long long wav_pitch;
+  int L_max, n_fft, log2_fft, win, hop, n_mels;
+  const int32_t *fb_start, *fb_count, *fb_off;
+  const float* fb_w;
+  float log_offset;
+  void* out;
+  int T;
+  long long out_pitch;
+  int out_mode;
+  int32_t* frames_out;
+};
+
+template <bool I16>
+__global__ void __launch_bounds__(128)
+logmel_generic_kernel(const MelGenParams p) {
+  __shared__ float2 z[2048];
+  __shared__ float P[1025];
+  const int b = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  const int L = min(max(__ldg(p.len + b), 0), p.L_max);
+  const int n_frames = L > 0 ? 1 + L / p.hop : 0;
+  if (p.frames_out != nullptr && t == 0 && tid == 0) p.frames_out[b] = 1 + L / p.hop;
+  const bool valid = t < n_frames;
+  const int N = p.n_fft;
+  if (valid) {
+    const float* xf = static_cast<const float*>(p.wav) + static_cast<long long>(b) * p.wav_pitch;
+    const short* xi = static_cast<const short*>(p.wav) + static_cast<long long>(b) * p.wav_pitch;
+    const int base = p.hop * t - N / 2, left = (N - p.win) / 2;
+    for (int n = tid; n < N; n += 128) {
+      const int m = n - left;
+      float v = 0.0f;
+      if (m >= 0 && m < p.win) {
+        const float w = 0.5f - 0.5f * cospif(float(2 * m) / float(p.win));     // periodic Hann(win)
+        int i = base + n;
+        i = i < 0 ? -i : i;
+        i = i >= L ? 2 * (L - 1) - i : i;
+        i = min(max(i, 0), L - 1);
+        v = (I16 ? float(__ldg(xi + i)) * (1.0f / 32768.0f) : __ldg(xf + i)) * w;
+      }
+      z[__brev(unsigned(n)) >> (32 - p.log2_fft)] = make_float2(v, 0.0f);
+    }
+    __syncthreads();
+    for (int len2 = 2; len2 <= N; len2 <<= 1) {
+      const int half = len2 >> 1;
+      for (int k = tid; k < N / 2; k += 128) {
+        const int j = k & (half - 1), i0 = ((k - j) << 1) + j, i1 = i0 + half;
+        float sn, cs;
+        sincospif(-float(2 * j) / float(len2), &sn, &cs);
+        const float2 a = z[i0], c = z[i1];
+        const float2 wc = make_float2(c.x * cs - c.y * sn, c.x * sn + c.y * cs);
+        z[i0] = make_float2(a.x + wc.x, a.y + wc.y);
+        z[i1] = make_float2(a.x - wc.x, a.y - wc.y);
+      }
+      __syncthreads();
+    }
+    for (int k = tid; k <= N / 2; k += 128) P[k] = z[k].x * z[k].x + z[k].y * z[k].y;
+    __syncthreads();
+  }
+  const float blank = p.out_mode == V100_MEL_POWER_F32_NCW ? 0.0f : logf(p.log_offset);
+  for (int m = tid; m < p.n_mels; m += 128) {
+    float val = blank;
+    if (valid) {
+      const int s0 = __ldg(p.fb_start + m), cnt = __ldg(p.fb_count + m);
+      const float* w = p.fb_w + __ldg(p.fb_off + m);
+      float acc = 0.0f;
+      for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(w + i), P[s0 + i], acc);
+      val = p.out_mode == V100_MEL_POWER_F32_NCW ? acc : logf(acc + p.log_offset);
+    }
+    if (p.out_mode == V100_MEL_LOG_F32_NTC) {
+      static_cast<float*>(p.out)[(static_cast<long long>(b) * p.T + t) * p.n_mels + m] = val;
+    } else {
+      const long long o = (static_cast<long long>(b) * p.n_mels + m) * p.out_pitch + t;
+      if (p.out_mode == V100_MEL_POWER_F32_NCW) static_cast<float*>(p.out)[o] = val;
+      else if (p.out_mode == V100_MEL_LOG_F16_NCW) static_cast<unsigned short*>(p.out)[o] = f2h<DT_F16>(val);
+      else static_cast<unsigned short*>(p.out)[o] = f2h<DT_BF16>(val);
+    }
+  }
+}
+
+int logmel_generic(const void* wav, int wav_dtype, const int32_t* len, int B, int64_t wav_pitch, int L_max, int n_fft,
+                   int win_length, int hop_length, int n_mels, const int32_t* fb_start, const int32_t* fb_count,
+                   const int32_t* fb_off, const float* fb_w, float log_offset, void* out, int T, int64_t out_pitch,
+                   int out_mode, int32_t* frames_out, cudaStream_t stream) {
+  if (wav == nullptr || len == nullptr || out == nullptr || fb_start == nullptr || fb_count == nullptr ||
+      fb_off == nullptr || fb_w == nullptr)
+    return fail(V100_E_INVALID, "logmel_generic: null pointer");
+  if (wav_dtype != V100_WAV_F32 && wav_dtype != V100_WAV_I16) return fail(V100_E_INVALID, "logmel_generic: bad wav_dtype");
+  if (B <= 0 || B > 65535 || T <= 0) return fail(V100_E_INVALID, "logmel_generic: bad B=%d or T=%d", B, T);
+  if (L_max < 0 || wav_pitch < L_max) return fail(V100_E_INVALID, "logmel_generic: wav_pitch %lld < L_max %d", (long long)wav_pitch, L_max);
+  int log2_fft = 0;
+  while ((1 << log2_fft) < n_fft) ++log2_fft;
+  if (n_fft < 8 || n_fft > 2048 || (1 << log2_fft) != n_fft)
+    return fail(V100_E_UNSUPPORTED, "logmel_generic: n_fft=%d must be a power of two in [8, 2048]", n_fft);
+  if (win_length <= 0 || win_length > n_fft || hop_length <= 0 || n_mels <= 0)
+    return fail(V100_E_INVALID, "logmel_generic: need 0 < win_length <= n_fft, hop_length > 0, n_mels > 0");
+  if (!(log_offset > 0.0f) && out_mode != V100_MEL_POWER_F32_NCW) return fail(V100_E_INVALID, "logmel_generic: log_offset must be positive");
+  if (out_mode == V100_MEL_LOG_BF16_NCW || out_mode == V100_MEL_LOG_F16_NCW || out_mode == V100_MEL_POWER_F32_NCW) {
+    if (out_pitch < T) return fail(V100_E_INVALID, "logmel_generic: NCW pitch must be >= T");
+  } else if (out_mode != V100_MEL_LOG_F32_NTC) {
+    return fail(V100_E_INVALID, "logmel_generic: unknown out_mode %d", out_mode);
+  }
+  MelGenParams p{};
+  p.wav = wav; p.len = len; p.wav_pitch = wav_pitch; p.L_max = L_max;
+  p.n_fft = n_fft; p.log2_fft = log2_fft; p.win = win_length; p.hop = hop_length; p.n_mels = n_mels;
+  p.fb_start = fb_start; p.fb_count = fb_count; p.fb_off = fb_off; p.fb_w = fb_w;
+  p.log_offset = log_offset; p.out = out; p.T = T; p.out_pitch = out_pitch; p.out_mode = out_mode; p.frames_out = frames_out;
+  const long long cols = out_mode == V100_MEL_LOG_F32_NTC ? T : out_pitch;   // NCW rows are written to the pitch
+  dim3 grid((unsigned)cols, B);
+  if (wav_dtype == V100_WAV_I16) logmel_generic_kernel<true><<<grid, 128, 0, stream>>>(p);
+  else logmel_generic_kernel<false><<<grid, 128, 0, stream>>>(p);
+  V100_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace v100

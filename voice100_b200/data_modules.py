@@ -58,9 +58,12 @@ class MelSpectrogramAudioTransform(nn.Module):
     def __init__(self, sample_rate: int = 16000, n_fft: int = 512, win_length: int = 400, hop_length: int = 160,
                  n_mels: int = MELSPEC_DIM, log_offset: float = LOG_OFFSET) -> None:
         super().__init__()
-        if (n_fft, win_length, hop_length, n_mels) != (512, 400, 160, 64):
-            raise V100Error("the fused log-mel kernel is specialised for n_fft=512, win_length=400, hop_length=160, "
-                            "n_mels=64 (the only configuration the reference uses, data_modules.py:266-269)")
+        # (512, 400, 160, 64) -- the only configuration the reference ever builds, data_modules.py:266-269 -- runs the tuned
+        # kernel; any other one the generic kernel (v100_logmel_generic)
+        if n_fft < 8 or n_fft > 2048 or (n_fft & (n_fft - 1)) != 0:
+            raise V100Error(f"n_fft={n_fft}: powers of two in [8, 2048] are supported")
+        if not (0 < win_length <= n_fft) or hop_length <= 0 or n_mels <= 0:
+            raise V100Error("need 0 < win_length <= n_fft, hop_length > 0, n_mels > 0")
         self.sample_rate, self.n_fft, self.win_length, self.hop_length = sample_rate, n_fft, win_length, hop_length
         self.n_mels, self.log_offset = n_mels, log_offset
         fb = mel_filterbank(sample_rate, n_fft, n_mels)
@@ -70,6 +73,10 @@ class MelSpectrogramAudioTransform(nn.Module):
     @property
     def audio_size(self) -> int:
         return self.n_mels
+
+    @property
+    def _config(self):
+        return (self.n_fft, self.win_length, self.hop_length, self.n_mels)
 
     def _fb(self, device):
         if self.fb_w.device != device:
@@ -90,7 +97,7 @@ class MelSpectrogramAudioTransform(nn.Module):
         wav = self._samples(waveform.reshape(-1, L))
         lengths = torch.full((wav.shape[0],), L, dtype=torch.int32, device=wav.device)
         T = self.num_frames(L)
-        out, _ = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, K.MEL_POWER_F32_NCW)
+        out, _ = K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, K.MEL_POWER_F32_NCW, self._config)
         return out.valid().reshape(*lead, self.n_mels, T)
 
     @staticmethod
@@ -119,7 +126,7 @@ class MelSpectrogramAudioTransform(nn.Module):
         lengths = lengths.to(device=wav.device, dtype=torch.int32).contiguous()
         T = self.num_frames(wav.shape[1])
         mode = K.MEL_LOG_F32_NTC if ncw_dtype is None else (K.MEL_LOG_F16_NCW if K.dt(ncw_dtype) == 1 else K.MEL_LOG_BF16_NCW)
-        return K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, mode)
+        return K.logmel(wav, lengths, self._fb(wav.device), self.log_offset, T, mode, self._config)
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
         """One clip `[L] -> [T, 64]` log-mel features.  (The reference's forward takes a file path and does

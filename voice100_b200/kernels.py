@@ -89,9 +89,12 @@ def _cuda(t: torch.Tensor, dtype=None):
     return t
 
 
-def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: int, mode: int):
+def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: int, mode: int, config=None):
     """wav fp32 or int16 PCM [B, L]; lengths int32 [B] (device); fb = (start, count, off, w) device tensors.
-    -> (features, audio_len int32 [B] = 1 + len // 160, written by the same kernel)."""
+    -> (features, audio_len int32 [B] = 1 + len // hop, written by the same kernel).
+    `config` = (n_fft, win_length, hop_length, n_mels); None or (512, 400, 160, 64) runs the tuned kernel, anything else
+    the generic one (v100_logmel_generic)."""
+    nm = 64 if config is None else int(config[3])
     _cuda(lengths, torch.int32)
     if wav.dtype not in (torch.float32, torch.int16):
         raise _lib.V100Error(f"waveforms must be float32 or int16 PCM, got {wav.dtype}")
@@ -99,15 +102,21 @@ def logmel(wav: torch.Tensor, lengths: torch.Tensor, fb, log_offset: float, T: i
     _same_device(wav, lengths, fb[3])
     B = wav.shape[0]
     if mode in (MEL_LOG_BF16_NCW, MEL_LOG_F16_NCW):
-        out = empty_ncw(B, 64, T, wav.device, torch.bfloat16 if mode == MEL_LOG_BF16_NCW else torch.float16)
+        out = empty_ncw(B, nm, T, wav.device, torch.bfloat16 if mode == MEL_LOG_BF16_NCW else torch.float16)
         optr, pitch = out.data.data_ptr(), out.pitch
     elif mode == MEL_POWER_F32_NCW:
-        out = Ncw(torch.empty((B, 64, pitch_of(T, 4)), device=wav.device, dtype=torch.float32), T)
+        out = Ncw(torch.empty((B, nm, pitch_of(T, 4)), device=wav.device, dtype=torch.float32), T)
         optr, pitch = out.data.data_ptr(), out.pitch
     else:
-        out = torch.empty((B, T, 64), device=wav.device, dtype=torch.float32)
-        optr, pitch = out.data_ptr(), 64
+        out = torch.empty((B, T, nm), device=wav.device, dtype=torch.float32)
+        optr, pitch = out.data_ptr(), nm
     frames = torch.empty((B,), device=wav.device, dtype=torch.int32)
+    if config is not None and tuple(int(c) for c in config) != (512, 400, 160, 64):
+        n_fft, win, hop, _ = (int(c) for c in config)
+        _call(wav, "v100_logmel_generic", wav.data_ptr(), 1 if wav.dtype == torch.int16 else 0, lengths.data_ptr(), B,
+              wav.stride(0), wav.shape[1], n_fft, win, hop, nm, fb[0].data_ptr(), fb[1].data_ptr(), fb[2].data_ptr(),
+              fb[3].data_ptr(), float(log_offset), optr, T, pitch, mode, frames.data_ptr())
+        return out, frames
     _call(wav, "v100_logmel", wav.data_ptr(), 1 if wav.dtype == torch.int16 else 0, lengths.data_ptr(), B,
           wav.stride(0), wav.shape[1], fb[0].data_ptr(), fb[1].data_ptr(), fb[2].data_ptr(), fb[3].data_ptr(),
           fb[3].numel(), float(log_offset), optr, T, pitch, mode, frames.data_ptr())
